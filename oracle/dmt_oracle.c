@@ -1,0 +1,899 @@
+/*
+ * dmt_oracle.c — CPU ORACLE (scalar FP64 C99).  TEST INFRASTRUCTURE ONLY — see dmt_oracle.h.
+ * PARITY UNPINNED (no reference tests / golden vectors exist; Julia absent) — pinned by analytic KATs only.
+ *
+ * Restates, per function, either reference code under /root/reference/src (cited) or the published
+ * guided-proposal equations as summarised in SURVEY.md Appendix A (cited as "A.n").
+ * Dense row-major d x d matrices, one heap array per interval, pointer swaps on accept — i.e. the
+ * reference's object graph, on purpose unlike the device library's tiled SoA.
+ */
+#define _GNU_SOURCE
+#include "dmt_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define D2 (ORC_MAXD * ORC_MAXD)
+
+/* ======================================================================== models (Appendix B) */
+
+int orc_model_dims(int model, int *d, int *dw, int *npar, int *constdiff) {
+    int D, W, P, C = 1;
+    switch (model) {
+    case ORC_FHN:    D = 2; W = 1; P = 5;  break;
+    case ORC_LV:     D = 2; W = 2; P = 6;  break;
+    case ORC_LORENZ: D = 3; W = 3; P = 4;  break;
+    case ORC_PROK:   D = 4; W = 4; P = 9;  C = 0; break;
+    case ORC_JR:     D = 6; W = 1; P = 10; break;
+    case ORC_OU2:    D = 2; W = 2; P = 8;  break;
+    default: return -1;
+    }
+    if (d) *d = D;
+    if (dw) *dw = W;
+    if (npar) *npar = P;
+    if (constdiff) *constdiff = C;
+    return 0;
+}
+
+static double jr_sigm(const double *th, double v) { /* nu_max / (1 + exp(r (v0 - v))) */
+    return th[5] / (1.0 + exp(th[7] * (th[6] - v)));
+}
+static double jr_dsigm(const double *th, double v) {
+    double s = jr_sigm(th, v);
+    return th[7] * s * (1.0 - s / th[5]);
+}
+
+/* Prokaryotic autoregulation: 8 reactions on (RNA, P, P2, DNA); stoichiometry S (4 x 8). */
+static const double PROK_S[4][8] = {
+    { 0, 0, 1, 0,  0,  0, -1,  0},
+    { 0, 0, 0, 1, -2,  2,  0, -1},
+    {-1, 1, 0, 0,  1, -1,  0,  0},
+    {-1, 1, 0, 0,  0,  0,  0,  0}};
+static void prok_hazards(const double *c, const double *x, double *h) {
+    h[0] = c[0] * x[3] * x[2];
+    h[1] = c[1] * (c[8] - x[3]);
+    h[2] = c[2] * x[3];
+    h[3] = c[3] * x[0];
+    h[4] = c[4] * x[1] * (x[1] - 1.0) * 0.5;
+    h[5] = c[5] * x[2];
+    h[6] = c[6] * x[0];
+    h[7] = c[7] * x[1];
+}
+static void prok_a(const double *c, const double *x, double *a /*4x4*/) {
+    double h[8];
+    prok_hazards(c, x, h);
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) {
+            double s = 0;
+            for (int r = 0; r < 8; r++) s += PROK_S[i][r] * h[r] * PROK_S[j][r];
+            a[i * 4 + j] = s;
+        }
+}
+
+void orc_drift(int model, const double *th, const double *x, double *b) {
+    switch (model) {
+    case ORC_FHN: /* (eps, s, gamma, beta, sigma) */
+        b[0] = (x[0] - x[1] - x[0] * x[0] * x[0] + th[1]) / th[0];
+        b[1] = th[2] * x[0] - x[1] + th[3];
+        break;
+    case ORC_LV: /* (alpha, beta, gamma, delta, s1, s2) */
+        b[0] = th[0] * x[0] - th[1] * x[0] * x[1];
+        b[1] = th[3] * x[0] * x[1] - th[2] * x[1];
+        break;
+    case ORC_LORENZ: /* (th1, th2, th3, sigma) */
+        b[0] = th[0] * (x[1] - x[0]);
+        b[1] = th[1] * x[0] - x[1] - x[0] * x[2];
+        b[2] = x[0] * x[1] - th[2] * x[2];
+        break;
+    case ORC_PROK: {
+        double h[8];
+        prok_hazards(th, x, h);
+        for (int i = 0; i < 4; i++) {
+            double s = 0;
+            for (int r = 0; r < 8; r++) s += PROK_S[i][r] * h[r];
+            b[i] = s;
+        }
+    } break;
+    case ORC_JR: { /* (A, a, B, b, C, numax, v0, r, mu, sigy); C1=C, C2=.8C, C3=C4=.25C */
+        double A = th[0], a = th[1], Bc = th[2], bb = th[3], C = th[4], mu = th[8];
+        double C1 = C, C2 = 0.8 * C, C3 = 0.25 * C, C4 = 0.25 * C;
+        b[0] = x[3];
+        b[1] = x[4];
+        b[2] = x[5];
+        b[3] = A * a * jr_sigm(th, x[1] - x[2]) - 2.0 * a * x[3] - a * a * x[0];
+        b[4] = A * a * (mu + C2 * jr_sigm(th, C1 * x[0])) - 2.0 * a * x[4] - a * a * x[1];
+        b[5] = Bc * bb * C4 * jr_sigm(th, C3 * x[0]) - 2.0 * bb * x[5] - bb * bb * x[2];
+    } break;
+    case ORC_OU2: /* (B11,B12,B21,B22, beta1,beta2, s1,s2) */
+        b[0] = th[0] * x[0] + th[1] * x[1] + th[4];
+        b[1] = th[2] * x[0] + th[3] * x[1] + th[5];
+        break;
+    }
+}
+
+static int chol_lower(const double *A, int n, double *Lo) { /* A = Lo Lo^T ; returns 0 on success */
+    memset(Lo, 0, sizeof(double) * n * n);
+    for (int j = 0; j < n; j++) {
+        double s = A[j * n + j];
+        for (int k = 0; k < j; k++) s -= Lo[j * n + k] * Lo[j * n + k];
+        if (!(s > 0.0)) return 1;
+        double l = sqrt(s);
+        Lo[j * n + j] = l;
+        for (int i = j + 1; i < n; i++) {
+            double t = A[i * n + j];
+            for (int k = 0; k < j; k++) t -= Lo[i * n + k] * Lo[j * n + k];
+            Lo[i * n + j] = t / l;
+        }
+    }
+    return 0;
+}
+
+void orc_sigma(int model, const double *th, const double *x, double *S) {
+    int d, dw;
+    orc_model_dims(model, &d, &dw, 0, 0);
+    memset(S, 0, sizeof(double) * d * dw);
+    switch (model) {
+    case ORC_FHN: S[1] = th[4]; break;
+    case ORC_LV: S[0] = th[4]; S[3] = th[5]; break;
+    case ORC_LORENZ: S[0] = S[4] = S[8] = th[3]; break;
+    case ORC_PROK: { /* sigma(x) := lower Cholesky factor of a(x) = S diag(h) S^T */
+        double a[16];
+        prok_a(th, x, a);
+        if (chol_lower(a, 4, S)) for (int i = 0; i < 16; i++) S[i] = NAN;
+    } break;
+    case ORC_JR: S[4] = th[9]; break;
+    case ORC_OU2: S[0] = th[6]; S[3] = th[7]; break;
+    }
+}
+
+void orc_jacobian(int model, const double *th, const double *x, double *J) {
+    int d;
+    orc_model_dims(model, &d, 0, 0, 0);
+    memset(J, 0, sizeof(double) * d * d);
+    switch (model) {
+    case ORC_FHN:
+        J[0] = (1.0 - 3.0 * x[0] * x[0]) / th[0]; J[1] = -1.0 / th[0];
+        J[2] = th[2];                              J[3] = -1.0;
+        break;
+    case ORC_LV:
+        J[0] = th[0] - th[1] * x[1]; J[1] = -th[1] * x[0];
+        J[2] = th[3] * x[1];         J[3] = th[3] * x[0] - th[2];
+        break;
+    case ORC_LORENZ:
+        J[0] = -th[0];        J[1] = th[0]; J[2] = 0;
+        J[3] = th[1] - x[2];  J[4] = -1.0;  J[5] = -x[0];
+        J[6] = x[1];          J[7] = x[0];  J[8] = -th[2];
+        break;
+    case ORC_PROK: { /* dh/dx then S * dh/dx */
+        double dh[8][4];
+        memset(dh, 0, sizeof dh);
+        const double *c = th;
+        dh[0][3] = c[0] * x[2]; dh[0][2] = c[0] * x[3];
+        dh[1][3] = -c[1];
+        dh[2][3] = c[2];
+        dh[3][0] = c[3];
+        dh[4][1] = c[4] * (2.0 * x[1] - 1.0) * 0.5;
+        dh[5][2] = c[5];
+        dh[6][0] = c[6];
+        dh[7][1] = c[7];
+        for (int i = 0; i < 4; i++)
+            for (int j = 0; j < 4; j++) {
+                double s = 0;
+                for (int r = 0; r < 8; r++) s += PROK_S[i][r] * dh[r][j];
+                J[i * 4 + j] = s;
+            }
+    } break;
+    case ORC_JR: {
+        double A = th[0], a = th[1], Bc = th[2], bb = th[3], C = th[4];
+        double C1 = C, C2 = 0.8 * C, C3 = 0.25 * C, C4 = 0.25 * C;
+        J[0 * 6 + 3] = 1; J[1 * 6 + 4] = 1; J[2 * 6 + 5] = 1;
+        double s12 = jr_dsigm(th, x[1] - x[2]);
+        J[3 * 6 + 0] = -a * a; J[3 * 6 + 1] = A * a * s12; J[3 * 6 + 2] = -A * a * s12; J[3 * 6 + 3] = -2 * a;
+        J[4 * 6 + 0] = A * a * C2 * C1 * jr_dsigm(th, C1 * x[0]); J[4 * 6 + 1] = -a * a; J[4 * 6 + 4] = -2 * a;
+        J[5 * 6 + 0] = Bc * bb * C4 * C3 * jr_dsigm(th, C3 * x[0]); J[5 * 6 + 2] = -bb * bb; J[5 * 6 + 5] = -2 * bb;
+    } break;
+    case ORC_OU2:
+        J[0] = th[0]; J[1] = th[1]; J[2] = th[2]; J[3] = th[3];
+        break;
+    }
+}
+
+int orc_bound_ok(int model, const double *th, const double *x) {
+    int d;
+    orc_model_dims(model, &d, 0, 0, 0);
+    for (int i = 0; i < d; i++)
+        if (!isfinite(x[i])) return 0;
+    switch (model) {
+    case ORC_LV: return x[0] > 0 && x[1] > 0;
+    case ORC_PROK: return x[0] > 0 && x[1] > 1.0 && x[2] > 0 && x[3] > 0 && x[3] < th[8];
+    default: return 1;
+    }
+}
+
+static void a_of(int model, const double *th, const double *x, int d, int dw, double *a) {
+    double S[D2];
+    orc_sigma(model, th, x, S);
+    for (int i = 0; i < d; i++)
+        for (int j = 0; j < d; j++) {
+            double s = 0;
+            for (int k = 0; k < dw; k++) s += S[i * dw + k] * S[j * dw + k];
+            a[i * d + j] = s;
+        }
+}
+
+void orc_linearise(int model, const double *th, const double *xbar, double *B, double *beta, double *at) {
+    int d, dw;
+    orc_model_dims(model, &d, &dw, 0, 0);
+    double b[ORC_MAXD];
+    orc_jacobian(model, th, xbar, B);
+    orc_drift(model, th, xbar, b);
+    for (int i = 0; i < d; i++) {
+        double s = b[i];
+        for (int j = 0; j < d; j++) s -= B[i * d + j] * xbar[j];
+        beta[i] = s;
+    }
+    a_of(model, th, xbar, d, dw, at);
+}
+
+/* ======================================================================== Philox4x32-10 */
+
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+#define STREAM_PCN 3u
+#define STREAM_ACC 4u
+
+static void box_muller(const uint32_t o[4], double *z0, double *z1) {
+    uint64_t w0 = ((uint64_t)o[1] << 32) | o[0], w1 = ((uint64_t)o[3] << 32) | o[2];
+    double u1 = (double)((w0 >> 11) + 1) * 0x1.0p-53; /* (0,1] */
+    double u2 = (double)(w1 >> 11) * 0x1.0p-53;       /* [0,1) */
+    double r = sqrt(-2.0 * log(u1));
+    double ang = 2.0 * M_PI * u2;
+    *z0 = r * cos(ang);
+    *z1 = r * sin(ang);
+}
+
+void orc_tile_normals(uint64_t seed, uint32_t chain, uint32_t gtile, uint32_t iter, int dw, double *z) {
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    int ncall = 2 * dw; /* 4*dw normals */
+    for (int call = 0; call < ncall; call++) {
+        uint32_t ctr[4] = {chain, gtile, iter, (STREAM_PCN << 8) | (uint32_t)call}, o[4];
+        orc_philox4x32_10(ctr, key, o);
+        box_muller(o, &z[2 * call], &z[2 * call + 1]);
+    }
+}
+
+double orc_accept_exponential(uint64_t seed, uint32_t chain, uint32_t block, uint32_t iter, uint32_t layout) {
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    uint32_t ctr[4] = {chain, block, iter, (STREAM_ACC << 8) | layout}, o[4];
+    orc_philox4x32_10(ctr, key, o);
+    uint64_t w0 = ((uint64_t)o[1] << 32) | o[0];
+    double u = (double)((w0 >> 11) + 1) * 0x1.0p-53;
+    return -log(u);
+}
+
+/* ======================================================================== containers */
+
+typedef struct {
+    double theta[ORC_MAXPAR];
+    double B[D2], beta[ORC_MAXD], at[D2];
+    double L[D2], Sig[D2], v[ORC_MAXD];
+    int exact; /* blocking law (guid_prop_for_blocking, src/sampling_unit.jl:61-66): L=I, Sigma=eps I */
+    double *H, *F, *c; /* [n][d*d], [n][d], [n] */
+} orc_law;
+
+typedef struct { /* SamplingUnit, src/sampling_unit.jl:48-54 */
+    orc_law **PP, **PPb;
+    double **XX, **WW; /* XX[k]: n_k x d ; WW[k]: (n_k-1) x dw (increments) */
+} orc_unit;
+
+struct orc_pair {
+    int model, d, dw, npar, constdiff, m, K;
+    int *n, *off;
+    double *t;
+    double eps;
+    orc_unit u[2];
+};
+
+static orc_law *law_new(int n, int d) {
+    orc_law *l = (orc_law *)calloc(1, sizeof(orc_law));
+    l->H = (double *)calloc((size_t)n * d * d, sizeof(double));
+    l->F = (double *)calloc((size_t)n * d, sizeof(double));
+    l->c = (double *)calloc((size_t)n, sizeof(double));
+    return l;
+}
+static void law_free(orc_law *l) { free(l->H); free(l->F); free(l->c); free(l); }
+
+orc_pair *orc_pair_create(int model, int K, const int *n, const double *t, int m, double eps) {
+    orc_pair *p = (orc_pair *)calloc(1, sizeof(orc_pair));
+    p->model = model; p->K = K; p->m = m; p->eps = eps;
+    if (orc_model_dims(model, &p->d, &p->dw, &p->npar, &p->constdiff)) { free(p); return 0; }
+    p->n = (int *)malloc(sizeof(int) * K);
+    p->off = (int *)malloc(sizeof(int) * (K + 1));
+    p->off[0] = 0;
+    for (int k = 0; k < K; k++) { p->n[k] = n[k]; p->off[k + 1] = p->off[k] + n[k]; }
+    p->t = (double *)malloc(sizeof(double) * p->off[K]);
+    memcpy(p->t, t, sizeof(double) * p->off[K]);
+    for (int s = 0; s < 2; s++) { /* u and u° = deepcopy(u), src/sampling_pair.jl:51 */
+        orc_unit *u = &p->u[s];
+        u->PP = (orc_law **)malloc(sizeof(void *) * K);
+        u->PPb = (orc_law **)malloc(sizeof(void *) * K);
+        u->XX = (double **)malloc(sizeof(void *) * K);
+        u->WW = (double **)malloc(sizeof(void *) * K);
+        for (int k = 0; k < K; k++) {
+            u->PP[k] = law_new(n[k], p->d);
+            u->PPb[k] = law_new(n[k], p->d);
+            u->PPb[k]->exact = 1;
+            u->XX[k] = (double *)calloc((size_t)n[k] * p->d, sizeof(double));
+            u->WW[k] = (double *)calloc((size_t)(n[k] - 1) * p->dw, sizeof(double));
+        }
+    }
+    return p;
+}
+
+void orc_pair_destroy(orc_pair *p) {
+    if (!p) return;
+    for (int s = 0; s < 2; s++) {
+        orc_unit *u = &p->u[s];
+        for (int k = 0; k < p->K; k++) { law_free(u->PP[k]); law_free(u->PPb[k]); free(u->XX[k]); free(u->WW[k]); }
+        free(u->PP); free(u->PPb); free(u->XX); free(u->WW);
+    }
+    free(p->n); free(p->off); free(p->t); free(p);
+}
+
+static orc_law *law_at(orc_pair *p, int side, int store, int k) { return store ? p->u[side].PPb[k] : p->u[side].PP[k]; }
+
+void orc_set_theta(orc_pair *p, int side, int store, int k, const double *theta) {
+    memcpy(law_at(p, side, store, k)->theta, theta, sizeof(double) * p->npar);
+}
+void orc_set_aux(orc_pair *p, int side, int store, int k, const double *B, const double *beta, const double *at) {
+    orc_law *l = law_at(p, side, store, k);
+    memcpy(l->B, B, sizeof(double) * p->d * p->d);
+    memcpy(l->beta, beta, sizeof(double) * p->d);
+    memcpy(l->at, at, sizeof(double) * p->d * p->d);
+}
+void orc_set_obs(orc_pair *p, int side, int k, const double *L, const double *Sig, const double *v) {
+    orc_law *l = p->u[side].PP[k];
+    memcpy(l->L, L, sizeof(double) * p->m * p->d);
+    memcpy(l->Sig, Sig, sizeof(double) * p->m * p->m);
+    memcpy(l->v, v, sizeof(double) * p->m);
+}
+void orc_set_start(orc_pair *p, const double *x0) {
+    for (int s = 0; s < 2; s++) memcpy(p->u[s].XX[0], x0, sizeof(double) * p->d);
+}
+void orc_set_W(orc_pair *p, int side, int k, const double *dW) { memcpy(p->u[side].WW[k], dW, sizeof(double) * (p->n[k] - 1) * p->dw); }
+void orc_set_X(orc_pair *p, int side, int k, const double *X) { memcpy(p->u[side].XX[k], X, sizeof(double) * p->n[k] * p->d); }
+void orc_get_W(const orc_pair *p, int side, int k, double *dW) { memcpy(dW, p->u[side].WW[k], sizeof(double) * (p->n[k] - 1) * p->dw); }
+void orc_get_X(const orc_pair *p, int side, int k, double *X) { memcpy(X, p->u[side].XX[k], sizeof(double) * p->n[k] * p->d); }
+void orc_get_HFc(const orc_pair *p, int side, int store, int k, double *H, double *F, double *c) {
+    const orc_law *l = store ? p->u[side].PPb[k] : p->u[side].PP[k];
+    int n = p->n[k], d = p->d;
+    if (H) memcpy(H, l->H, sizeof(double) * n * d * d);
+    if (F) memcpy(F, l->F, sizeof(double) * n * d);
+    if (c) memcpy(c, l->c, sizeof(double) * n);
+}
+void orc_set_HFc(orc_pair *p, int side, int store, int k, const double *H, const double *F, const double *c) {
+    orc_law *l = law_at(p, side, store, k);
+    int n = p->n[k], d = p->d;
+    memcpy(l->H, H, sizeof(double) * n * d * d);
+    memcpy(l->F, F, sizeof(double) * n * d);
+    memcpy(l->c, c, sizeof(double) * n);
+}
+
+/* ======================================================================== small dense linear algebra */
+
+static void mat_mul(const double *A, const double *Bm, int n, double *C) { /* C = A Bm */
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) {
+            double s = 0;
+            for (int k = 0; k < n; k++) s += A[i * n + k] * Bm[k * n + j];
+            C[i * n + j] = s;
+        }
+}
+static void mat_tmul(const double *A, const double *Bm, int n, double *C) { /* C = A^T Bm */
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) {
+            double s = 0;
+            for (int k = 0; k < n; k++) s += A[k * n + i] * Bm[k * n + j];
+            C[i * n + j] = s;
+        }
+}
+static void mat_vec(const double *A, const double *x, int n, double *y) {
+    for (int i = 0; i < n; i++) {
+        double s = 0;
+        for (int j = 0; j < n; j++) s += A[i * n + j] * x[j];
+        y[i] = s;
+    }
+}
+static void mat_tvec(const double *A, const double *x, int n, double *y) {
+    for (int i = 0; i < n; i++) {
+        double s = 0;
+        for (int j = 0; j < n; j++) s += A[j * n + i] * x[j];
+        y[i] = s;
+    }
+}
+static double dot(const double *a, const double *b, int n) {
+    double s = 0;
+    for (int i = 0; i < n; i++) s += a[i] * b[i];
+    return s;
+}
+/* SPD inverse + log det via Cholesky */
+static int spd_inv(const double *A, int n, double *Ai, double *logdet) {
+    double Lo[D2], Li[D2];
+    if (chol_lower(A, n, Lo)) return 1;
+    double ld = 0;
+    memset(Li, 0, sizeof Li);
+    for (int j = 0; j < n; j++) { /* Li = Lo^{-1} (lower) */
+        ld += log(Lo[j * n + j]);
+        Li[j * n + j] = 1.0 / Lo[j * n + j];
+        for (int i = j + 1; i < n; i++) {
+            double s = 0;
+            for (int k = j; k < i; k++) s -= Lo[i * n + k] * Li[k * n + j];
+            Li[i * n + j] = s / Lo[i * n + i];
+        }
+    }
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) {
+            double s = 0;
+            for (int k = (i > j ? i : j); k < n; k++) s += Li[k * n + i] * Li[k * n + j];
+            Ai[i * n + j] = s;
+        }
+    if (logdet) *logdet = 2.0 * ld;
+    return 0;
+}
+/* general solve A x = b, partial pivoting */
+static int gauss_solve(const double *A, const double *b, int n, double *x) {
+    double M[D2], r[ORC_MAXD];
+    memcpy(M, A, sizeof(double) * n * n);
+    memcpy(r, b, sizeof(double) * n);
+    for (int c = 0; c < n; c++) {
+        int piv = c;
+        for (int i = c + 1; i < n; i++)
+            if (fabs(M[i * n + c]) > fabs(M[piv * n + c])) piv = i;
+        if (M[piv * n + c] == 0.0) return 1;
+        if (piv != c) {
+            for (int j = 0; j < n; j++) { double t = M[c * n + j]; M[c * n + j] = M[piv * n + j]; M[piv * n + j] = t; }
+            double t = r[c]; r[c] = r[piv]; r[piv] = t;
+        }
+        for (int i = c + 1; i < n; i++) {
+            double f = M[i * n + c] / M[c * n + c];
+            for (int j = c; j < n; j++) M[i * n + j] -= f * M[c * n + j];
+            r[i] -= f * r[c];
+        }
+    }
+    for (int i = n - 1; i >= 0; i--) {
+        double s = r[i];
+        for (int j = i + 1; j < n; j++) s -= M[i * n + j] * x[j];
+        x[i] = s / M[i * n + i];
+    }
+    return 0;
+}
+
+/* ======================================================================== K1 backward filter (A.1) */
+
+/* RHS of the (H,F,c) ODE:  dH = -B'H - HB + H at H ; dF = -B'F + H at F + H beta ;
+ *                          dc = beta'F + 1/2 F' at F - 1/2 tr(H at)                                   */
+static void hfc_rhs(const orc_law *l, int d, const double *H, const double *F, double *dH, double *dF, double *dc) {
+    double BtH[D2], HB[D2], Ha[D2], HaH[D2], tmp[ORC_MAXD], tmp2[ORC_MAXD];
+    mat_tmul(l->B, H, d, BtH);
+    mat_mul(H, l->B, d, HB);
+    mat_mul(H, l->at, d, Ha);
+    mat_mul(Ha, H, d, HaH);
+    for (int i = 0; i < d * d; i++) dH[i] = -BtH[i] - HB[i] + HaH[i];
+    mat_tvec(l->B, F, d, tmp);
+    mat_vec(Ha, F, d, tmp2);
+    double Hb[ORC_MAXD];
+    mat_vec(H, l->beta, d, Hb);
+    for (int i = 0; i < d; i++) dF[i] = -tmp[i] + tmp2[i] + Hb[i];
+    double aF[ORC_MAXD], tr = 0;
+    mat_vec(l->at, F, d, aF);
+    for (int i = 0; i < d; i++) tr += Ha[i * d + i];
+    *dc = dot(l->beta, F, d) + 0.5 * dot(F, aF, d) - 0.5 * tr;
+}
+
+/* RHS of the (P,nu) ODE used on exact-observation (blocking) intervals, P = H^{-1}, nu = P F:
+ *    dP = B P + P B' - at ;  dnu = B nu + beta   (linear, non-stiff even for Sigma = 1e-11 I)          */
+static void pnu_rhs(const orc_law *l, int d, const double *P, const double *nu, double *dP, double *dnu) {
+    double BP[D2];
+    mat_mul(l->B, P, d, BP);
+    for (int i = 0; i < d; i++)
+        for (int j = 0; j < d; j++) dP[i * d + j] = BP[i * d + j] + BP[j * d + i] - l->at[i * d + j];
+    mat_vec(l->B, nu, d, dnu);
+    for (int i = 0; i < d; i++) dnu[i] += l->beta[i];
+}
+
+static void solve_law_backward(orc_pair *p, orc_law *l, int k, const orc_law *next) {
+    int d = p->d, n = p->n[k], m = p->m;
+    const double *t = p->t + p->off[k];
+    double Hp[D2] = {0}, Fp[ORC_MAXD] = {0}, cp = 0.0;
+    if (next) { memcpy(Hp, next->H, sizeof(double) * d * d); memcpy(Fp, next->F, sizeof(double) * d); cp = next->c[0]; }
+
+    if (l->exact) {
+        /* exact artificial observation v of the full state with noise eps*I; nothing beyond the block end */
+        double P[D2] = {0}, nu[ORC_MAXD];
+        for (int i = 0; i < d; i++) { P[i * d + i] = p->eps; nu[i] = l->v[i]; }
+        double trB = 0;
+        for (int i = 0; i < d; i++) trB += l->B[i * d + i];
+        double T = t[n - 1];
+        for (int j = n - 1; j >= 0; j--) {
+            if (j < n - 1) { /* RK4 step from t[j+1] back to t[j] */
+                double h = t[j + 1] - t[j];
+                double k1P[D2], k2P[D2], k3P[D2], k4P[D2], k1n[ORC_MAXD], k2n[ORC_MAXD], k3n[ORC_MAXD], k4n[ORC_MAXD];
+                double Ps[D2], ns[ORC_MAXD];
+                pnu_rhs(l, d, P, nu, k1P, k1n);
+                for (int i = 0; i < d * d; i++) Ps[i] = P[i] - 0.5 * h * k1P[i];
+                for (int i = 0; i < d; i++) ns[i] = nu[i] - 0.5 * h * k1n[i];
+                pnu_rhs(l, d, Ps, ns, k2P, k2n);
+                for (int i = 0; i < d * d; i++) Ps[i] = P[i] - 0.5 * h * k2P[i];
+                for (int i = 0; i < d; i++) ns[i] = nu[i] - 0.5 * h * k2n[i];
+                pnu_rhs(l, d, Ps, ns, k3P, k3n);
+                for (int i = 0; i < d * d; i++) Ps[i] = P[i] - h * k3P[i];
+                for (int i = 0; i < d; i++) ns[i] = nu[i] - h * k3n[i];
+                pnu_rhs(l, d, Ps, ns, k4P, k4n);
+                for (int i = 0; i < d * d; i++) P[i] -= h / 6.0 * (k1P[i] + 2.0 * k2P[i] + 2.0 * k3P[i] + k4P[i]);
+                for (int i = 0; i < d; i++) nu[i] -= h / 6.0 * (k1n[i] + 2.0 * k2n[i] + 2.0 * k3n[i] + k4n[i]);
+            }
+            double logdetP;
+            double *H = l->H + (size_t)j * d * d, *F = l->F + (size_t)j * d;
+            if (spd_inv(P, d, H, &logdetP)) { for (int i = 0; i < d * d; i++) H[i] = NAN; logdetP = NAN; }
+            mat_vec(H, nu, d, F);
+            /* c(t) = d/2 log 2pi + 1/2 log det P + tr(B)(T-t) + 1/2 nu' H nu  (closed form of the c-ODE) */
+            l->c[j] = 0.5 * d * log(2.0 * M_PI) + 0.5 * logdetP + trB * (T - t[j]) + 0.5 * dot(nu, F, d);
+        }
+        return;
+    }
+
+    /* jump at the observation (A.1): H = H+ + L' S^-1 L ; F = F+ + L' S^-1 v ; c = c+ + 1/2(m log 2pi + log det S + v' S^-1 v) */
+    double Si[D2], logdetS = 0;
+    if (m > 0) spd_inv(l->Sig, m, Si, &logdetS);
+    double *H = l->H + (size_t)(n - 1) * d * d, *F = l->F + (size_t)(n - 1) * d;
+    double SiL[D2], Siv[ORC_MAXD];
+    for (int a = 0; a < m; a++) {
+        for (int j = 0; j < d; j++) {
+            double s = 0;
+            for (int b = 0; b < m; b++) s += Si[a * m + b] * l->L[b * d + j];
+            SiL[a * d + j] = s;
+        }
+        double s = 0;
+        for (int b = 0; b < m; b++) s += Si[a * m + b] * l->v[b];
+        Siv[a] = s;
+    }
+    for (int i = 0; i < d; i++) {
+        for (int j = 0; j < d; j++) {
+            double s = 0;
+            for (int a = 0; a < m; a++) s += l->L[a * d + i] * SiL[a * d + j];
+            H[i * d + j] = Hp[i * d + j] + s;
+        }
+        double s = 0;
+        for (int a = 0; a < m; a++) s += l->L[a * d + i] * Siv[a];
+        F[i] = Fp[i] + s;
+    }
+    l->c[n - 1] = cp + 0.5 * (m * log(2.0 * M_PI) + logdetS + dot(l->v, Siv, m));
+
+    for (int j = n - 2; j >= 0; j--) { /* classical RK4 from t[j+1] back to t[j] (A.1, oracle-defined discretisation) */
+        double h = t[j + 1] - t[j];
+        const double *H1 = l->H + (size_t)(j + 1) * d * d, *F1 = l->F + (size_t)(j + 1) * d;
+        double c1 = l->c[j + 1];
+        double kH[4][D2], kF[4][ORC_MAXD], kc[4], Hs[D2], Fs[ORC_MAXD];
+        hfc_rhs(l, d, H1, F1, kH[0], kF[0], &kc[0]);
+        for (int i = 0; i < d * d; i++) Hs[i] = H1[i] - 0.5 * h * kH[0][i];
+        for (int i = 0; i < d; i++) Fs[i] = F1[i] - 0.5 * h * kF[0][i];
+        hfc_rhs(l, d, Hs, Fs, kH[1], kF[1], &kc[1]);
+        for (int i = 0; i < d * d; i++) Hs[i] = H1[i] - 0.5 * h * kH[1][i];
+        for (int i = 0; i < d; i++) Fs[i] = F1[i] - 0.5 * h * kF[1][i];
+        hfc_rhs(l, d, Hs, Fs, kH[2], kF[2], &kc[2]);
+        for (int i = 0; i < d * d; i++) Hs[i] = H1[i] - h * kH[2][i];
+        for (int i = 0; i < d; i++) Fs[i] = F1[i] - h * kF[2][i];
+        hfc_rhs(l, d, Hs, Fs, kH[3], kF[3], &kc[3]);
+        double *H0 = l->H + (size_t)j * d * d, *F0 = l->F + (size_t)j * d;
+        for (int i = 0; i < d * d; i++) H0[i] = H1[i] - h / 6.0 * (kH[0][i] + 2.0 * kH[1][i] + 2.0 * kH[2][i] + kH[3][i]);
+        for (int i = 0; i < d; i++) F0[i] = F1[i] - h / 6.0 * (kF[0][i] + 2.0 * kF[1][i] + 2.0 * kF[2][i] + kF[3][i]);
+        l->c[j] = c1 - h / 6.0 * (kc[0] + 2.0 * kc[1] + 2.0 * kc[2] + kc[3]);
+    }
+}
+
+/* src/block.jl:104-110 — Block{false}: recompute_guiding_term!(b.PP, b.P_last[1]) ; Block{true}: (b.PP).
+ * Views (src/block.jl:66-69): PP = u.PP[i0 : i1-!last], P_last = u.PPb[i1] (non-terminal only).        */
+void orc_recompute_guiding_term(orc_pair *p, const orc_biblock *bb, int side) {
+    orc_unit *u = &p->u[side];
+    const orc_law *next = 0;
+    int kend = bb->i1;
+    if (!bb->last) {
+        solve_law_backward(p, u->PPb[bb->i1], bb->i1, 0);
+        next = u->PPb[bb->i1];
+        kend = bb->i1 - 1;
+    }
+    for (int k = kend; k >= bb->i0; k--) {
+        solve_law_backward(p, u->PP[k], k, next);
+        next = u->PP[k];
+    }
+}
+
+/* src/biblock.jl:275-278 — artificial obs of BOTH b.P_last[1] and b°.P_last[1] := b.XX[end].x[end] */
+void orc_set_artificial_obs(orc_pair *p, const orc_biblock *bb) {
+    if (bb->last) return; /* src/biblock.jl:280 */
+    const double *xe = p->u[0].XX[bb->i1] + (size_t)(p->n[bb->i1] - 1) * p->d;
+    memcpy(p->u[0].PPb[bb->i1]->v, xe, sizeof(double) * p->d);
+    memcpy(p->u[1].PPb[bb->i1]->v, xe, sizeof(double) * p->d);
+}
+
+/* ======================================================================== K2/K4/K5 per interval (A.3-A.5) */
+
+static double loglikhd_obs(const orc_pair *p, const orc_law *l, const double *y) { /* log h~(t0,y) = -c - y'Hy/2 + F'y */
+    double Hy[ORC_MAXD];
+    mat_vec(l->H, y, p->d, Hy);
+    return -l->c[0] - 0.5 * dot(y, Hy, p->d) + dot(l->F, y, p->d);
+}
+
+/* integrand G(t_i,x_i) of A.4 and the guided drift b + a r of A.3 at grid index i of law l */
+static void step_terms(const orc_pair *p, const orc_law *l, int i, const double *x, double *gdrift, double *S, double *G) {
+    int d = p->d, dw = p->dw;
+    const double *H = l->H + (size_t)i * d * d, *F = l->F + (size_t)i * d;
+    double r[ORC_MAXD], Hx[ORC_MAXD], b[ORC_MAXD], a[D2], ar[ORC_MAXD], bt[ORC_MAXD];
+    mat_vec(H, x, d, Hx);
+    for (int q = 0; q < d; q++) r[q] = F[q] - Hx[q];
+    orc_drift(p->model, l->theta, x, b);
+    orc_sigma(p->model, l->theta, x, S);
+    for (int q = 0; q < d; q++)
+        for (int j = 0; j < d; j++) {
+            double s = 0;
+            for (int w = 0; w < dw; w++) s += S[q * dw + w] * S[j * dw + w];
+            a[q * d + j] = s;
+        }
+    mat_vec(a, r, d, ar);
+    for (int q = 0; q < d; q++) gdrift[q] = b[q] + ar[q];
+    if (G) {
+        mat_vec(l->B, x, d, bt);
+        double g = 0;
+        for (int q = 0; q < d; q++) g += (b[q] - (bt[q] + l->beta[q])) * r[q];
+        if (!p->constdiff) { /* - 1/2 tr((a-at)H) + 1/2 r'(a-at)r */
+            double tr = 0, q2 = 0;
+            for (int q = 0; q < d; q++)
+                for (int j = 0; j < d; j++) {
+                    double da = a[q * d + j] - l->at[q * d + j];
+                    tr += da * H[j * d + q];
+                    q2 += r[q] * da * r[j];
+                }
+            g += -0.5 * tr + 0.5 * q2;
+        }
+        *G = g;
+    }
+}
+
+/* GP.solve_and_ll!(X, W, P, y1; skip) — guided Euler–Maruyama + ll integral (A.3, A.4). */
+static int solve_and_ll(const orc_pair *p, const orc_law *l, int k, const double *y1, const double *dW, double *X, int skip, double *ll_out) {
+    int d = p->d, dw = p->dw, n = p->n[k];
+    const double *t = p->t + p->off[k];
+    double ll = 0;
+    memcpy(X, y1, sizeof(double) * d);
+    for (int i = 0; i < n - 1; i++) {
+        const double *x = X + (size_t)i * d;
+        double *xn = X + (size_t)(i + 1) * d;
+        double dt = t[i + 1] - t[i], g[ORC_MAXD], S[D2], G;
+        step_terms(p, l, i, x, g, S, &G);
+        if (i < n - 1 - skip) ll += G * dt;
+        for (int q = 0; q < d; q++) {
+            double s = x[q] + g[q] * dt;
+            for (int w = 0; w < dw; w++) s += S[q * dw + w] * dW[(size_t)i * dw + w];
+            xn[q] = s;
+        }
+        if (!orc_bound_ok(p->model, l->theta, xn)) { *ll_out = -INFINITY; return 0; }
+    }
+    *ll_out = ll;
+    return 1;
+}
+
+/* loglikhd(P, X) for one interval (A.4) */
+static double loglik_interval(const orc_pair *p, const orc_law *l, int k, const double *X, int skip) {
+    int d = p->d, n = p->n[k];
+    const double *t = p->t + p->off[k];
+    double ll = 0;
+    for (int i = 0; i < n - 1 - skip; i++) {
+        double g[ORC_MAXD], S[D2], G;
+        step_terms(p, l, i, X + (size_t)i * d, g, S, &G);
+        ll += G * (t[i + 1] - t[i]);
+    }
+    return ll;
+}
+
+static const int *noisy_rows(int model, int *cnt) {
+    static const int fhn[] = {1}, jr[] = {4}, all[] = {0, 1, 2, 3, 4, 5};
+    switch (model) {
+    case ORC_FHN: *cnt = 1; return fhn;
+    case ORC_JR: *cnt = 1; return jr;
+    default: orc_model_dims(model, cnt, 0, 0, 0); return all;
+    }
+}
+
+/* DD.invsolve!(X, W, P) (A.5): dW_i = sigma^+ (x_{i+1} - x_i - (b + a r) dt) on the non-degenerate rows */
+static void invsolve_interval(const orc_pair *p, const orc_law *l, int k, const double *X, double *dW) {
+    int d = p->d, dw = p->dw, n = p->n[k], nr;
+    const double *t = p->t + p->off[k];
+    const int *rows = noisy_rows(p->model, &nr);
+    for (int i = 0; i < n - 1; i++) {
+        const double *x = X + (size_t)i * d, *xn = X + (size_t)(i + 1) * d;
+        double dt = t[i + 1] - t[i], g[ORC_MAXD], S[D2], A[D2], rhs[ORC_MAXD], sol[ORC_MAXD];
+        step_terms(p, l, i, x, g, S, 0);
+        for (int a = 0; a < nr; a++) {
+            int q = rows[a];
+            rhs[a] = xn[q] - x[q] - g[q] * dt;
+            for (int w = 0; w < dw; w++) A[a * dw + w] = S[q * dw + w];
+        }
+        if (gauss_solve(A, rhs, dw, sol)) for (int w = 0; w < dw; w++) sol[w] = NAN;
+        for (int w = 0; w < dw; w++) dW[(size_t)i * dw + w] = sol[w];
+    }
+}
+
+/* ======================================================================== Block / BiBlock methods */
+
+/* src/block.jl:120-131 */
+void orc_find_W_for_X(orc_pair *p, const orc_biblock *bb) {
+    orc_unit *u = &p->u[0];
+    int kend = bb->last ? bb->i1 : bb->i1 - 1;
+    for (int k = bb->i0; k <= kend; k++) invsolve_interval(p, u->PP[k], k, u->XX[k], u->WW[k]);
+    if (!bb->last) invsolve_interval(p, u->PPb[bb->i1], bb->i1, u->XX[bb->i1], u->WW[bb->i1]);
+}
+
+/* src/block.jl:140-152: loglikhd(b.PP, b.XX) (+ loglikhd(b.P_last[1], b.XX[end]));
+ * loglikhd(PP, XX) = loglikhd_obs(PP[1], XX[1].x[1]) + sum_k loglikhd(PP[k], XX[k])  [UPSTREAM GP; same
+ * composition as _recompute_path!, src/block.jl:176-187]. */
+double orc_loglikhd(orc_pair *p, orc_biblock *bb, int side, int skip) {
+    orc_unit *u = &p->u[side];
+    int kend = bb->last ? bb->i1 : bb->i1 - 1;
+    double ll = loglikhd_obs(p, u->PP[bb->i0], u->XX[bb->i0]);
+    for (int k = bb->i0; k <= kend; k++) ll += loglik_interval(p, u->PP[k], k, u->XX[k], skip);
+    if (!bb->last) ll += loglik_interval(p, u->PPb[bb->i1], bb->i1, u->XX[bb->i1], skip);
+    bb->ll[side] = ll;
+    return ll;
+}
+
+/* pCN (A.2) on increments: dW° = rho dW + sqrt(1-rho^2) sqrt(dt) xi */
+static void pcn_interval(const orc_pair *p, int k, double rho, const double *dW, const double *xi, double *dWo) {
+    int dw = p->dw, n = p->n[k];
+    const double *t = p->t + p->off[k];
+    double cr = sqrt(1.0 - rho * rho);
+    for (int i = 0; i < n - 1; i++) {
+        double sq = sqrt(t[i + 1] - t[i]);
+        for (int w = 0; w < dw; w++) dWo[(size_t)i * dw + w] = rho * dW[(size_t)i * dw + w] + cr * sq * xi[(size_t)i * dw + w];
+    }
+}
+
+static void interval_normals(const orc_pair *p, int k, const double *Zblock, size_t *zoff, uint64_t seed, uint32_t chain,
+                             uint32_t iter, const int *gtile0, double *xi) {
+    int dw = p->dw, ns = p->n[k] - 1;
+    if (Zblock) {
+        memcpy(xi, Zblock + *zoff, sizeof(double) * ns * dw);
+        *zoff += (size_t)ns * dw;
+        return;
+    }
+    double z[4 * ORC_MAXD];
+    for (int i = 0; i < ns; i++) {
+        if (i % 4 == 0) orc_tile_normals(seed, chain, (uint32_t)(gtile0[k] + i / 4), iter, dw, z);
+        for (int w = 0; w < dw; w++) xi[(size_t)i * dw + w] = z[(i % 4) * dw + w];
+    }
+}
+
+/* src/biblock.jl:80-106: law = ACCEPTED bb.b.PP (+ bb.b.P_last), noise in = bb.b.WW, out = bb.b°.XX / bb.b°.WW,
+ * start = bb.b.XX[1].x[1]; ll° = loglikhd_obs(PP[1], y1) + sum ll_k; failure => ll° = failing value, stop. */
+int orc_draw_proposal_path(orc_pair *p, orc_biblock *bb, const double *Z, uint64_t seed, uint32_t chain, uint32_t iter,
+                           const int *gtile0) {
+    orc_unit *u = &p->u[0], *uo = &p->u[1];
+    int d = p->d, nmax = 0;
+    for (int k = bb->i0; k <= bb->i1; k++) if (p->n[k] > nmax) nmax = p->n[k];
+    double *xi = (double *)malloc(sizeof(double) * nmax * p->dw);
+    size_t zoff = 0;
+    double y1[ORC_MAXD];
+    memcpy(y1, u->XX[bb->i0], sizeof(double) * d);
+    int kend = bb->last ? bb->i1 : bb->i1 - 1, ok = 1;
+    double ll = loglikhd_obs(p, u->PP[bb->i0], y1);
+    for (int k = bb->i0; k <= bb->i1 && ok; k++) {
+        const orc_law *l = (k <= kend) ? u->PP[k] : u->PPb[k];
+        double llk;
+        interval_normals(p, k, Z, &zoff, seed, chain, iter, gtile0, xi);
+        pcn_interval(p, k, bb->rho, u->WW[k], xi, uo->WW[k]);
+        ok = solve_and_ll(p, l, k, y1, uo->WW[k], uo->XX[k], 0, &llk);
+        if (!ok) { ll = llk; break; }
+        ll += llk;
+        memcpy(y1, uo->XX[k] + (size_t)(p->n[k] - 1) * d, sizeof(double) * d);
+    }
+    bb->ll[1] = ll;
+    free(xi);
+    return ok;
+}
+
+/* src/block.jl:161-187 via set_proposal_law! (src/biblock.jl:343): recompute_path!(bb.b°, bb.b.WW; skip) */
+int orc_recompute_path(orc_pair *p, orc_biblock *bb, int law_side, int w_side, int skip) {
+    orc_unit *u = &p->u[law_side], *uw = &p->u[w_side];
+    int d = p->d;
+    double y1[ORC_MAXD];
+    memcpy(y1, u->XX[bb->i0], sizeof(double) * d); /* y1 = b.XX[1].x[1], src/block.jl:177 */
+    int kend = bb->last ? bb->i1 : bb->i1 - 1;
+    double ll = loglikhd_obs(p, u->PP[bb->i0], y1);
+    for (int k = bb->i0; k <= bb->i1; k++) {
+        const orc_law *l = (k <= kend) ? u->PP[k] : u->PPb[k];
+        double llk;
+        int ok = solve_and_ll(p, l, k, y1, uw->WW[k], u->XX[k], skip, &llk);
+        if (!ok) { bb->ll[law_side] = llk; return 0; }
+        ll += llk;
+        memcpy(y1, u->XX[k] + (size_t)(p->n[k] - 1) * d, sizeof(double) * d);
+    }
+    bb->ll[law_side] = ll;
+    return 1;
+}
+
+static void swap_ptr(double **a, double **b) { double *t = *a; *a = *b; *b = t; }
+static void swap_law(orc_law **a, orc_law **b) { orc_law *t = *a; *a = *b; *b = t; }
+
+void orc_swap_XX(orc_pair *p, const orc_biblock *bb) { /* src/biblock.jl:158-162 */
+    for (int k = bb->i0; k <= bb->i1; k++) swap_ptr(&p->u[0].XX[k], &p->u[1].XX[k]);
+}
+void orc_swap_WW(orc_pair *p, const orc_biblock *bb) { /* src/biblock.jl:169-173 */
+    for (int k = bb->i0; k <= bb->i1; k++) swap_ptr(&p->u[0].WW[k], &p->u[1].WW[k]);
+}
+void orc_swap_PP(orc_pair *p, const orc_biblock *bb) { /* src/biblock.jl:182-199 */
+    int kend = bb->last ? bb->i1 : bb->i1 - 1;
+    for (int k = bb->i0; k <= kend; k++) swap_law(&p->u[0].PP[k], &p->u[1].PP[k]); /* _swap_PP! */
+    if (!bb->last) {
+        swap_law(&p->u[0].PPb[bb->i1], &p->u[1].PPb[bb->i1]);                            /* P_last  */
+        swap_law(&p->u[0].PP[bb->i1], &p->u[1].PP[bb->i1]);                              /* P_excl  */
+        for (int k = bb->i0; k < bb->i1; k++) swap_law(&p->u[0].PPb[k], &p->u[1].PPb[k]); /* Pb_excl */
+    }
+}
+void orc_swap_ll(orc_biblock *bb) { double t = bb->ll[0]; bb->ll[0] = bb->ll[1]; bb->ll[1] = t; }
+
+/* src/biblock.jl:121-127: accepted = E > -(ll° - ll); swap paths; record; save both ll BEFORE swap_ll! */
+int orc_accept_reject(orc_pair *p, orc_biblock *bb, double E, double *ll_hist_out) {
+    int accepted = E > -(bb->ll[1] - bb->ll[0]);
+    if (accepted) { orc_swap_XX(p, bb); orc_swap_WW(p, bb); }
+    if (ll_hist_out) { ll_hist_out[0] = bb->ll[0]; ll_hist_out[1] = bb->ll[1]; }
+    if (accepted) orc_swap_ll(bb);
+    return accepted;
+}
+
+/* ======================================================================== bulk CPU baseline */
+
+/* One blocking sweep (docs/src/tutorials/block_collection/inference_with_blocking.md:52-58) or, with
+ * blocking=0, one plain draw+accept (docs/src/tutorials/biblock/smoothing.md:44-47), over M recordings. */
+double orc_sweep_many(orc_pair **pairs, orc_biblock *blocks, int M, int nb, uint64_t seed, uint32_t chain0, uint32_t iter,
+                      uint32_t layout, const int *gtile0, int blocking, int nthreads, int *n_accept) {
+    double total = 0;
+    int nacc = 0;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#else
+    (void)nthreads;
+#endif
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) reduction(+ : total, nacc)
+#endif
+    for (int c = 0; c < M; c++) {
+        orc_pair *p = pairs[c];
+        orc_biblock *bbs = blocks + (size_t)c * nb;
+        if (blocking) {
+            for (int b = 0; b < nb; b++) orc_set_artificial_obs(p, &bbs[b]);
+            for (int b = 0; b < nb; b++) orc_recompute_guiding_term(p, &bbs[b], 0);
+            for (int b = 0; b < nb; b++) orc_find_W_for_X(p, &bbs[b]);
+            for (int b = 0; b < nb; b++) orc_loglikhd(p, &bbs[b], 0, 0);
+        }
+        for (int b = 0; b < nb; b++) orc_draw_proposal_path(p, &bbs[b], 0, seed, chain0 + (uint32_t)c, iter, gtile0);
+        for (int b = 0; b < nb; b++) {
+            double E = orc_accept_exponential(seed, chain0 + (uint32_t)c, (uint32_t)b, iter, layout);
+            nacc += orc_accept_reject(p, &bbs[b], E, 0);
+            total += bbs[b].ll[0];
+        }
+    }
+    if (n_accept) *n_accept = nacc;
+    return total;
+}

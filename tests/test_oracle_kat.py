@@ -1,0 +1,280 @@
+"""Known-answer tests that pin the CPU oracle (the reference ships none: test/runtests.jl:4-6 is empty).
+
+Each test checks oracle arithmetic against an INDEPENDENT computation (published vectors, scipy, closed forms).
+"""
+import numpy as np
+import pytest
+from scipy.integrate import solve_ivp
+from scipy.linalg import expm
+
+
+def tau_grid(t0, t1, dt):
+    """standard_guid_prop_time_transf on a uniform grid."""
+    n = int(round((t1 - t0) / dt)) + 1
+    s = np.linspace(0.0, t1 - t0, n)
+    T = t1 - t0
+    return t0 + s * (2.0 - s / T)
+
+
+# ---- Philox4x32-10: Random123 kat_vectors -------------------------------------------------------------
+@pytest.mark.parametrize("ctr,key,exp", [
+    ((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+    ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+    ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+     (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)),
+])
+def test_philox_kat(orc, olib, ctr, key, exp):
+    assert tuple(orc.philox(olib, ctr, key)) == exp
+
+
+def test_tile_normals_moments(orc, olib):
+    z = np.concatenate([orc.tile_normals(olib, 1234, c, 7, 3, 3) for c in range(20000)])
+    assert abs(z.mean()) < 0.01 and abs(z.std() - 1) < 0.01
+    assert abs((z ** 4).mean() - 3) < 0.1
+    # pairs from one Philox call are uncorrelated
+    assert abs(np.corrcoef(z[0::2], z[1::2])[0, 1]) < 0.01
+
+
+# ---- models: Jacobian vs finite differences --------------------------------------------------------------
+THETA = {
+    0: [0.1, -0.8, 1.5, 0.0, 0.3],
+    1: [2 / 3, 4 / 3, 1.0, 1.0, 0.1, 0.1],
+    2: [10.0, 28.0, 8 / 3, 3.0],
+    3: [0.1, 0.7, 0.35, 0.2, 0.1, 0.9, 0.3, 0.1, 10.0],
+    4: [3.25, 100.0, 22.0, 50.0, 135.0, 5.0, 6.0, 0.56, 220.0, 2000.0],
+    5: [-0.5, 0.3, -0.2, -1.0, 0.1, -0.3, 0.4, 0.7],
+}
+XREF = {0: [-0.9, -1.0], 1: [2.0, 0.25], 2: [1.5, -1.5, 25.0], 3: [8.0, 8.0, 8.0, 5.0],
+        4: [0.08, 18.0, 15.0, -0.5, 0.0, 0.0], 5: [0.3, -0.2]}
+
+
+@pytest.mark.parametrize("model", range(6))
+def test_jacobian_fd(orc, olib, model):
+    import ctypes as C
+    d, dw, npar, _ = orc.model_dims(olib, model)
+    th = np.array(THETA[model]); x = np.array(XREF[model])
+    dp = C.POINTER(C.c_double)
+    J = np.zeros((d, d))
+    olib.orc_jacobian(model, th.ctypes.data_as(dp), x.ctypes.data_as(dp), J.ctypes.data_as(dp))
+
+    def b(xx):
+        out = np.zeros(d)
+        xx = np.ascontiguousarray(xx)
+        olib.orc_drift(model, th.ctypes.data_as(dp), xx.ctypes.data_as(dp), out.ctypes.data_as(dp))
+        return out
+    Jfd = np.zeros((d, d))
+    for j in range(d):
+        h = 1e-6 * max(1.0, abs(x[j]))
+        e = np.zeros(d); e[j] = h
+        Jfd[:, j] = (b(x + e) - b(x - e)) / (2 * h)
+    assert np.allclose(J, Jfd, rtol=1e-6, atol=1e-6 * np.abs(J).max())
+
+
+# ---- K1: linear-Gaussian state space => log h~(0,x0) is the exact marginal likelihood ----------------------
+def kalman_loglik(Bm, beta, a, x0, tobs, L, Sig, vs):
+    """log p(v_1..v_K | X_0 = x0) for dX = (B X + beta) dt + sigma dW observed v_k = L X(t_k) + N(0,Sig)."""
+    d = len(x0)
+    mean = np.array(x0, float); cov = np.zeros((d, d)); ll = 0.0; tprev = 0.0
+    for tk, v in zip(tobs, vs):
+        h = tk - tprev
+        # Van Loan: exact discretisation
+        Mv = np.zeros((2 * d + 1, 2 * d + 1))
+        A = np.zeros((d + 1, d + 1)); A[:d, :d] = Bm; A[:d, d] = beta
+        E = expm(A * h); Phi = E[:d, :d]; mu = E[:d, d]
+        V = np.zeros((2 * d, 2 * d)); V[:d, :d] = -Bm; V[:d, d:] = a; V[d:, d:] = Bm.T
+        EV = expm(V * h); Q = EV[d:, d:].T @ EV[:d, d:]
+        mean = Phi @ mean + mu; cov = Phi @ cov @ Phi.T + Q
+        S = L @ cov @ L.T + Sig; r = v - L @ mean
+        ll += -0.5 * (len(v) * np.log(2 * np.pi) + np.linalg.slogdet(S)[1] + r @ np.linalg.solve(S, r))
+        Kg = cov @ L.T @ np.linalg.inv(S)
+        mean = mean + Kg @ r; cov = cov - Kg @ S @ Kg.T
+        tprev = tk
+    return ll
+
+
+def make_ou_pair(orc, olib, K=4, dt=1e-3, seed=3, m=1):
+    th = np.array(THETA[5]); d = 2
+    Bm = th[:4].reshape(2, 2); beta = th[4:6]; a = np.diag(th[6:8] ** 2)
+    tobs = 0.1 * np.arange(1, K + 1)
+    grids = [tau_grid(tobs[k] - 0.1, tobs[k], dt) for k in range(K)]
+    n = [len(g) for g in grids]
+    P = orc.Pair(olib, orc.OU2, n, np.concatenate(grids), m)
+    rng = np.random.default_rng(seed)
+    L = np.array([[1.0, 0.5]]) if m == 1 else np.eye(2)
+    Sig = 0.02 * np.eye(m)
+    vs = [rng.normal(size=m) * 0.3 for _ in range(K)]
+    P.set_theta(th)
+    for k in range(K):
+        P.set_aux(k, Bm, beta, a)
+        P.set_obs(k, L, Sig, vs[k])
+    x0 = np.array(XREF[5])
+    P.set_start(x0)
+    return P, dict(B=Bm, beta=beta, a=a, tobs=tobs, L=L, Sig=Sig, vs=vs, x0=x0, th=th, grids=grids)
+
+
+@pytest.mark.parametrize("m", [1, 2])
+def test_backward_filter_vs_kalman(orc, olib, m):
+    P, s = make_ou_pair(orc, olib, K=4, m=m)
+    bb = P.biblock(0, P.K - 1, True)
+    P.recompute_guiding_term(bb, 0)
+    H, F, c = P.get_HFc(0, 0, 0)
+    x0 = s["x0"]
+    logh = -c[0] - 0.5 * x0 @ H[0] @ x0 + F[0] @ x0
+    ref = kalman_loglik(s["B"], s["beta"], s["a"], x0, s["tobs"], s["L"], s["Sig"], s["vs"])
+    assert abs(logh - ref) < 1e-7 * max(1.0, abs(ref))
+
+
+def test_linear_target_equals_aux_ll_is_path_independent(orc, olib):
+    """target == auxiliary => G == 0 => ll° = log h~(0,x0) whatever the noise (SURVEY §7.1 self-check a)."""
+    P, s = make_ou_pair(orc, olib, K=3)
+    bb = P.biblock(0, P.K - 1, True, rho=0.0)
+    P.recompute_guiding_term(bb, 0)
+    H, F, c = P.get_HFc(0, 0, 0)
+    x0 = s["x0"]
+    logh = -c[0] - 0.5 * x0 @ H[0] @ x0 + F[0] @ x0
+    for it in range(3):
+        assert P.draw_proposal_path(bb, seed=11, chain=0, it=it)
+        assert abs(bb.ll[1] - logh) < 1e-9 * max(1.0, abs(logh))
+
+
+# ---- K1: RK4-on-grid vs scipy's adaptive solver on the H,F,c ODE (non-trivial aux: Lorenz linearised) ---------
+def test_backward_ode_vs_scipy(orc, olib):
+    th = np.array(THETA[2]); d = 3
+    grid = tau_grid(0.0, 0.1, 1e-3)
+    P = orc.Pair(olib, orc.LORENZ, [len(grid)], grid, 2)
+    Bm, beta, at = orc.linearise(olib, orc.LORENZ, th, XREF[2])
+    L = np.array([[1.0, 0, 0], [0, 1.0, 0]]); Sig = 0.5 * np.eye(2); v = np.array([1.2, -1.1])
+    P.set_theta(th); P.set_aux(0, Bm, beta, at); P.set_obs(0, L, Sig, v)
+    bb = P.biblock(0, 0, True)
+    P.recompute_guiding_term(bb, 0)
+    H, F, c = P.get_HFc(0, 0, 0)
+    Si = np.linalg.inv(Sig)
+    HT = L.T @ Si @ L; FT = L.T @ Si @ v
+    cT = 0.5 * (2 * np.log(2 * np.pi) + np.linalg.slogdet(Sig)[1] + v @ Si @ v)
+    assert np.allclose(H[-1], HT, rtol=1e-14) and np.allclose(F[-1], FT, rtol=1e-14) and abs(c[-1] - cT) < 1e-13
+
+    def rhs(t, y):
+        Hm = y[:9].reshape(3, 3); Fv = y[9:12]
+        dH = -Bm.T @ Hm - Hm @ Bm + Hm @ at @ Hm
+        dF = -Bm.T @ Fv + Hm @ at @ Fv + Hm @ beta
+        dc = beta @ Fv + 0.5 * Fv @ at @ Fv - 0.5 * np.trace(Hm @ at)
+        return np.concatenate([dH.ravel(), dF, [dc]])
+    sol = solve_ivp(rhs, [0.1, 0.0], np.concatenate([HT.ravel(), FT, [cT]]), method="DOP853", rtol=1e-12, atol=1e-14,
+                    t_eval=grid[::-1])
+    Y = sol.y[:, ::-1].T
+    # RK4 on the path grid (h <= 2e-3, |B| ~ 28, |at H| ~ 18) has ~3e-8 truncation error; that is the oracle's definition
+    assert np.allclose(H.reshape(-1, 9), Y[:, :9], rtol=5e-7, atol=1e-8)
+    assert np.allclose(F, Y[:, 9:12], rtol=5e-7, atol=1e-8)
+    assert np.allclose(c, Y[:, 12], rtol=5e-7, atol=1e-8)
+
+
+# ---- K1 exact-observation (blocking) interval: (P,nu) form == the H,F,c ODE, at a non-stiff eps -----------------
+def test_exact_obs_pnu_form_matches_hfc_ode(orc, olib):
+    th = np.array(THETA[2]); d = 3; eps = 1e-4
+    g0 = tau_grid(0.0, 0.1, 1e-3); g1 = tau_grid(0.1, 0.2, 1e-3)
+    P = orc.Pair(olib, orc.LORENZ, [len(g0), len(g1)], np.concatenate([g0, g1]), 2, eps=eps)
+    Bm, beta, at = orc.linearise(olib, orc.LORENZ, th, XREF[2])
+    P.set_theta(th)
+    for k in range(2):
+        P.set_aux(k, Bm, beta, at)
+        P.set_obs(k, np.eye(2, 3), 0.5 * np.eye(2), [1.0, -1.0])
+    xe = np.array([1.4, -1.2, 24.0])
+    X1 = np.zeros((len(g1), d)); X1[-1] = xe
+    P.set_X(0, 1, X1)
+    bb = P.biblock(0, 1, False)
+    P.set_artificial_obs(bb)
+    P.recompute_guiding_term(bb, 0)
+    H, F, c = P.get_HFc(0, 1, 1)  # blocking store, interval 1
+    HT = np.eye(d) / eps; FT = xe / eps
+    cT = 0.5 * (d * np.log(2 * np.pi) + d * np.log(eps) + xe @ xe / eps)
+    assert np.allclose(H[-1], HT, rtol=1e-12) and np.allclose(F[-1], FT, rtol=1e-12) and abs(c[-1] - cT) < 1e-9 * abs(cT)
+
+    def rhs(t, y):
+        Hm = y[:9].reshape(3, 3); Fv = y[9:12]
+        dH = -Bm.T @ Hm - Hm @ Bm + Hm @ at @ Hm
+        dF = -Bm.T @ Fv + Hm @ at @ Fv + Hm @ beta
+        dc = beta @ Fv + 0.5 * Fv @ at @ Fv - 0.5 * np.trace(Hm @ at)
+        return np.concatenate([dH.ravel(), dF, [dc]])
+    sol = solve_ivp(rhs, [0.2, 0.1], np.concatenate([HT.ravel(), FT, [cT]]), method="Radau", rtol=1e-11, atol=1e-12,
+                    t_eval=g1[::-1])
+    Y = sol.y[:, ::-1].T
+    sl = slice(0, len(g1) - 1)
+    assert np.allclose(H.reshape(-1, 9)[sl], Y[sl, :9], rtol=2e-6, atol=1e-6)
+    assert np.allclose(F[sl], Y[sl, 9:12], rtol=2e-6, atol=1e-5)
+    # log h~ differences (what enters ll) agree
+    x = np.array([1.3, -1.25, 24.2])
+    lo = -c[0] - 0.5 * x @ H[0] @ x + F[0] @ x
+    lr = -Y[0, 12] - 0.5 * x @ Y[0, :9].reshape(3, 3) @ x + Y[0, 9:12] @ x
+    assert abs(lo - lr) < 1e-5 * max(1, abs(lr))
+    # and the preceding regular interval chained onto it (jump + RK4) is finite and symmetric
+    H0, F0, c0 = P.get_HFc(0, 0, 0)
+    assert np.isfinite(H0).all() and np.allclose(H0, np.swapaxes(H0, 1, 2), rtol=1e-10, atol=1e-12)
+
+
+# ---- K2/K5: invsolve o solve == identity on W; rho=1 => proposal == accepted bit-exactly -----------------------
+OBS = {  # per-model observation schemes of the BASELINE.json configs
+    0: (np.array([[1.0, 0.0]]), np.array([[0.01]])),
+    1: (np.eye(2), 0.01 * np.eye(2)),
+    2: (np.eye(2, 3), 0.5 * np.eye(2)),
+    3: (np.eye(4), 2.0 * np.eye(4)),
+    4: (np.array([[0, 1.0, -1.0, 0, 0, 0]]), np.array([[1e-2]])),
+    5: (np.eye(2), 0.02 * np.eye(2)),
+}
+
+
+def make_pair(orc, olib, model, K=3, dt=1e-3, seed=0, obs_dt=0.1):
+    d, dw, npar, _ = orc.model_dims(olib, model)
+    th = np.array(THETA[model]); xref = np.array(XREF[model])
+    grids = [tau_grid(k * obs_dt, (k + 1) * obs_dt, dt) for k in range(K)]
+    n = [len(g) for g in grids]
+    L, Sig = OBS[model]
+    m = L.shape[0]
+    P = orc.Pair(olib, model, n, np.concatenate(grids), m)
+    rng = np.random.default_rng(seed)
+    P.set_theta(th)
+    Bm, beta, at = orc.linearise(olib, model, th, xref)
+    for k in range(K):
+        P.set_aux(k, Bm, beta, at)
+        P.set_obs(k, L, Sig, L @ xref + np.sqrt(np.diag(Sig)) * rng.normal(size=m))
+    P.set_start(xref)
+    return P
+
+
+@pytest.mark.parametrize("model", [0, 1, 2, 3, 4])
+def test_invsolve_roundtrip_and_rho1(orc, olib, model):
+    odt = 0.01 if model == 4 else 0.1
+    P = make_pair(orc, olib, model, K=3, dt=odt / 100, obs_dt=odt)
+    bb = P.biblock(0, 2, True, rho=0.0)
+    P.recompute_guiding_term(bb, 0)
+    ok = P.draw_proposal_path(bb, seed=5, chain=1, it=0)
+    assert ok and np.isfinite(bb.ll[1])
+    acc, _ = P.accept_reject(bb, np.inf)   # force accept: E=inf > anything finite
+    assert acc
+    W = [P.get_W(0, k).copy() for k in range(3)]
+    X = [P.get_X(0, k).copy() for k in range(3)]
+    ll = P.loglikhd(bb, 0)
+    assert abs(ll - bb.ll[0]) < 1e-9 * max(1, abs(ll))  # ll from draw == ll recomputed from the stored path
+    P.find_W_for_X(bb)
+    for k in range(3):
+        scale = np.abs(W[k]).max()
+        assert np.allclose(P.get_W(0, k), W[k], rtol=0, atol=1e-9 * scale)
+        P.set_W(0, k, W[k])
+    bb.rho = 1.0
+    assert P.draw_proposal_path(bb, seed=5, chain=1, it=1)
+    for k in range(3):
+        assert np.array_equal(P.get_X(1, k), X[k])
+        assert np.array_equal(P.get_W(1, k), W[k])
+
+
+def test_accept_truth_table(orc, olib):
+    P = make_pair(orc, olib, 0, K=2)
+    for ll, llo, E, exp in [(0.0, 1.0, 0.1, True), (0.0, -1.0, 0.5, False), (0.0, -1.0, 1.5, True),
+                            (0.0, -np.inf, 1e300, False), (0.0, np.nan, 1.0, False), (-np.inf, 0.0, 0.0, True),
+                            (1.0, 1.0, 0.0, False)]:
+        bb = P.biblock(0, 1, True)
+        bb.ll[0], bb.ll[1] = ll, llo
+        acc, hist = P.accept_reject(bb, E)
+        assert acc == exp
+        assert np.array_equal(hist, [ll, llo], equal_nan=True)      # saved BEFORE swap_ll!  (src/biblock.jl:125-126)
+        if acc:
+            assert bb.ll[0] == llo or (np.isnan(llo) and np.isnan(bb.ll[0]))
