@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py — guided path updates/s (chains x EM steps / s, FP64) of the blocking path update, BASELINE.json config C3:
+Lorenz 3-D, 4096 chains PER GPU (weak scaling), 200 observation intervals x 100 EM steps, two staggered block layouts
+(10 / 11 blocks) alternated, pCN rho = 0.9, every chain with its own data and guiding term (P = M).
+
+One "step" = one blocking sweep over one layout, exactly the tutorial loop body
+(/root/reference/docs/src/tutorials/block_collection/inference_with_blocking.md:52-58):
+    set_obs! -> recompute_guiding_term!(P only) -> find_W_for_X! + loglikhd! -> draw_proposal_path! ->
+    accept_reject_proposal_path! -> (N > 1: NCCL allreduce of ll sums / accept counts)
+and it advances every chain by S = 20,000 guided Euler–Maruyama steps: units per step = M x S per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c3|c2|c4|c5] [--chains M] [--impl reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_BYTES = {  # per chain per EM step of draw_proposal_path! = 8(2 dw + d) [+ 8(d(d+1)/2 + d) when P = M]
+    "c2": (48, 88), "c3": (72, 144), "c4": (96, 208), "c5": (64, 280), "c1": (32, 72),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="c3")
+    ap.add_argument("--chains", type=int, default=None, help="chains PER GPU (default: the config's M)")
+    ap.add_argument("--psets", type=int, default=None)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-chains", type=int, default=None, help="chains in the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm (oracle port)
+def cpu_arm(cfg_name, n_chains, sweeps, warm, threads=None):
+    """Times the C restatement of the reference algorithm (oracle/, OpenMP over recordings) on a bounded sample of the
+    same workload.  kind = "port": the Julia reference and its un-vendored numerical dependencies cannot run here."""
+    import dmt_b200
+    from dmt_b200 import configs
+    from oracle import orc
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from harness import OracleEnsemble
+    import ctypes as C
+    threads = threads or os.cpu_count() or 1
+    prob = configs.named_config(cfg_name, M=n_chains, seed=123)
+    lib = orc.load(omp=True)
+    ora = OracleEnsemble(orc, lib, prob, seed=123)
+    blocking = len(prob.layouts) > 1
+    # initial paths: whole-path guiding term, fresh noise, forced accept
+    for P in ora.pairs:
+        bb = P.biblock(0, prob.K - 1, True, 0.0)
+        P.recompute_guiding_term(bb, 0)
+        tries = 0
+        while not P.draw_proposal_path(bb, seed=123, chain=tries, it=9999):
+            tries += 1
+        P.accept_reject(bb, float("inf"))
+        P.loglikhd(bb, 0)
+        if not blocking:
+            for lay in ora.layouts:
+                lay[ora.pairs.index(P)][0].ll[0] = bb.ll[0]
+    arr_t = C.c_void_p * len(ora.pairs)
+    handles = arr_t(*[P.h for P in ora.pairs])
+    gt0 = orc.gtile0_of(prob.n_pts)
+    flat = []
+    for l, lay in enumerate(ora.layouts):
+        nb = len(lay[0])
+        blk = (orc.BiBlock * (nb * prob.M))()
+        for c in range(prob.M):
+            for b in range(nb):
+                blk[c * nb + b] = lay[c][b]
+        flat.append((blk, nb))
+    nacc = C.c_int()
+
+    def sweep(it):
+        l = it % len(flat)
+        blk, nb = flat[l]
+        lib.orc_sweep_many(handles, blk, prob.M, nb, 123, 0, it, l, gt0.ctypes.data_as(C.POINTER(C.c_int)), int(blocking), threads,
+                           C.byref(nacc))
+    for it in range(warm):
+        sweep(it)
+    t0 = time.perf_counter()
+    for it in range(warm, warm + sweeps):
+        sweep(it)
+    dt = time.perf_counter() - t0
+    units = prob.M * prob.steps_per_chain * sweeps
+    return units / dt, dt / sweeps, threads, "%d chains x %d sweeps of config %s (%d steps/chain), %d OpenMP threads" % (
+        prob.M, sweeps, cfg_name, prob.steps_per_chain, threads)
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                for nme, val in zip(names, r[4:8]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def gpu_arm(a):
+    import torch
+    import torch.distributed as dist
+    import dmt_b200
+    from dmt_b200 import _lib, configs
+
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    base = configs.named_config(a.config, M=1, seed=0)  # only to learn the default M cheaply
+    M = a.chains or {"c1": 1, "c2": 1024, "c3": 4096, "c4": 16384, "c5": 8192}[a.config]
+    prob = configs.named_config(a.config, M=M, seed=0, chain_offset=rank * M, P=a.psets)
+    del base
+    blocking = len(prob.layouts) > 1
+    nlay = len(prob.layouts)
+    ctx = dmt_b200.Ctx(prob.model, prob.n_pts, prob.tt, prob.M, prob.P, obs_dim=prob.m, device=local, n_layouts=nlay + 1,
+                       chain_offset=rank * M, seed=2026, pset_of_chain=prob.pset_of_chain)
+    configs.upload(prob, ctx)
+    whole = nlay
+    ctx.set_blocks(whole, [(0, prob.K - 1)], 0.0)
+    ctx.recompute_guiding_term(whole, _lib.P_ONLY)
+    nfail = ctx.init_paths(whole, iter0=1 << 20, max_tries=100)
+    assert nfail == 0, "init_paths left %d failing chains" % nfail
+    if not blocking:
+        ctx.recompute_guiding_term(0, _lib.P_ONLY)
+        ctx.loglikhd(0, 0, 0)
+    if world > 1:  # native NCCL communicator inside libdmt for the small stats allreduce
+        uid = torch.from_numpy(ctx.nccl_unique_id() if rank == 0 else np.zeros(128, np.uint8)).to(dev)
+        dist.broadcast(uid, 0)
+        ctx.comm_init(world, rank, uid.cpu().numpy())
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
+
+    names = (["set_obs", "bwd_filter", "invsolve_ll"] if blocking else []) + ["draw", "accept", "stats"]
+    launches_per_step = (3 if blocking else 0) + 1 + 1 + 2
+    ev = {n: [] for n in names}
+
+    def sweep(it, timed):
+        l = it % nlay
+        marks = []
+
+        def mark():
+            if timed:
+                e = torch.cuda.Event(enable_timing=True); e.record(stream); marks.append(e)
+        mark()
+        if blocking:
+            ctx.set_artificial_obs(l); mark()
+            ctx.recompute_guiding_term(l, _lib.P_ONLY); mark()
+            ctx.find_W_and_loglikhd(l); mark()
+        ctx.draw_proposal_path(l, it); mark()
+        ctx.accept_reject_path(l, it); mark()
+        stats = ctx.allreduce_stats(l); mark()        # [sum ll, sum ll°, accept counts...] (NCCL allreduce when N > 1)
+        if timed:
+            for n, e0, e1 in zip(names, marks[:-1], marks[1:]):
+                ev[n].append((e0, e1))
+        return stats
+
+    def barrier():
+        ctx.sync(); torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ctx.sync(); torch.cuda.synchronize()
+
+    for it in range(a.warmup):
+        sweep(it, False)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e_start = torch.cuda.Event(enable_timing=True); e_stop = torch.cuda.Event(enable_timing=True)
+    e_start.record(stream)
+    last = None
+    for it in range(a.warmup, a.warmup + a.steps):
+        last = sweep(it, True)
+    e_stop.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = torch.tensor([e_start.elapsed_time(e_stop)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    units_per_step = prob.M * prob.steps_per_chain * world
+    value = units_per_step * a.steps / (ms_total * 1e-3)
+    kern_ms = {n: float(np.mean([e0.elapsed_time(e1) for e0, e1 in ev[n]])) for n in names}
+
+    # ---- roofline of the dominant kernel of the unit of work: fwd_kernel<Lorenz, OP_DRAW> (pCN + guided EM + ll)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    bsh, bper = ALGO_BYTES[a.config]
+    bpu = bper if prob.P == prob.M else bsh
+    algo_bytes = bpu * prob.M * prob.steps_per_chain
+    achieved = algo_bytes / (kern_ms["draw"] * 1e-3) / 1e9
+    roofline = {"kernel": "fwd_kernel<%s, OP_DRAW>" % _lib.MODEL_NAMES[prob.model], "bound": "hbm", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                "algorithmic_bytes_per_unit": bpu, "units_per_launch": prob.M * prob.steps_per_chain, "launch_ms": kern_ms["draw"]}
+    if blocking:  # the whole sweep also moves the K1 write and the K5+K4 pass (reported separately)
+        d, dw = prob.d, prob.dw
+        nh = d * (d + 1) // 2
+        sweep_bytes = (bpu + 8 * (nh + d) + 8 * (d + dw) + 8 * (nh + d)) * prob.M * prob.steps_per_chain
+        roofline["sweep"] = {"algorithmic_bytes_per_unit": sweep_bytes // (prob.M * prob.steps_per_chain),
+                             "achieved": sweep_bytes / (ms_total / a.steps * 1e-3) / 1e9, "frac": sweep_bytes / (ms_total / a.steps * 1e-3) / 1e9 / peak}
+
+    # ---- end to end through the C ABI with host buffers: H2D theta upload, D2H per-chain ll + accept flags every step
+    e2e = None
+    if not a.no_e2e:
+        theta_host = np.repeat(prob.theta[:, None], prob.P, axis=1).copy()
+        nb_max = max(len(r) for r, _ in prob.layouts)
+        barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(3, a.steps // 2)
+        for it in range(a.warmup + a.steps, a.warmup + a.steps + n_e2e):
+            l = it % nlay
+            ctx.set_params(theta_host, side=0, stores=3)              # H2D (pageable host -> device, inside the call)
+            sweep(it, False)
+            ll_host = ctx.get_ll(l, 0)                                # D2H
+            acc_host = ctx.get_last_accept(l)                         # D2H
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        nb_l = [len(r) for r, _ in prob.layouts]
+        e2e = {"value": units_per_step * n_e2e / float(dt.item()), "unit": "guided EM steps/s",
+               "h2d_bytes_per_step": int(theta_host.nbytes * 2), "d2h_bytes_per_step": int(np.mean(nb_l) * prob.M * 9 + 8 * (2 + np.mean(nb_l))),
+               "steps": n_e2e, "note": "dmt_set_params + sweep + dmt_get_ll + dmt_get_last_accept, host numpy buffers, wall clock"}
+
+    out = {
+        "metric": "guided path updates/sec (chains x EM steps/s, FP64)", "value": value, "unit": "guided EM steps/s",
+        "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_total / a.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "BASELINE.json configs[2] (C3): Lorenz 3-D, %d chains per GPU, %d obs intervals x %d EM steps, "
+                               "BlockCollection %s blocks alternated, pCN rho=0.9, P=%d parameter/data sets per GPU"
+                               % (prob.M, prob.K, int(prob.n_pts[0] - 1), "/".join(str(len(r)) for r, _ in prob.layouts), prob.P)
+                   if a.config == "c3" else "config %s: model %s, %d chains per GPU, K=%d" % (a.config, _lib.MODEL_NAMES[prob.model], prob.M, prob.K),
+                   "config_id": a.config, "chains_per_gpu": prob.M, "steps_per_chain": prob.steps_per_chain,
+                   "l2": "inputs (paths %.1f GB + guiding term %.1f GB per GPU) are far larger than the 126 MB L2"
+                         % (2 * 8 * 4 * ctx.S * (prob.d + prob.dw) * prob.M / 1e9, 8 * 4 * ctx.S * (prob.d * (prob.d + 1) // 2 + prob.d) * prob.P / 1e9),
+                   "step": "one blocking sweep over one layout" if blocking else "draw + accept"},
+        "roofline": roofline, "kernel_ms": kern_ms, "gpu_launches": launches_per_step * a.steps, "clocks": clocks,
+        "last_stats": {"sum_ll": float(last[0]), "sum_ll_prop": float(last[1]), "accept_frac": float(np.sum(last[2:]) / (len(last[2:]) * prob.M * world))},
+    }
+    if e2e:
+        out["e2e"] = e2e
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        nch = a.cpu_chains or min(512, 16 * (os.cpu_count() or 1))
+        v, spt, thr, sample = cpu_arm(a.config, nch, sweeps=4, warm=1)
+        out["cpu_baseline"] = {"value": v, "unit": "guided EM steps/s", "cores": thr, "kind": "port", "sample": sample,
+                               "note": "C restatement of the reference algorithm (oracle/), not the Julia package: Julia is not installed"}
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+def reference_arm(a):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    nch = a.cpu_chains or min(512, 16 * (os.cpu_count() or 1))
+    M = a.chains or {"c1": 1, "c2": 1024, "c3": 4096, "c4": 16384, "c5": 8192}[a.config]
+    v, spt, thr, sample = cpu_arm(a.config, nch, sweeps=max(1, min(a.steps, 4)), warm=max(0, min(a.warmup, 1)))
+    out = {"impl": "reference", "metric": "guided path updates/sec (chains x EM steps/s, FP64)", "value": v, "unit": "guided EM steps/s",
+           "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": spt * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "bounded sample of config %s (%d of %d chains per step)" % (a.config, nch, M), "config_id": a.config},
+           "cpu_baseline": {"value": v, "unit": "guided EM steps/s", "cores": thr, "kind": "port", "sample": sample},
+           "e2e": {"value": v, "unit": "guided EM steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "note": "reference arm = C restatement of the reference algorithm (oracle/, OpenMP); the Julia reference cannot run in this image"}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)

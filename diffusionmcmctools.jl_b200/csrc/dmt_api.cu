@@ -1,0 +1,860 @@
+// dmt_api.cu — the C ABI of include/dmt.h: context management, uploads, kernel launches.
+// No torch types, no CPU fallback: every compute entry point launches sm_100a kernels or fails.
+#include "../../include/dmt.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+using namespace dmt;
+
+namespace {
+
+struct DmtError : std::runtime_error {
+    int code;
+    DmtError(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+#define CK(call)                                                                                                   \
+    do {                                                                                                           \
+        cudaError_t e_ = (call);                                                                                   \
+        if (e_ != cudaSuccess)                                                                                     \
+            throw DmtError(DMT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                      \
+    } while (0)
+#define REQUIRE(cond, code, msg)                                                                                   \
+    do {                                                                                                           \
+        if (!(cond)) throw DmtError(code, msg);                                                                    \
+    } while (0)
+
+std::string g_create_error;
+
+struct ModelDims { int D, DW, NPAR; bool constdiff; };
+bool model_dims(int model, ModelDims &md) {
+    switch (model) {
+    case M_FHN: md = {Model<M_FHN>::D, Model<M_FHN>::DW, Model<M_FHN>::NPAR, Model<M_FHN>::CONSTDIFF}; return true;
+    case M_LV: md = {Model<M_LV>::D, Model<M_LV>::DW, Model<M_LV>::NPAR, Model<M_LV>::CONSTDIFF}; return true;
+    case M_LORENZ: md = {Model<M_LORENZ>::D, Model<M_LORENZ>::DW, Model<M_LORENZ>::NPAR, Model<M_LORENZ>::CONSTDIFF}; return true;
+    case M_PROK: md = {Model<M_PROK>::D, Model<M_PROK>::DW, Model<M_PROK>::NPAR, Model<M_PROK>::CONSTDIFF}; return true;
+    case M_JR: md = {Model<M_JR>::D, Model<M_JR>::DW, Model<M_JR>::NPAR, Model<M_JR>::CONSTDIFF}; return true;
+    case M_OU2: md = {Model<M_OU2>::D, Model<M_OU2>::DW, Model<M_OU2>::NPAR, Model<M_OU2>::CONSTDIFF}; return true;
+    }
+    return false;
+}
+
+template <class T> struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    void alloc(size_t count, bool zero = true) {
+        release();
+        n = count;
+        if (count) {
+            CK(cudaMalloc(&p, count * sizeof(T)));
+            if (zero) CK(cudaMemset(p, 0, count * sizeof(T)));
+        }
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { release(); }
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+};
+
+struct Layout {
+    bool set = false;
+    int nb = 0;
+    std::vector<int> i0, i1;
+    std::vector<uint8_t> last;
+    DevBuf<int> d_i0, d_i1;
+    DevBuf<uint8_t> d_last, d_ok, d_last_acc, d_acc_hist;
+    DevBuf<double> d_rho, d_ll, d_ll_hist;
+    LayoutDev dev{};
+};
+
+// ---- NCCL, resolved at run time so that libdmt.so has no link-time dependency on it
+struct NcclApi {
+    void *h = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, struct UidByValue, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+struct UidByValue { char internal[128]; };
+NcclApi g_nccl;
+void load_nccl() {
+    if (g_nccl.h) return;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names) {
+        g_nccl.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.h) break;
+    }
+    REQUIRE(g_nccl.h, DMT_ERR_NCCL, std::string("dlopen(libnccl.so.2) failed: ") + dlerror());
+    g_nccl.GetUniqueId = (int (*)(void *))dlsym(g_nccl.h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void **, int, UidByValue, int))dlsym(g_nccl.h, "ncclCommInitRank");
+    g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(g_nccl.h, "ncclAllReduce");
+    g_nccl.CommDestroy = (int (*)(void *))dlsym(g_nccl.h, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char *(*)(int))dlsym(g_nccl.h, "ncclGetErrorString");
+    REQUIRE(g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.CommDestroy, DMT_ERR_NCCL, "NCCL symbols missing");
+}
+#define NCK(call)                                                                                                  \
+    do {                                                                                                           \
+        int r_ = (call);                                                                                           \
+        if (r_ != 0)                                                                                               \
+            throw DmtError(DMT_ERR_NCCL, std::string(#call) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "nccl error")); \
+    } while (0)
+
+} // namespace
+
+struct dmt_ctx {
+    dmt_config cfg{};
+    ModelDims md{};
+    int D = 0, DW = 0, NPAR = 0, NH = 0, NG = 0, NAUX = 0, NOBS = 0;
+    int K = 0, M = 0, P = 0, m = 0, NT = 0, NTb = 0, S = 0, NP = 0;
+    std::vector<int> nsteps, tile0, step0, pt0, ppb_tile0;
+    cudaStream_t stream = nullptr;
+    DevCtx dev{};
+    std::vector<Layout> layouts;
+    std::string err;
+    // device storage
+    DevBuf<int> d_tile0, d_step0, d_pt0, d_nsteps, d_ppb_tile0, d_pset;
+    DevBuf<double> d_dt, d_sqdt, d_X, d_W, d_X0;
+    DevBuf<uint8_t> d_parX, d_parW, d_parP[2];
+    DevBuf<double> d_G[2][2], d_c0[2][2], d_theta[2][2], d_aux[2][2], d_obs[2], d_vart[2];
+    DevBuf<double> d_scratch, d_partial, d_stats;
+    DevBuf<uint8_t> d_mask;
+    void *nccl_comm = nullptr;
+    int n_ranks = 1;
+
+    double *scratch(size_t n) {
+        if (d_scratch.n < n) d_scratch.alloc(n, false);
+        return d_scratch.p;
+    }
+};
+
+namespace {
+
+Layout &layout_of(dmt_ctx *c, int id) {
+    REQUIRE(id >= 0 && id < (int)c->layouts.size(), DMT_ERR_ARG, "layout index out of range");
+    REQUIRE(c->layouts[id].set, DMT_ERR_STATE, "layout not registered (dmt_set_blocks)");
+    return c->layouts[id];
+}
+
+void check_side(dmt_ctx *c, int side) {
+    REQUIRE(side == 0 || side == 1, DMT_ERR_ARG, "side must be 0 (accepted) or 1 (proposal)");
+}
+void check_law_side(dmt_ctx *c, int side) {
+    check_side(c, side);
+    REQUIRE(side == 0 || c->cfg.two_sided_laws, DMT_ERR_STATE, "proposal laws not allocated (dmt_config.two_sided_laws = 0)");
+}
+void check_range(dmt_ctx *c, int k0, int k1) { REQUIRE(0 <= k0 && k0 <= k1 && k1 < c->K, DMT_ERR_ARG, "interval range out of bounds"); }
+
+dim3 chain_grid(dmt_ctx *c, int ny, int tpb) { return dim3((c->M + tpb - 1) / tpb, ny, 1); }
+dim3 pset_grid(dmt_ctx *c, int ny, int tpb, int nz = 1) { return dim3((c->P + tpb - 1) / tpb, ny, nz); }
+
+template <int OP> void launch_fwd(dmt_ctx *c, Layout &L, const FwdArgs &fa) {
+    dim3 grid = chain_grid(c, L.nb, FWD_TPB);
+#define DMT_CASE(MID)                                                                                              \
+    case MID: fwd_kernel<Model<MID>, OP><<<grid, FWD_TPB, 0, c->stream>>>(c->dev, L.dev, fa); break;
+    switch (c->cfg.model) {
+        DMT_CASE(M_FHN) DMT_CASE(M_LV) DMT_CASE(M_LORENZ) DMT_CASE(M_PROK) DMT_CASE(M_JR) DMT_CASE(M_OU2)
+    }
+#undef DMT_CASE
+    CK(cudaGetLastError());
+}
+
+void launch_bwd(dmt_ctx *c, Layout &L, int side_mask) {
+    dim3 grid = pset_grid(c, L.nb, BWD_TPB, c->cfg.two_sided_laws ? 2 : 1);
+#define DMT_CASE(MID)                                                                                              \
+    case MID: bwd_kernel<Model<MID>><<<grid, BWD_TPB, 0, c->stream>>>(c->dev, L.dev, side_mask); break;
+    switch (c->cfg.model) {
+        DMT_CASE(M_FHN) DMT_CASE(M_LV) DMT_CASE(M_LORENZ) DMT_CASE(M_PROK) DMT_CASE(M_JR) DMT_CASE(M_OU2)
+    }
+#undef DMT_CASE
+    CK(cudaGetLastError());
+}
+
+// dst record arrays [K][NREC][P] (per slot, resolved by the law parity of `store`): write ncomp components at offset
+// `off` for k = k0..k1 from src [nk or 1][ncomp][P]
+__global__ void put_record_kernel(const DevCtx cx, int side, int store, double *rec0, double *rec1, int NREC, int off, int ncomp,
+                                  int k0, int k1, const double *src, int bcast_k) {
+    const int ps = blockIdx.x * blockDim.x + threadIdx.x, k = k0 + blockIdx.y;
+    if (ps >= cx.P || k > k1) return;
+    const size_t P = cx.P;
+    const int slot = side ^ cx.parP[store][(size_t)k * P + ps];
+    double *dst = slot ? rec1 : rec0;
+    for (int q = 0; q < ncomp; q++)
+        dst[((size_t)k * NREC + off + q) * P + ps] = src[((size_t)(bcast_k ? 0 : (k - k0)) * ncomp + q) * P + ps];
+}
+// accepted -> proposal copy of a whole record (equalize_*)
+__global__ void copy_record_kernel(const DevCtx cx, int store, double *rec0, double *rec1, int NREC, int k0, int k1) {
+    const int ps = blockIdx.x * blockDim.x + threadIdx.x, k = k0 + blockIdx.y;
+    if (ps >= cx.P || k > k1) return;
+    const size_t P = cx.P;
+    const int sa = cx.parP[store][(size_t)k * P + ps];
+    const double *src = sa ? rec1 : rec0;
+    double *dst = sa ? rec0 : rec1;
+    for (int q = 0; q < NREC; q++) dst[((size_t)k * NREC + q) * P + ps] = src[((size_t)k * NREC + q) * P + ps];
+}
+
+void put_record(dmt_ctx *c, int side, int store, double *rec0, double *rec1, int NREC, int off, int ncomp, int k0, int k1,
+                const double *host, bool bcast_k) {
+    const size_t nk = bcast_k ? 1 : (size_t)(k1 - k0 + 1);
+    const size_t n = nk * ncomp * c->P;
+    double *tmp = c->scratch(n);
+    CK(cudaMemcpyAsync(tmp, host, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    put_record_kernel<<<pset_grid(c, k1 - k0 + 1, 128), 128, 0, c->stream>>>(c->dev, side, store, rec0, rec1, NREC, off, ncomp, k0,
+                                                                             k1, tmp, bcast_k ? 1 : 0);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream)); // the host buffer is the caller's; scratch is reused
+}
+
+void rebuild_ppb_store(dmt_ctx *c) {
+    // intervals that end a non-terminal block in ANY layout need a blocking-law guiding term (P_last, src/block.jl:68)
+    std::vector<int> t0(c->K, -1);
+    int nt = 0;
+    std::vector<char> need(c->K, 0);
+    for (auto &L : c->layouts)
+        if (L.set)
+            for (int b = 0; b < L.nb; b++)
+                if (!L.last[b]) need[L.i1[b]] = 1;
+    for (int k = 0; k < c->K; k++)
+        if (need[k]) { t0[k] = nt; nt += (c->nsteps[k] + 3) / 4; }
+    if (t0 == c->ppb_tile0 && nt == c->NTb) return;
+    c->ppb_tile0 = t0;
+    c->NTb = nt;
+    CK(cudaMemcpy(c->d_ppb_tile0.p, t0.data(), sizeof(int) * c->K, cudaMemcpyHostToDevice));
+    for (int s = 0; s < (c->cfg.two_sided_laws ? 2 : 1); s++) {
+        c->d_G[s][1].alloc((size_t)std::max(nt, 1) * c->NG * c->P * 4);
+        c->dev.G[s][1] = c->d_G[s][1].p;
+    }
+    c->dev.NTb = nt;
+}
+
+void fill_stats(dmt_ctx *c, Layout &L, double *host_out /* [2+3nb] */) {
+    const int ncta = (c->M + 255) / 256;
+    if (c->d_partial.n < (size_t)3 * L.nb * ncta) c->d_partial.alloc((size_t)3 * L.nb * ncta);
+    if (c->d_stats.n < (size_t)(2 + 3 * L.nb)) c->d_stats.alloc(2 + 3 * L.nb);
+    reduce_stats_kernel<<<dim3(ncta, L.nb), 256, 0, c->stream>>>(L.d_ll.p, L.d_last_acc.p, c->M, L.nb, c->d_partial.p);
+    CK(cudaGetLastError());
+    finish_stats_kernel<<<1, 64, 0, c->stream>>>(c->d_partial.p, ncta, L.nb, c->d_stats.p);
+    CK(cudaGetLastError());
+    if (host_out) {
+        CK(cudaMemcpyAsync(host_out, c->d_stats.p, sizeof(double) * (2 + 3 * L.nb), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+}
+
+template <class F> int32_t guarded(dmt_ctx *ctx, F &&f) {
+    if (!ctx) return DMT_ERR_ARG;
+    try {
+        CK(cudaSetDevice(ctx->cfg.device));
+        f();
+        return DMT_OK;
+    } catch (const DmtError &e) {
+        ctx->err = e.what();
+        return e.code;
+    } catch (const std::exception &e) {
+        ctx->err = e.what();
+        return DMT_ERR_STATE;
+    }
+}
+
+} // namespace
+
+// =============================================================================================================== API
+extern "C" {
+
+int32_t dmt_version(void) { return 100; }
+
+int32_t dmt_model_dims(int32_t model, int32_t *d, int32_t *dw, int32_t *npar, int32_t *constdiff) {
+    ModelDims md;
+    if (!model_dims(model, md)) return DMT_ERR_ARG;
+    if (d) *d = md.D;
+    if (dw) *dw = md.DW;
+    if (npar) *npar = md.NPAR;
+    if (constdiff) *constdiff = md.constdiff ? 1 : 0;
+    return DMT_OK;
+}
+
+const char *dmt_last_error(const dmt_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int32_t dmt_create(const dmt_config *cfg, const int32_t *n_pts, const double *tt, const int32_t *pset_of_chain, dmt_ctx **out) {
+    if (!cfg || !n_pts || !tt || !out) { g_create_error = "null argument"; return DMT_ERR_ARG; }
+    dmt_ctx *c = nullptr;
+    try {
+        c = new dmt_ctx();
+        c->cfg = *cfg;
+        REQUIRE(model_dims(cfg->model, c->md), DMT_ERR_ARG, "unknown model id");
+        c->D = c->md.D; c->DW = c->md.DW; c->NPAR = c->md.NPAR;
+        c->NH = c->D * (c->D + 1) / 2; c->NG = c->NH + c->D; c->NAUX = c->D * c->D + c->D + c->NH;
+        c->K = cfg->n_intervals; c->M = cfg->n_chains; c->P = cfg->n_psets; c->m = cfg->obs_dim;
+        REQUIRE(c->K >= 1 && c->M >= 1, DMT_ERR_ARG, "need n_intervals >= 1 and n_chains >= 1");
+        REQUIRE(c->P >= 1 && c->P <= c->M, DMT_ERR_ARG, "need 1 <= n_psets <= n_chains");
+        REQUIRE(c->m >= 1 && c->m <= c->D, DMT_ERR_ARG, "need 1 <= obs_dim <= d");
+        REQUIRE(cfg->n_layouts >= 1 && cfg->n_layouts <= 64, DMT_ERR_ARG, "need 1 <= n_layouts <= 64");
+        REQUIRE(cfg->artificial_noise > 0.0, DMT_ERR_ARG, "artificial_noise must be > 0");
+        c->NOBS = c->m * c->D + c->m * c->m + c->m;
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        REQUIRE(e == cudaSuccess && ndev > 0, DMT_ERR_CUDA, "no CUDA device: libdmt has no CPU fallback");
+        REQUIRE(cfg->device >= 0 && cfg->device < ndev, DMT_ERR_ARG, "device ordinal out of range");
+        CK(cudaSetDevice(cfg->device));
+        CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+
+        // ---- time grid -> tiles
+        const int K = c->K;
+        c->nsteps.resize(K); c->tile0.resize(K + 1); c->step0.resize(K + 1); c->pt0.resize(K + 1);
+        c->tile0[0] = c->step0[0] = c->pt0[0] = 0;
+        for (int k = 0; k < K; k++) {
+            REQUIRE(n_pts[k] >= 2, DMT_ERR_ARG, "every interval needs >= 2 grid points");
+            c->nsteps[k] = n_pts[k] - 1;
+            c->tile0[k + 1] = c->tile0[k] + (c->nsteps[k] + 3) / 4;
+            c->step0[k + 1] = c->step0[k] + c->nsteps[k];
+            c->pt0[k + 1] = c->pt0[k] + n_pts[k];
+        }
+        c->NT = c->tile0[K]; c->S = c->step0[K]; c->NP = c->pt0[K];
+        std::vector<double> dt((size_t)c->NT * 4, 0.0), sq((size_t)c->NT * 4, 0.0);
+        for (int k = 0; k < K; k++)
+            for (int j = 0; j < c->nsteps[k]; j++) {
+                const double h = tt[c->pt0[k] + j + 1] - tt[c->pt0[k] + j];
+                REQUIRE(h > 0.0, DMT_ERR_ARG, "time grid must be strictly increasing inside an interval");
+                dt[(size_t)c->tile0[k] * 4 + j] = h;
+                sq[(size_t)c->tile0[k] * 4 + j] = std::sqrt(h);
+            }
+        c->ppb_tile0.assign(K, -1);
+        std::vector<int> pset(c->M);
+        for (int i = 0; i < c->M; i++) {
+            pset[i] = pset_of_chain ? pset_of_chain[i] : (c->P == c->M ? i : 0);
+            REQUIRE(pset[i] >= 0 && pset[i] < c->P, DMT_ERR_ARG, "pset_of_chain entry out of range");
+            REQUIRE(pset_of_chain || c->P == c->M || c->P == 1, DMT_ERR_ARG, "pset_of_chain required when 1 < P < M");
+        }
+        c->d_tile0.alloc(K + 1); c->d_step0.alloc(K + 1); c->d_pt0.alloc(K + 1); c->d_nsteps.alloc(K); c->d_ppb_tile0.alloc(K);
+        c->d_pset.alloc(c->M); c->d_dt.alloc(dt.size()); c->d_sqdt.alloc(sq.size());
+        CK(cudaMemcpy(c->d_tile0.p, c->tile0.data(), sizeof(int) * (K + 1), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->d_step0.p, c->step0.data(), sizeof(int) * (K + 1), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->d_pt0.p, c->pt0.data(), sizeof(int) * (K + 1), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->d_nsteps.p, c->nsteps.data(), sizeof(int) * K, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->d_ppb_tile0.p, c->ppb_tile0.data(), sizeof(int) * K, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->d_pset.p, pset.data(), sizeof(int) * c->M, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->d_dt.p, dt.data(), sizeof(double) * dt.size(), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->d_sqdt.p, sq.data(), sizeof(double) * sq.size(), cudaMemcpyHostToDevice));
+
+        // ---- SoA containers (SamplingPair: accepted + proposal buffers)
+        const size_t M = c->M, P = c->P, NT = c->NT;
+        const size_t xb = NT * c->D * M * 4, wb = NT * c->DW * M * 4, x0b = (size_t)K * c->D * M;
+        c->d_X.alloc(2 * xb); c->d_W.alloc(2 * wb); c->d_X0.alloc(2 * x0b);
+        c->d_parX.alloc((size_t)K * M); c->d_parW.alloc((size_t)K * M);
+        const int nslot = cfg->two_sided_laws ? 2 : 1;
+        for (int st = 0; st < 2; st++) c->d_parP[st].alloc((size_t)K * P);
+        for (int s = 0; s < nslot; s++) {
+            c->d_G[s][0].alloc(NT * c->NG * P * 4);
+            c->d_G[s][1].alloc((size_t)c->NG * P * 4);
+            for (int st = 0; st < 2; st++) {
+                c->d_c0[s][st].alloc((size_t)K * P);
+                c->d_theta[s][st].alloc((size_t)K * c->NPAR * P);
+                c->d_aux[s][st].alloc((size_t)K * c->NAUX * P);
+            }
+            c->d_obs[s].alloc((size_t)K * c->NOBS * P);
+            c->d_vart[s].alloc((size_t)K * c->D * P);
+        }
+        DevCtx &d = c->dev;
+        d.M = c->M; d.P = c->P; d.K = K; d.NT = c->NT; d.NTb = 0; d.m = c->m; d.two_sided = cfg->two_sided_laws ? 1 : 0;
+        d.tile0 = c->d_tile0.p; d.step0 = c->d_step0.p; d.pt0 = c->d_pt0.p; d.nsteps = c->d_nsteps.p; d.ppb_tile0 = c->d_ppb_tile0.p;
+        d.dt = c->d_dt.p; d.sqdt = c->d_sqdt.p; d.pset = c->d_pset.p;
+        d.X = c->d_X.p; d.W = c->d_W.p; d.X0 = c->d_X0.p; d.Xbuf = xb; d.Wbuf = wb; d.X0buf = x0b;
+        d.parX = c->d_parX.p; d.parW = c->d_parW.p;
+        for (int st = 0; st < 2; st++) d.parP[st] = c->d_parP[st].p;
+        for (int s = 0; s < 2; s++) {
+            for (int st = 0; st < 2; st++) {
+                d.G[s][st] = c->d_G[s][st].p; d.c0[s][st] = c->d_c0[s][st].p;
+                d.theta[s][st] = c->d_theta[s][st].p; d.aux[s][st] = c->d_aux[s][st].p;
+            }
+            d.obs[s] = c->d_obs[s].p; d.vart[s] = c->d_vart[s].p;
+        }
+        d.eps = cfg->artificial_noise; d.seed = cfg->seed; d.chain_offset = (uint32_t)cfg->chain_offset;
+        c->layouts.resize(cfg->n_layouts);
+        CK(cudaDeviceSynchronize());
+        *out = c;
+        return DMT_OK;
+    } catch (const DmtError &e) {
+        g_create_error = e.what();
+        delete c;
+        return e.code;
+    } catch (const std::exception &e) {
+        g_create_error = e.what();
+        delete c;
+        return DMT_ERR_STATE;
+    }
+}
+
+int32_t dmt_destroy(dmt_ctx *ctx) {
+    if (!ctx) return DMT_OK;
+    cudaSetDevice(ctx->cfg.device);
+    if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->nccl_comm);
+    if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    delete ctx;
+    return DMT_OK;
+}
+
+int32_t dmt_sync(dmt_ctx *ctx) {
+    return guarded(ctx, [&] { CK(cudaStreamSynchronize(ctx->stream)); });
+}
+int32_t dmt_get_stream(dmt_ctx *ctx, void **s) {
+    return guarded(ctx, [&] { REQUIRE(s, DMT_ERR_ARG, "null"); *s = (void *)ctx->stream; });
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------- laws
+int32_t dmt_set_params(dmt_ctx *ctx, int32_t side, int32_t store_mask, int32_t k0, int32_t k1, const double *theta) {
+    return guarded(ctx, [&] {
+        check_law_side(ctx, side); check_range(ctx, k0, k1);
+        REQUIRE(theta && (store_mask & 3), DMT_ERR_ARG, "null theta or empty store mask");
+        for (int st = 0; st < 2; st++)
+            if ((store_mask >> st) & 1)
+                put_record(ctx, side, st, ctx->d_theta[0][st].p, ctx->d_theta[1][st].p, ctx->NPAR, 0, ctx->NPAR, k0, k1, theta, true);
+    });
+}
+
+int32_t dmt_set_aux(dmt_ctx *ctx, int32_t side, int32_t store, int32_t k0, int32_t k1, const double *B, const double *beta, const double *atil) {
+    return guarded(ctx, [&] {
+        check_law_side(ctx, side); check_range(ctx, k0, k1);
+        REQUIRE(store == 0 || store == 1, DMT_ERR_ARG, "store must be 0 (PP) or 1 (PPb)");
+        REQUIRE(B && beta && atil, DMT_ERR_ARG, "null aux array");
+        const int D = ctx->D, NH = ctx->NH, nk = k1 - k0 + 1;
+        const size_t P = ctx->P;
+        double *r0 = ctx->d_aux[0][store].p, *r1 = ctx->d_aux[1][store].p;
+        put_record(ctx, side, store, r0, r1, ctx->NAUX, 0, D * D, k0, k1, B, false);
+        put_record(ctx, side, store, r0, r1, ctx->NAUX, D * D, D, k0, k1, beta, false);
+        std::vector<double> packed((size_t)nk * NH * P); // symmetric part of atilde, packed upper
+        for (int k = 0; k < nk; k++)
+            for (int i = 0; i < D; i++)
+                for (int j = i; j < D; j++) {
+                    const int si = i * D - i * (i - 1) / 2 + (j - i);
+                    for (size_t p = 0; p < P; p++)
+                        packed[((size_t)k * NH + si) * P + p] =
+                            0.5 * (atil[((size_t)k * D * D + i * D + j) * P + p] + atil[((size_t)k * D * D + j * D + i) * P + p]);
+                }
+        put_record(ctx, side, store, r0, r1, ctx->NAUX, D * D + D, NH, k0, k1, packed.data(), false);
+    });
+}
+
+int32_t dmt_set_aux_linearised(dmt_ctx *ctx, int32_t side, int32_t store, int32_t k0, int32_t k1, const double *xbar) {
+    return guarded(ctx, [&] {
+        check_law_side(ctx, side); check_range(ctx, k0, k1);
+        REQUIRE(store == 0 || store == 1, DMT_ERR_ARG, "store must be 0 (PP) or 1 (PPb)");
+        REQUIRE(xbar, DMT_ERR_ARG, "null xbar");
+        const size_t n = (size_t)(k1 - k0 + 1) * ctx->D * ctx->P;
+        double *tmp = ctx->scratch(n);
+        CK(cudaMemcpyAsync(tmp, xbar, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        dim3 grid = pset_grid(ctx, k1 - k0 + 1, 128);
+#define DMT_CASE(MID)                                                                                              \
+    case MID: aux_linearise_kernel<Model<MID>><<<grid, 128, 0, ctx->stream>>>(ctx->dev, side, store, k0, k1, tmp); break;
+        switch (ctx->cfg.model) {
+            DMT_CASE(M_FHN) DMT_CASE(M_LV) DMT_CASE(M_LORENZ) DMT_CASE(M_PROK) DMT_CASE(M_JR) DMT_CASE(M_OU2)
+        }
+#undef DMT_CASE
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+int32_t dmt_set_obs(dmt_ctx *ctx, int32_t side, int32_t k0, int32_t k1, const double *L, const double *Sigma, const double *v) {
+    return guarded(ctx, [&] {
+        check_law_side(ctx, side); check_range(ctx, k0, k1);
+        REQUIRE(L && Sigma && v, DMT_ERR_ARG, "null observation array");
+        const int m = ctx->m, D = ctx->D;
+        double *r0 = ctx->d_obs[0].p, *r1 = ctx->d_obs[1].p;
+        put_record(ctx, side, 0, r0, r1, ctx->NOBS, 0, m * D, k0, k1, L, false);
+        put_record(ctx, side, 0, r0, r1, ctx->NOBS, m * D, m * m, k0, k1, Sigma, false);
+        put_record(ctx, side, 0, r0, r1, ctx->NOBS, m * D + m * m, m, k0, k1, v, false);
+    });
+}
+
+int32_t dmt_equalize_laws(dmt_ctx *ctx, int32_t store_mask, int32_t k0, int32_t k1) {
+    return guarded(ctx, [&] {
+        check_law_side(ctx, 1); check_range(ctx, k0, k1);
+        dim3 grid = pset_grid(ctx, k1 - k0 + 1, 128);
+        for (int st = 0; st < 2; st++) {
+            if (!((store_mask >> st) & 1)) continue;
+            copy_record_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->dev, st, ctx->d_theta[0][st].p, ctx->d_theta[1][st].p, ctx->NPAR, k0, k1);
+            copy_record_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->dev, st, ctx->d_aux[0][st].p, ctx->d_aux[1][st].p, ctx->NAUX, k0, k1);
+            if (st == 0) copy_record_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->dev, 0, ctx->d_obs[0].p, ctx->d_obs[1].p, ctx->NOBS, k0, k1);
+        }
+        CK(cudaGetLastError());
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------------------- layouts
+int32_t dmt_set_blocks(dmt_ctx *ctx, int32_t layout, int32_t n_blocks, const int32_t *i0, const int32_t *i1, const double *rho,
+                       const uint8_t *last, int32_t ll_hist_len) {
+    return guarded(ctx, [&] {
+        REQUIRE(layout >= 0 && layout < (int)ctx->layouts.size(), DMT_ERR_ARG, "layout index out of range");
+        REQUIRE(n_blocks >= 1 && n_blocks <= 64 && i0 && i1 && rho, DMT_ERR_ARG, "need 1 <= n_blocks <= 64 and non-null ranges/rho");
+        Layout &L = ctx->layouts[layout];
+        std::vector<uint8_t> lst(n_blocks);
+        for (int b = 0; b < n_blocks; b++) {
+            lst[b] = last ? (last[b] ? 1 : 0) : (b == n_blocks - 1 ? 1 : 0); // BlockCollection: i == N (src/block_collection.jl:29)
+            REQUIRE(0 <= i0[b] && i0[b] <= i1[b] && i1[b] < ctx->K, DMT_ERR_ARG, "block range out of bounds");
+            // a non-terminal block needs >= 2 intervals: the reference indexes b.PP[1] and XX[end-1] (src/block.jl:164,177)
+            REQUIRE(lst[b] || i1[b] > i0[b], DMT_ERR_ARG, "a non-terminal block must span at least 2 intervals");
+            REQUIRE(lst[b] || ctx->P == ctx->M, DMT_ERR_UNSUPPORTED,
+                    "blocking freezes a per-recording artificial observation: needs n_psets == n_chains");
+            REQUIRE(std::abs(rho[b]) <= 1.0, DMT_ERR_ARG, "rho must be in [-1, 1]");
+        }
+        const size_t M = ctx->M;
+        L.nb = n_blocks;
+        L.i0.assign(i0, i0 + n_blocks); L.i1.assign(i1, i1 + n_blocks); L.last = lst;
+        L.d_i0.alloc(n_blocks); L.d_i1.alloc(n_blocks); L.d_last.alloc(n_blocks); L.d_rho.alloc(n_blocks);
+        L.d_ll.alloc(2 * n_blocks * M); L.d_ok.alloc(n_blocks * M); L.d_last_acc.alloc(n_blocks * M);
+        CK(cudaMemcpy(L.d_i0.p, i0, sizeof(int) * n_blocks, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(L.d_i1.p, i1, sizeof(int) * n_blocks, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(L.d_last.p, lst.data(), n_blocks, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(L.d_rho.p, rho, sizeof(double) * n_blocks, cudaMemcpyHostToDevice));
+        {   // Block ctor: ll = -Inf (src/block.jl:74)
+            std::vector<double> ninf(2 * n_blocks * M, -INFINITY);
+            CK(cudaMemcpy(L.d_ll.p, ninf.data(), sizeof(double) * ninf.size(), cudaMemcpyHostToDevice));
+        }
+        const int hl_req = ll_hist_len >= 0 ? ll_hist_len : ctx->cfg.ll_hist_len;
+        const size_t hl = hl_req > 0 ? hl_req : 0;
+        if (hl) { L.d_acc_hist.alloc(hl * n_blocks * M); L.d_ll_hist.alloc(hl * 2 * n_blocks * M); }
+        L.dev.nb = n_blocks; L.dev.id = layout;
+        L.dev.i0 = L.d_i0.p; L.dev.i1 = L.d_i1.p; L.dev.last = L.d_last.p; L.dev.rho = L.d_rho.p;
+        L.dev.ll = L.d_ll.p; L.dev.ok = L.d_ok.p; L.dev.last_acc = L.d_last_acc.p;
+        L.dev.acc_hist = hl ? L.d_acc_hist.p : nullptr; L.dev.ll_hist = hl ? L.d_ll_hist.p : nullptr; L.dev.hist_len = (int)hl;
+        L.set = true;
+        rebuild_ppb_store(ctx);
+    });
+}
+
+int32_t dmt_set_rho(dmt_ctx *ctx, int32_t layout, const double *rho) {
+    return guarded(ctx, [&] {
+        Layout &L = layout_of(ctx, layout);
+        REQUIRE(rho, DMT_ERR_ARG, "null rho");
+        CK(cudaMemcpyAsync(L.d_rho.p, rho, sizeof(double) * L.nb, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------------------- paths
+int32_t dmt_set_start(dmt_ctx *ctx, const double *x0) {
+    return guarded(ctx, [&] {
+        REQUIRE(x0, DMT_ERR_ARG, "null x0");
+        const size_t n = (size_t)ctx->D * ctx->M;
+        for (int s = 0; s < 2; s++) // interval 0 is the head of both X0 buffers
+            CK(cudaMemcpyAsync(ctx->d_X0.p + s * ctx->dev.X0buf, x0, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+static void xfer_paths(dmt_ctx *ctx, int side, double *host, bool is_x, bool upload) {
+    check_side(ctx, side);
+    REQUIRE(host, DMT_ERR_ARG, "null host array");
+    const size_t n = is_x ? (size_t)ctx->NP * ctx->D * ctx->M : (size_t)ctx->S * ctx->DW * ctx->M;
+    DevBuf<double> nat;
+    nat.alloc(n, false);
+    if (upload) CK(cudaMemcpyAsync(nat.p, host, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    dim3 grid = chain_grid(ctx, ctx->K, 128);
+    if (is_x) xfer_X_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->dev, side, ctx->D, nat.p, upload ? 1 : 0);
+    else xfer_W_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->dev, side, ctx->DW, nat.p, upload ? 1 : 0);
+    CK(cudaGetLastError());
+    if (!upload) CK(cudaMemcpyAsync(host, nat.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+}
+int32_t dmt_set_X(dmt_ctx *ctx, int32_t side, const double *X) { return guarded(ctx, [&] { xfer_paths(ctx, side, (double *)X, true, true); }); }
+int32_t dmt_get_X(dmt_ctx *ctx, int32_t side, double *X) { return guarded(ctx, [&] { xfer_paths(ctx, side, X, true, false); }); }
+int32_t dmt_set_W(dmt_ctx *ctx, int32_t side, const double *W) { return guarded(ctx, [&] { xfer_paths(ctx, side, (double *)W, false, true); }); }
+int32_t dmt_get_W(dmt_ctx *ctx, int32_t side, double *W) { return guarded(ctx, [&] { xfer_paths(ctx, side, W, false, false); }); }
+
+int32_t dmt_init_paths(dmt_ctx *ctx, int32_t layout, uint32_t iter0, int32_t max_tries, int32_t *n_failed) {
+    return guarded(ctx, [&] {
+        Layout &L = layout_of(ctx, layout);
+        REQUIRE(L.nb == 1 && L.last[0] && L.i0[0] == 0 && L.i1[0] == ctx->K - 1, DMT_ERR_ARG,
+                "init_paths needs a layout made of one terminal block over all intervals");
+        REQUIRE(max_tries >= 1, DMT_ERR_ARG, "max_tries must be >= 1");
+        CK(cudaMemsetAsync(L.d_ok.p, 0, L.d_ok.n, ctx->stream));
+        std::vector<uint8_t> ok(L.d_ok.n);
+        int bad = 0;
+        for (int t = 0; t < max_tries; t++) { // while true: forward_guide!(...) && return   (src/sampling_unit.jl:84-86)
+            FwdArgs fa{iter0 + (uint32_t)t, 0, 0, 0, nullptr};
+            launch_fwd<OP_INIT>(ctx, L, fa);
+            CK(cudaMemcpyAsync(ok.data(), L.d_ok.p, ok.size(), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            bad = 0;
+            for (uint8_t o : ok) bad += !o;
+            if (!bad) break;
+        }
+        copy_acc_to_prop_kernel<<<chain_grid(ctx, ctx->K, 128), 128, 0, ctx->stream>>>(ctx->dev, ctx->D, ctx->DW);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (n_failed) *n_failed = bad;
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------------------- hot path
+int32_t dmt_set_artificial_obs(dmt_ctx *ctx, int32_t layout) {
+    return guarded(ctx, [&] {
+        Layout &L = layout_of(ctx, layout);
+        set_artificial_obs_kernel<<<chain_grid(ctx, L.nb, 128), 128, 0, ctx->stream>>>(ctx->dev, L.dev, ctx->D);
+        CK(cudaGetLastError());
+    });
+}
+
+int32_t dmt_recompute_guiding_term(dmt_ctx *ctx, int32_t layout, int32_t which) {
+    return guarded(ctx, [&] {
+        Layout &L = layout_of(ctx, layout);
+        REQUIRE(which >= 1 && which <= 3, DMT_ERR_ARG, "which must be DMT_P_ONLY, DMT_PO_ONLY or DMT_P_BOTH");
+        if (which & 2) check_law_side(ctx, 1);
+        launch_bwd(ctx, L, which);
+    });
+}
+
+int32_t dmt_find_W_for_X(dmt_ctx *ctx, int32_t layout) {
+    return guarded(ctx, [&] { launch_fwd<OP_INVSOLVE>(ctx, layout_of(ctx, layout), FwdArgs{0, 0, 0, 0, nullptr}); });
+}
+int32_t dmt_loglikhd(dmt_ctx *ctx, int32_t layout, int32_t side, int32_t skip) {
+    return guarded(ctx, [&] {
+        check_law_side(ctx, side);
+        REQUIRE(skip >= 0, DMT_ERR_ARG, "skip must be >= 0");
+        launch_fwd<OP_LOGLIK>(ctx, layout_of(ctx, layout), FwdArgs{0, side, 0, skip, nullptr});
+    });
+}
+int32_t dmt_find_W_and_loglikhd(dmt_ctx *ctx, int32_t layout) {
+    return guarded(ctx, [&] { launch_fwd<OP_INVSOLVE_LL>(ctx, layout_of(ctx, layout), FwdArgs{0, 0, 0, 0, nullptr}); });
+}
+
+int32_t dmt_draw_proposal_path(dmt_ctx *ctx, int32_t layout, uint32_t iter, const double *Z) {
+    return guarded(ctx, [&] {
+        Layout &L = layout_of(ctx, layout);
+        FwdArgs fa{iter, 0, 0, 0, nullptr};
+        if (Z) {
+            const size_t n = (size_t)ctx->S * ctx->DW * ctx->M;
+            double *tmp = ctx->scratch(n);
+            CK(cudaMemcpyAsync(tmp, Z, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            fa.Z = tmp;
+        }
+        launch_fwd<OP_DRAW>(ctx, L, fa);
+        if (Z) CK(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+int32_t dmt_recompute_path(dmt_ctx *ctx, int32_t layout, int32_t law_side, int32_t noise_side, int32_t skip) {
+    return guarded(ctx, [&] {
+        check_law_side(ctx, law_side); check_side(ctx, noise_side);
+        REQUIRE(skip >= 0, DMT_ERR_ARG, "skip must be >= 0");
+        launch_fwd<OP_RECOMPUTE>(ctx, layout_of(ctx, layout), FwdArgs{0, law_side, noise_side, skip, nullptr});
+    });
+}
+
+int32_t dmt_set_proposal_law(dmt_ctx *ctx, int32_t layout, int32_t critical_change, int32_t skip) {
+    return guarded(ctx, [&] {
+        check_law_side(ctx, 1);
+        Layout &L = layout_of(ctx, layout);
+        if (critical_change) launch_bwd(ctx, L, DMT_PO_ONLY);                           // src/biblock.jl:342
+        launch_fwd<OP_RECOMPUTE>(ctx, L, FwdArgs{0, 1, 0, skip, nullptr});              // src/biblock.jl:343
+    });
+}
+
+int32_t dmt_accept_reject_path(dmt_ctx *ctx, int32_t layout, uint32_t iter, const double *E) {
+    return guarded(ctx, [&] {
+        Layout &L = layout_of(ctx, layout);
+        const double *dE = nullptr;
+        if (E) {
+            const size_t n = (size_t)L.nb * ctx->M;
+            double *tmp = ctx->scratch(n);
+            CK(cudaMemcpyAsync(tmp, E, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            dE = tmp;
+        }
+        accept_kernel<<<chain_grid(ctx, L.nb, 128), 128, 0, ctx->stream>>>(ctx->dev, L.dev, iter, dE);
+        CK(cudaGetLastError());
+        if (E) CK(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+int32_t dmt_swap(dmt_ctx *ctx, int32_t layout, int32_t what, const uint8_t *chain_mask) {
+    return guarded(ctx, [&] {
+        Layout &L = layout_of(ctx, layout);
+        REQUIRE(what > 0 && what < 16, DMT_ERR_ARG, "empty or unknown swap mask");
+        const uint8_t *dm = nullptr;
+        if (chain_mask) {
+            REQUIRE(!(what & DMT_SWAP_PP) || ctx->P == ctx->M, DMT_ERR_UNSUPPORTED, "per-chain swap_PP! needs n_psets == n_chains");
+            if (ctx->d_mask.n < (size_t)ctx->M) ctx->d_mask.alloc(ctx->M);
+            CK(cudaMemcpyAsync(ctx->d_mask.p, chain_mask, ctx->M, cudaMemcpyHostToDevice, ctx->stream));
+            dm = ctx->d_mask.p;
+        }
+        if (what & (DMT_SWAP_XX | DMT_SWAP_WW | DMT_SWAP_LL))
+            swap_paths_kernel<<<chain_grid(ctx, L.nb, 128), 128, 0, ctx->stream>>>(ctx->dev, L.dev, what, dm);
+        if (what & DMT_SWAP_PP) {
+            check_law_side(ctx, 1);
+            swap_laws_kernel<<<pset_grid(ctx, L.nb, 128), 128, 0, ctx->stream>>>(ctx->dev, L.dev, dm);
+        }
+        CK(cudaGetLastError());
+        if (chain_mask) CK(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+int32_t dmt_save_ll(dmt_ctx *ctx, int32_t layout, uint32_t iter) {
+    return guarded(ctx, [&] {
+        Layout &L = layout_of(ctx, layout);
+        REQUIRE(L.dev.hist_len > 0 && iter < (uint32_t)L.dev.hist_len, DMT_ERR_ARG, "iteration beyond ll_hist_len");
+        save_ll_kernel<<<chain_grid(ctx, L.nb, 128), 128, 0, ctx->stream>>>(ctx->dev, L.dev, iter);
+        CK(cudaGetLastError());
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------------------- read-back
+int32_t dmt_fetch_ll(dmt_ctx *ctx, int32_t layout, int32_t side, double *total, double *per_block) {
+    return guarded(ctx, [&] {
+        Layout &L = layout_of(ctx, layout);
+        check_side(ctx, side);
+        std::vector<double> out(2 + 3 * L.nb);
+        fill_stats(ctx, L, out.data());
+        if (total) *total = out[side];
+        if (per_block)
+            for (int b = 0; b < L.nb; b++) per_block[b] = out[2 + (1 + side) * L.nb + b];
+    });
+}
+
+int32_t dmt_get_ll(dmt_ctx *ctx, int32_t layout, int32_t side, double *ll) {
+    return guarded(ctx, [&] {
+        Layout &L = layout_of(ctx, layout);
+        check_side(ctx, side); REQUIRE(ll, DMT_ERR_ARG, "null");
+        const size_t n = (size_t)L.nb * ctx->M;
+        CK(cudaMemcpyAsync(ll, L.d_ll.p + side * n, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    });
+}
+int32_t dmt_set_ll(dmt_ctx *ctx, int32_t layout, int32_t side, const double *ll) {
+    return guarded(ctx, [&] {
+        Layout &L = layout_of(ctx, layout);
+        check_side(ctx, side); REQUIRE(ll, DMT_ERR_ARG, "null");
+        const size_t n = (size_t)L.nb * ctx->M;
+        CK(cudaMemcpyAsync(L.d_ll.p + side * n, ll, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    });
+}
+int32_t dmt_get_success(dmt_ctx *ctx, int32_t layout, uint8_t *ok) {
+    return guarded(ctx, [&] {
+        Layout &L = layout_of(ctx, layout);
+        REQUIRE(ok, DMT_ERR_ARG, "null");
+        CK(cudaMemcpyAsync(ok, L.d_ok.p, (size_t)L.nb * ctx->M, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    });
+}
+int32_t dmt_get_last_accept(dmt_ctx *ctx, int32_t layout, uint8_t *acc) {
+    return guarded(ctx, [&] {
+        Layout &L = layout_of(ctx, layout);
+        REQUIRE(acc, DMT_ERR_ARG, "null");
+        CK(cudaMemcpyAsync(acc, L.d_last_acc.p, (size_t)L.nb * ctx->M, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    });
+}
+int32_t dmt_get_accept_history(dmt_ctx *ctx, int32_t layout, uint32_t it0, uint32_t it1, uint8_t *acc) {
+    return guarded(ctx, [&] {
+        Layout &L = layout_of(ctx, layout);
+        REQUIRE(acc && it0 <= it1 && it1 < (uint32_t)L.dev.hist_len, DMT_ERR_ARG, "bad history range");
+        const size_t per = (size_t)L.nb * ctx->M;
+        CK(cudaMemcpyAsync(acc, L.d_acc_hist.p + it0 * per, (size_t)(it1 - it0 + 1) * per, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    });
+}
+int32_t dmt_get_ll_history(dmt_ctx *ctx, int32_t layout, int32_t side, uint32_t it0, uint32_t it1, double *ll) {
+    return guarded(ctx, [&] {
+        Layout &L = layout_of(ctx, layout);
+        check_side(ctx, side);
+        REQUIRE(ll && it0 <= it1 && it1 < (uint32_t)L.dev.hist_len, DMT_ERR_ARG, "bad history range");
+        const size_t per = (size_t)L.nb * ctx->M;
+        for (uint32_t it = it0; it <= it1; ++it)
+            CK(cudaMemcpyAsync(ll + (size_t)(it - it0) * per, L.d_ll_hist.p + ((size_t)it * 2 + side) * per, per * sizeof(double),
+                               cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    });
+}
+int32_t dmt_accept_counts(dmt_ctx *ctx, int32_t layout, uint32_t it0, uint32_t it1, int64_t *counts) {
+    return guarded(ctx, [&] {
+        Layout &L = layout_of(ctx, layout);
+        REQUIRE(counts && it0 <= it1 && it1 < (uint32_t)L.dev.hist_len, DMT_ERR_ARG, "bad history range");
+        DevBuf<unsigned long long> d;
+        d.alloc(L.nb);
+        accept_counts_kernel<<<chain_grid(ctx, L.nb, 128), 128, 0, ctx->stream>>>(L.d_acc_hist.p, L.nb, ctx->M, it0, it1, d.p);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(counts, d.p, sizeof(int64_t) * L.nb, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------------------- guiding term
+static void xfer_guiding(dmt_ctx *ctx, int side, int store, int k, double *H, double *F, double *c, bool upload) {
+    check_law_side(ctx, side); check_range(ctx, k, k);
+    REQUIRE(store == 0 || store == 1, DMT_ERR_ARG, "store must be 0 (PP) or 1 (PPb)");
+    REQUIRE(store == 0 || ctx->ppb_tile0[k] >= 0, DMT_ERR_STATE, "interval has no blocking law in any registered layout");
+    REQUIRE(H && F && c, DMT_ERR_ARG, "null");
+    const size_t n = ctx->nsteps[k] + 1, P = ctx->P, D = ctx->D;
+    DevBuf<double> dH, dF, dc;
+    dH.alloc(n * D * D * P, false); dF.alloc(n * D * P, false); dc.alloc(n * P, false);
+    if (upload) {
+        CK(cudaMemcpyAsync(dH.p, H, dH.n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(dF.p, F, dF.n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(dc.p, c, dc.n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    xfer_guiding_kernel<<<pset_grid(ctx, 1, 128), 128, 0, ctx->stream>>>(ctx->dev, side, store, k, ctx->D, dH.p, dF.p, dc.p, upload ? 1 : 0);
+    CK(cudaGetLastError());
+    if (!upload) {
+        CK(cudaMemcpyAsync(H, dH.p, dH.n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(F, dF.p, dF.n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(c, dc.p, dc.n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+}
+int32_t dmt_get_guiding_term(dmt_ctx *ctx, int32_t side, int32_t store, int32_t k, double *H, double *F, double *c) {
+    return guarded(ctx, [&] { xfer_guiding(ctx, side, store, k, H, F, c, false); });
+}
+int32_t dmt_upload_guiding_term(dmt_ctx *ctx, int32_t side, int32_t store, int32_t k, const double *H, const double *F, const double *c) {
+    return guarded(ctx, [&] { xfer_guiding(ctx, side, store, k, (double *)H, (double *)F, (double *)c, true); });
+}
+
+// ---------------------------------------------------------------------------------------------------------------- multi-GPU
+int32_t dmt_nccl_unique_id(uint8_t *id128) {
+    try {
+        REQUIRE(id128, DMT_ERR_ARG, "null");
+        load_nccl();
+        NCK(g_nccl.GetUniqueId(id128));
+        return DMT_OK;
+    } catch (const DmtError &e) {
+        g_create_error = e.what();
+        return e.code;
+    }
+}
+int32_t dmt_comm_init(dmt_ctx *ctx, int32_t n_ranks, int32_t rank, const uint8_t *id128) {
+    return guarded(ctx, [&] {
+        REQUIRE(id128 && n_ranks >= 1 && rank >= 0 && rank < n_ranks, DMT_ERR_ARG, "bad communicator arguments");
+        load_nccl();
+        UidByValue uid;
+        memcpy(uid.internal, id128, 128);
+        NCK(g_nccl.CommInitRank(&ctx->nccl_comm, n_ranks, uid, rank));
+        ctx->n_ranks = n_ranks;
+    });
+}
+int32_t dmt_allreduce_stats(dmt_ctx *ctx, int32_t layout, double *out) {
+    return guarded(ctx, [&] {
+        Layout &L = layout_of(ctx, layout);
+        REQUIRE(out, DMT_ERR_ARG, "null");
+        fill_stats(ctx, L, nullptr);
+        if (ctx->nccl_comm) // ONE small allreduce: [sum ll, sum ll°, accept counts per block]  
+            NCK(g_nccl.AllReduce(ctx->d_stats.p, ctx->d_stats.p, (size_t)(2 + L.nb), 8 /* ncclDouble */, 0 /* ncclSum */, ctx->nccl_comm, ctx->stream));
+        CK(cudaMemcpyAsync(out, ctx->d_stats.p, sizeof(double) * (2 + L.nb), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+} // extern "C"

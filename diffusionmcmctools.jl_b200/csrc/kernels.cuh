@@ -1,0 +1,920 @@
+// kernels.cuh — hand-written sm_100a kernels of the guided-proposal path update.
+//
+// DATA LAYOUT IN HBM.  Time is cut into TILES of 4 Euler–Maruyama steps that never straddle an
+// observation interval.  Every streamed array is  [tile][component][chain or pset][4 steps]  so that ONE LANE OWNS
+// ONE 32-BYTE DRAM SECTOR per component per tile and moves it with a single 256-bit LDG/STG.  This is the
+// [time][dim][chain] structure-of-arrays of the north star with the time axis blocked by 4: loads/stores of a warp
+// are still contiguous (32 lanes x 32 B = 1 KiB), but accepted/proposal buffer selection (per-chain parity bits,
+// the SoA form of the reference's pointer swaps, /root/reference/src/biblock.jl:148-173) and pset gathers become
+// sector-exact: no over-fetch on reads, no read-modify-write on writes.
+//   X  [2][NT][D ][M][4]   X[..][s] = state AFTER step 4*tile+s  (XX[k].x[2:end] of the reference)
+//   X0 [2][K ][D ][M]      first point of every interval          (XX[k].x[1])
+//   W  [2][NT][DW][M][4]   Wiener increments                      (WW[k])
+//   G  [slot][store] [NT or NTb][NH+D][P][4]   guiding term H (packed symmetric), F at the LEFT point of each step
+//   c0 [slot][store] [K][P]                     c at the interval start
+// parX/parW [K][M], parP [store][K][P]: which physical buffer/slot currently holds the ACCEPTED object.
+#pragma once
+#include "models.cuh"
+#include "philox.cuh"
+#include <stdint.h>
+
+namespace dmt {
+
+constexpr int FWD_TPB = 64;
+constexpr int BWD_TPB = 32;
+
+struct DevCtx {
+    int M, P, K, NT, NTb, m, two_sided;
+    const int *tile0;     // [K+1] first tile of interval k
+    const int *step0;     // [K+1] first (unpadded) step of interval k
+    const int *pt0;       // [K+1] first (unpadded) point of interval k
+    const int *nsteps;    // [K]
+    const int *ppb_tile0; // [K] first tile in the PPb store, -1 if interval k never ends a non-terminal block
+    const double *dt, *sqdt; // [NT*4] (padded like the tiles)
+    const int *pset;      // [M]
+    double *X, *W, *X0;
+    size_t Xbuf, Wbuf, X0buf; // buffer strides in doubles
+    uint8_t *parX, *parW;     // [K][M]
+    uint8_t *parP[2];         // [store] [K][P]
+    double *G[2][2];          // [slot][store]
+    double *c0[2][2];         // [slot][store] [K][P]
+    double *theta[2][2];      // [slot][store] [K][NPAR][P]
+    double *aux[2][2];        // [slot][store] [K][NAUX][P]   B (row-major d*d), beta (d), atilde (packed NH)
+    double *obs[2];           // [slot] [K][NOBS][P]          L (m*d), Sigma (m*m), v (m)
+    double *vart[2];          // [slot] [K][D][P]             artificial exact observation of the PPb law
+    double eps;
+    uint64_t seed;
+    uint32_t chain_offset;
+};
+
+struct LayoutDev {
+    int nb, id;
+    const int *i0, *i1;
+    const uint8_t *last;
+    const double *rho;
+    double *ll;        // [2][nb][M]
+    uint8_t *ok;       // [nb][M] success of the last forward op
+    uint8_t *last_acc; // [nb][M]
+    uint8_t *acc_hist; // [hist_len][nb][M] or null
+    double *ll_hist;   // [hist_len][2][nb][M] or null
+    int hist_len;
+};
+
+enum { OP_DRAW = 0, OP_RECOMPUTE = 1, OP_LOGLIK = 2, OP_INVSOLVE = 3, OP_INVSOLVE_LL = 4, OP_INIT = 5 };
+
+struct FwdArgs {
+    uint32_t iter;
+    int law_side, w_side, skip;
+    const double *Z; // device, [S][DW][M] standard normals or null
+};
+
+// ------------------------------------------------------------------------------------------- 256-bit sector access
+__device__ __forceinline__ void ld256(const double *p, double *v) { // streaming read-only sector
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ void ld256u(const double *p, double *v) { // chain-uniform data (dt, sqrt dt): keep in L1
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ void st256(double *p, const double *v) {
+    asm volatile("st.global.L1::no_allocate.v4.f64 [%4], {%0,%1,%2,%3};" ::"d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]), "l"(p) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// ------------------------------------------------------------------------------------------- one EM step's terms
+// r = F - H x ; guided drift gd = b + a r (A.3) ; integrand G = (b - btilde).r [- tr((a-at)H)/2 + r'(a-at)r/2] (A.4)
+template <class MD, bool WANT_G>
+__device__ __forceinline__ void guided_terms(const typename MD::Par &par, const typename MD::Diff &df, const double *Bm,
+                                             const double *beta, const double *at, const double *Hs, const double *F,
+                                             const double *x, double *gd, double &G) {
+    constexpr int D = MD::D, NH = D * (D + 1) / 2;
+    double r[D], b[D], ar[D];
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+        double s = F[i];
+#pragma unroll
+        for (int j = 0; j < D; j++) s = fma(-Hs[sidx<D>(i, j)], x[j], s);
+        r[i] = s;
+    }
+    MD::drift(par, x, b);
+    df.a_mul(r, ar);
+#pragma unroll
+    for (int i = 0; i < D; i++) gd[i] = b[i] + ar[i];
+    if (WANT_G) {
+        double g = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; i++) {
+            double bt = beta[i];
+#pragma unroll
+            for (int j = 0; j < D; j++) bt = fma(Bm[i * D + j], x[j], bt);
+            g = fma(b[i] - bt, r[i], g);
+        }
+        if (!MD::CONSTDIFF) {
+            double a[NH];
+            df.a_sym(a);
+            double tr = 0.0, q = 0.0;
+#pragma unroll
+            for (int i = 0; i < D; i++)
+#pragma unroll
+                for (int j = 0; j < D; j++) {
+                    double da = a[sidx<D>(i, j)] - at[sidx<D>(i, j)];
+                    tr = fma(da, Hs[sidx<D>(i, j)], tr);
+                    q = fma(r[i] * da, r[j], q);
+                }
+            g += -0.5 * tr + 0.5 * q;
+        }
+        G = g;
+    }
+}
+
+// =========================================================================================== K2/K3/K4/K5 forward kernel
+// One thread = one (chain, block).  grid = (ceil(M/TPB), n_blocks).  Replaces, per OP:
+//   OP_DRAW        draw_proposal_path!(bb)            src/biblock.jl:80-106   (pCN + guided EM + ll, fused; K3+K2+K4)
+//   OP_RECOMPUTE   recompute_path!(b°, b.WW; skip)    src/block.jl:161-187    (K2+K4)
+//   OP_LOGLIK      loglikhd!(b)                       src/block.jl:140-152    (K4)
+//   OP_INVSOLVE    find_W_for_X!(b)                   src/block.jl:120-131    (K5)
+//   OP_INVSOLVE_LL both of the above in one pass over X
+//   OP_INIT        init_paths! / draw_proposal_path!(u::SamplingUnit)  src/sampling_unit.jl:83-87,118-120 (fresh noise, in place)
+template <class MD, int OP>
+__global__ void __launch_bounds__(FWD_TPB) fwd_kernel(const DevCtx cx, const LayoutDev ly, const FwdArgs fa) {
+    constexpr int D = MD::D, DW = MD::DW, NPAR = MD::NPAR, NH = D * (D + 1) / 2, NG = NH + D, NAUX = D * D + D + NH;
+    constexpr bool READS_X = (OP == OP_LOGLIK || OP == OP_INVSOLVE || OP == OP_INVSOLVE_LL);
+    constexpr bool WRITES_X = (OP == OP_DRAW || OP == OP_RECOMPUTE || OP == OP_INIT);
+    constexpr bool READS_W = (OP == OP_DRAW || OP == OP_RECOMPUTE);
+    constexpr bool WRITES_W = (OP == OP_DRAW || OP == OP_INIT || OP == OP_INVSOLVE || OP == OP_INVSOLVE_LL);
+    constexpr bool WANT_LL = (OP != OP_INVSOLVE);
+    constexpr bool RNG = (OP == OP_DRAW || OP == OP_INIT);
+
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (c >= cx.M) return;
+    const size_t M = cx.M, P = cx.P;
+    if (OP == OP_INIT && ly.ok[(size_t)b * M + c]) return; // retry only the chains that failed so far
+    const int ps = cx.pset[c];
+    const int i0 = ly.i0[b], i1 = ly.i1[b];
+    const bool last = ly.last[b] != 0;
+
+    const int law_side = (OP == OP_RECOMPUTE || OP == OP_LOGLIK) ? fa.law_side : 0;
+    const int xin_side = law_side;                                 // start point / path that is read
+    const int xout_side = (OP == OP_DRAW) ? 1 : law_side;
+    const int win_side = (OP == OP_RECOMPUTE) ? fa.w_side : 0;
+    const int wout_side = (OP == OP_DRAW) ? 1 : 0;
+    const int ll_side = (OP == OP_DRAW) ? 1 : law_side;
+    const double rho = (OP == OP_DRAW) ? ly.rho[b] : 0.0;
+    const double crho = (OP == OP_DRAW) ? sqrt(1.0 - rho * rho) : 1.0;
+    const int skip = fa.skip;
+
+    double x[D];
+    {   // y1 = XX[1].x[1] of the block  (src/biblock.jl:96, src/block.jl:177)
+        const int sl = xin_side ^ cx.parX[(size_t)i0 * M + c];
+#pragma unroll
+        for (int i = 0; i < D; i++) x[i] = cx.X0[sl * cx.X0buf + ((size_t)i0 * D + i) * M + c];
+    }
+    double ll = 0.0;
+    bool ok = true;
+
+    for (int k = i0; k <= i1 && ok; ++k) {
+        const int store = (k == i1 && !last) ? 1 : 0; // P_last comes from PPb (src/block.jl:68)
+        const int slotL = law_side ^ cx.parP[store][(size_t)k * P + ps];
+        double th[NPAR];
+        {
+            const double *tp = cx.theta[slotL][store] + (size_t)k * NPAR * P + ps;
+#pragma unroll
+            for (int i = 0; i < NPAR; i++) th[i] = tp[(size_t)i * P];
+        }
+        const typename MD::Par par(th);
+        double Bm[D * D], beta[D], at[NH];
+        if (WANT_LL) {
+            const double *ap = cx.aux[slotL][store] + (size_t)k * NAUX * P + ps;
+#pragma unroll
+            for (int i = 0; i < D * D; i++) Bm[i] = ap[(size_t)i * P];
+#pragma unroll
+            for (int i = 0; i < D; i++) beta[i] = ap[(size_t)(D * D + i) * P];
+            if (!MD::CONSTDIFF) {
+#pragma unroll
+                for (int i = 0; i < NH; i++) at[i] = ap[(size_t)(D * D + D + i) * P];
+            }
+        }
+        const int nst = cx.nsteps[k];
+        const int t0 = cx.tile0[k];
+        const int gt0 = store ? cx.ppb_tile0[k] : t0;
+        const double *Gp = cx.G[slotL][store] + ((size_t)gt0 * NG * P + ps) * 4;
+        const size_t gstr = P * 4; // stride between components
+
+        if (WANT_LL && k == i0) { // loglikhd_obs(PP[1], y1) = -c - y'Hy/2 + F'y  (src/block.jl:178)
+            double g0[NG];
+#pragma unroll
+            for (int q = 0; q < NG; q++) g0[q] = Gp[(size_t)q * gstr];
+            double s = -cx.c0[slotL][store][(size_t)k * P + ps];
+#pragma unroll
+            for (int i = 0; i < D; i++) {
+                double hx = 0.0;
+#pragma unroll
+                for (int j = 0; j < D; j++) hx = fma(g0[sidx<D>(i, j)], x[j], hx);
+                s += x[i] * (g0[NH + i] - 0.5 * hx);
+            }
+            ll = s;
+        }
+
+        const uint8_t pw = cx.parW[(size_t)k * M + c], px = cx.parX[(size_t)k * M + c];
+        const double *Win = cx.W + (size_t)(win_side ^ pw) * cx.Wbuf + ((size_t)t0 * DW * M + c) * 4;
+        double *Wout = cx.W + (size_t)(wout_side ^ pw) * cx.Wbuf + ((size_t)t0 * DW * M + c) * 4;
+        const double *Xin = cx.X + (size_t)(xin_side ^ px) * cx.Xbuf + ((size_t)t0 * D * M + c) * 4;
+        double *Xout = cx.X + (size_t)(xout_side ^ px) * cx.Xbuf + ((size_t)t0 * D * M + c) * 4;
+        if (READS_X && k > i0) { // an existing path: interval k starts at ITS OWN XX[k].x[1]
+#pragma unroll
+            for (int i = 0; i < D; i++) x[i] = cx.X0[(size_t)(xin_side ^ px) * cx.X0buf + ((size_t)k * D + i) * M + c];
+        }
+        if (WRITES_X) { // XX°[k].x[1] = y1
+            double *x0p = cx.X0 + (size_t)(xout_side ^ px) * cx.X0buf + (size_t)k * D * M + c;
+#pragma unroll
+            for (int i = 0; i < D; i++) x0p[(size_t)i * M] = x[i];
+        }
+
+        const int ntl = (nst + 3) >> 2;
+        for (int q = 0; q < ntl; ++q) {
+            double g[NG][4], w[DW][4], xt[D][4], dt4[4], sq4[4];
+#pragma unroll
+            for (int i = 0; i < NG; i++) ld256(Gp + ((size_t)q * NG + i) * gstr, g[i]);
+            if (READS_W) {
+#pragma unroll
+                for (int j = 0; j < DW; j++) ld256(Win + ((size_t)q * DW + j) * M * 4, w[j]);
+            }
+            if (READS_X) {
+#pragma unroll
+                for (int i = 0; i < D; i++) ld256(Xin + ((size_t)q * D + i) * M * 4, xt[i]);
+            }
+            ld256u(cx.dt + (size_t)(t0 + q) * 4, dt4);
+            if (RNG) ld256u(cx.sqdt + (size_t)(t0 + q) * 4, sq4);
+            if (q + 2 < ntl) { // pull the tile after next into L2 while this one is computed
+#pragma unroll
+                for (int i = 0; i < NG; i++) prefetch_l2(Gp + ((size_t)(q + 2) * NG + i) * gstr);
+                if (READS_W) {
+#pragma unroll
+                    for (int j = 0; j < DW; j++) prefetch_l2(Win + ((size_t)(q + 2) * DW + j) * M * 4);
+                }
+                if (READS_X) {
+#pragma unroll
+                    for (int i = 0; i < D; i++) prefetch_l2(Xin + ((size_t)(q + 2) * D + i) * M * 4);
+                }
+            }
+            if (RNG) { // K3: dW° = rho dW + sqrt(1-rho^2) sqrt(dt) xi   (A.2)
+                double z[4 * DW];
+                if (fa.Z) {
+#pragma unroll
+                    for (int s = 0; s < 4; s++)
+#pragma unroll
+                        for (int j = 0; j < DW; j++) {
+                            const int i = 4 * q + s;
+                            z[s * DW + j] = (i < nst) ? fa.Z[((size_t)(cx.step0[k] + i) * DW + j) * M + c] : 0.0;
+                        }
+                } else {
+                    tile_normals<DW>(cx.seed, cx.chain_offset + (uint32_t)c, (uint32_t)(t0 + q), fa.iter, z);
+                }
+#pragma unroll
+                for (int s = 0; s < 4; s++)
+#pragma unroll
+                    for (int j = 0; j < DW; j++) {
+                        if (OP == OP_DRAW) w[j][s] = rho * w[j][s] + crho * sq4[s] * z[s * DW + j];
+                        else w[j][s] = sq4[s] * z[s * DW + j];
+                    }
+            }
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                const int i = 4 * q + s;
+                if (i < nst && ok) {
+                    double Hs[NH], F[D], gd[D], G = 0.0;
+#pragma unroll
+                    for (int a = 0; a < NH; a++) Hs[a] = g[a][s];
+#pragma unroll
+                    for (int a = 0; a < D; a++) F[a] = g[NH + a][s];
+                    const typename MD::Diff df(par, x);
+                    guided_terms<MD, WANT_LL>(par, df, Bm, beta, at, Hs, F, x, gd, G);
+                    if (WANT_LL && i < nst - skip) ll = fma(G, dt4[s], ll);
+                    double xn[D];
+                    if (WRITES_X) { // K2: x' = x + (b + a r) dt + sigma dW   (A.3)
+                        double dwv[DW], sw[D];
+#pragma unroll
+                        for (int j = 0; j < DW; j++) dwv[j] = w[j][s];
+                        df.sig_mul(dwv, sw);
+#pragma unroll
+                        for (int a = 0; a < D; a++) xn[a] = fma(gd[a], dt4[s], x[a]) + sw[a];
+                        bool fin = df.ok();
+#pragma unroll
+                        for (int a = 0; a < D; a++) fin = fin && isfinite(xn[a]);
+                        if (!(fin && MD::bound_ok(par, xn))) { ok = false; ll = -INFINITY; } // src/block.jl:181
+#pragma unroll
+                        for (int a = 0; a < D; a++) xt[a][s] = xn[a];
+                    } else {
+#pragma unroll
+                        for (int a = 0; a < D; a++) xn[a] = xt[a][s];
+                        if (OP == OP_INVSOLVE || OP == OP_INVSOLVE_LL) { // K5: dW = sigma^+ (x' - x - (b + a r) dt)   (A.5)
+                            double res[D], dwv[DW];
+#pragma unroll
+                            for (int a = 0; a < D; a++) res[a] = xn[a] - x[a] - gd[a] * dt4[s];
+                            df.inv_sig(res, dwv);
+#pragma unroll
+                            for (int j = 0; j < DW; j++) w[j][s] = dwv[j];
+                        }
+                    }
+#pragma unroll
+                    for (int a = 0; a < D; a++) x[a] = xn[a];
+                } else {
+                    if (WRITES_X) {
+#pragma unroll
+                        for (int a = 0; a < D; a++) xt[a][s] = 0.0;
+                    }
+                    if (WRITES_W && !RNG) {
+#pragma unroll
+                        for (int j = 0; j < DW; j++) w[j][s] = 0.0;
+                    }
+                }
+            }
+            if (WRITES_W) {
+#pragma unroll
+                for (int j = 0; j < DW; j++) st256(Wout + ((size_t)q * DW + j) * M * 4, w[j]);
+            }
+            if (WRITES_X) {
+#pragma unroll
+                for (int i = 0; i < D; i++) st256(Xout + ((size_t)q * D + i) * M * 4, xt[i]);
+            }
+            if (!ok) break;
+        }
+    }
+    if (WANT_LL) ly.ll[((size_t)ll_side * ly.nb + b) * M + c] = ll;
+    if (WRITES_X) ly.ok[(size_t)b * M + c] = ok ? 1 : 0;
+}
+
+// =========================================================================================== K1 backward filter
+template <int D>
+__device__ __forceinline__ void hfc_rhs(const double *Bm, const double *beta, const double *at, const double *H, const double *F,
+                                        double *dH, double *dF, double &dc) {
+    // dH = -B'H - HB + H at H ; dF = -B'F + H at F + H beta ; dc = beta'F + F' at F/2 - tr(H at)/2   (A.1)
+    double M1[D][D], N[D][D];
+#pragma unroll
+    for (int i = 0; i < D; i++)
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+            double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+            for (int k = 0; k < D; k++) {
+                s1 = fma(H[sidx<D>(i, k)], Bm[k * D + j], s1);
+                s2 = fma(H[sidx<D>(i, k)], at[sidx<D>(k, j)], s2);
+            }
+            M1[i][j] = s1;
+            N[i][j] = s2;
+        }
+#pragma unroll
+    for (int i = 0; i < D; i++)
+#pragma unroll
+        for (int j = i; j < D; j++) {
+            double s = -(M1[i][j] + M1[j][i]);
+#pragma unroll
+            for (int k = 0; k < D; k++) s = fma(N[i][k], H[sidx<D>(k, j)], s);
+            dH[sidx<D>(i, j)] = s;
+        }
+    double tr = 0.0, bF = 0.0, FaF = 0.0;
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+        double s = 0.0, aF = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            s = fma(-Bm[k * D + i], F[k], s);
+            s = fma(N[i][k], F[k], s);
+            s = fma(H[sidx<D>(i, k)], beta[k], s);
+            aF = fma(at[sidx<D>(i, k)], F[k], aF);
+        }
+        dF[i] = s;
+        tr += N[i][i];
+        bF = fma(beta[i], F[i], bF);
+        FaF = fma(F[i], aF, FaF);
+    }
+    dc = bF + 0.5 * FaF - 0.5 * tr;
+}
+
+template <int D>
+__device__ __forceinline__ void pnu_rhs(const double *Bm, const double *beta, const double *at, const double *Pm, const double *nu,
+                                        double *dP, double *dnu) {
+    // dP = B P + P B' - at ; dnu = B nu + beta   (covariance form used on exact-observation intervals)
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+#pragma unroll
+        for (int j = i; j < D; j++) {
+            double s = -at[sidx<D>(i, j)];
+#pragma unroll
+            for (int k = 0; k < D; k++) {
+                s = fma(Bm[i * D + k], Pm[sidx<D>(k, j)], s);
+                s = fma(Bm[j * D + k], Pm[sidx<D>(k, i)], s);
+            }
+            dP[sidx<D>(i, j)] = s;
+        }
+        double s = beta[i];
+#pragma unroll
+        for (int k = 0; k < D; k++) s = fma(Bm[i * D + k], nu[k], s);
+        dnu[i] = s;
+    }
+}
+
+// inverse and log-determinant of a packed SPD matrix via Cholesky
+template <int D> __device__ __forceinline__ bool spd_inverse(const double *A, double *Ai, double &logdet) {
+    double L[D][D], Li[D][D];
+    bool good = true;
+    double ld = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+        double s = A[sidx<D>(j, j)];
+#pragma unroll
+        for (int k = 0; k < j; k++) s -= L[j][k] * L[j][k];
+        good = good && (s > 0.0);
+        const double l = sqrt(s), il = 1.0 / l;
+        L[j][j] = l;
+        ld += log(l);
+#pragma unroll
+        for (int i = j + 1; i < D; i++) {
+            double t = A[sidx<D>(i, j)];
+#pragma unroll
+            for (int k = 0; k < j; k++) t -= L[i][k] * L[j][k];
+            L[i][j] = t * il;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+        Li[j][j] = 1.0 / L[j][j];
+#pragma unroll
+        for (int i = j + 1; i < D; i++) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = j; k < i; k++) s -= L[i][k] * Li[k][j];
+            Li[i][j] = s / L[i][i];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < D; i++)
+#pragma unroll
+        for (int j = i; j < D; j++) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = j; k < D; k++) s = fma(Li[k][i], Li[k][j], s);
+            Ai[sidx<D>(i, j)] = s;
+        }
+    logdet = 2.0 * ld;
+    return good;
+}
+
+// jump at a (partial, Gaussian) observation: H += L' S^-1 L ; F += L' S^-1 v ; c += (m log 2pi + log det S + v' S^-1 v)/2
+template <int D>
+__device__ __forceinline__ void obs_jump(int m, const double *op, size_t P, double *H, double *F, double &c) {
+    // op -> [NOBS][P] record of this (k, pset): L (m*D), Sigma (m*m), v (m)
+    double Lm[D][D], Sg[D][D], v[D], Lc[D][D];
+#pragma unroll
+    for (int a = 0; a < D; a++) {
+#pragma unroll
+        for (int j = 0; j < D; j++) Lm[a][j] = (a < m) ? op[(size_t)(a * D + j) * P] : 0.0;
+#pragma unroll
+        for (int bq = 0; bq < D; bq++) Sg[a][bq] = (a < m && bq < m) ? op[(size_t)(m * D + a * m + bq) * P] : (a == bq ? 1.0 : 0.0);
+        v[a] = (a < m) ? op[(size_t)(m * D + m * m + a) * P] : 0.0;
+    }
+    double ld = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; j++) { // Cholesky of Sigma (identity-padded beyond m)
+        double s = Sg[j][j];
+#pragma unroll
+        for (int k = 0; k < j; k++) s -= Lc[j][k] * Lc[j][k];
+        const double l = sqrt(s);
+        Lc[j][j] = l;
+        if (j < m) ld += log(l);
+#pragma unroll
+        for (int i = j + 1; i < D; i++) {
+            double t = Sg[i][j];
+#pragma unroll
+            for (int k = 0; k < j; k++) t -= Lc[i][k] * Lc[j][k];
+            Lc[i][j] = t / l;
+        }
+    }
+    // Y = Lc^-1 L, y = Lc^-1 v (forward substitution, row by row)
+    double Y[D][D], y[D];
+#pragma unroll
+    for (int a = 0; a < D; a++) {
+        const double il = 1.0 / Lc[a][a];
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+            double s = Lm[a][j];
+#pragma unroll
+            for (int k = 0; k < a; k++) s -= Lc[a][k] * Y[k][j];
+            Y[a][j] = s * il;
+        }
+        double s = v[a];
+#pragma unroll
+        for (int k = 0; k < a; k++) s -= Lc[a][k] * y[k];
+        y[a] = s * il;
+    }
+    double yy = 0.0;
+#pragma unroll
+    for (int a = 0; a < D; a++) yy = fma(y[a], y[a], yy);
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+#pragma unroll
+        for (int j = i; j < D; j++) {
+            double s = 0.0;
+#pragma unroll
+            for (int a = 0; a < D; a++) s = fma(Y[a][i], Y[a][j], s);
+            H[sidx<D>(i, j)] += s;
+        }
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < D; a++) s = fma(Y[a][i], y[a], s);
+        F[i] += s;
+    }
+    c += 0.5 * (m * 1.8378770664093453 /* log 2pi */ + 2.0 * ld + yy);
+}
+
+// recompute_guiding_term!(b::Block)  src/block.jl:104-110.  One thread = one (pset, block, side).
+// grid = (ceil(P/TPB), n_blocks, 2 sides).  Regular intervals: classical RK4 on the path grid for (H,F,c), backward,
+// with the observation jump fused at the interval end.  The last interval of a non-terminal block (the PPb law with
+// its exact artificial observation, Sigma = eps I) is integrated in covariance form (P = H^-1, nu = P F), which is a
+// linear non-stiff ODE, and converted to (H,F) per grid point; c has a closed form there.
+template <class MD>
+__global__ void __launch_bounds__(BWD_TPB) bwd_kernel(const DevCtx cx, const LayoutDev ly, const int side_mask) {
+    constexpr int D = MD::D, NH = D * (D + 1) / 2, NG = NH + D, NAUX = D * D + D + NH;
+    const int ps = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y, side = blockIdx.z;
+    if (ps >= cx.P || !((side_mask >> side) & 1)) return;
+    const size_t P = cx.P;
+    const int i0 = ly.i0[b], i1 = ly.i1[b];
+    const bool last = ly.last[b] != 0;
+    double H[NH], F[D], cc = 0.0;
+#pragma unroll
+    for (int i = 0; i < NH; i++) H[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < D; i++) F[i] = 0.0;
+
+    for (int k = i1; k >= i0; --k) {
+        const int store = (k == i1 && !last) ? 1 : 0;
+        const int slot = side ^ cx.parP[store][(size_t)k * P + ps];
+        double Bm[D * D], beta[D], at[NH];
+        {
+            const double *ap = cx.aux[slot][store] + (size_t)k * NAUX * P + ps;
+#pragma unroll
+            for (int i = 0; i < D * D; i++) Bm[i] = ap[(size_t)i * P];
+#pragma unroll
+            for (int i = 0; i < D; i++) beta[i] = ap[(size_t)(D * D + i) * P];
+#pragma unroll
+            for (int i = 0; i < NH; i++) at[i] = ap[(size_t)(D * D + D + i) * P];
+        }
+        const int nst = cx.nsteps[k], t0 = cx.tile0[k];
+        const int gt0 = store ? cx.ppb_tile0[k] : t0;
+        double *Gp = cx.G[slot][store] + ((size_t)gt0 * NG * P + ps) * 4;
+        const size_t gstr = P * 4;
+        const double *dtp = cx.dt + (size_t)t0 * 4;
+
+        if (store) { // exact artificial observation (guid_prop_for_blocking, src/sampling_unit.jl:61-66)
+            double Pm[NH], nu[D];
+#pragma unroll
+            for (int i = 0; i < D; i++)
+#pragma unroll
+                for (int j = i; j < D; j++) Pm[sidx<D>(i, j)] = (i == j) ? cx.eps : 0.0;
+#pragma unroll
+            for (int i = 0; i < D; i++) nu[i] = cx.vart[slot][((size_t)k * D + i) * P + ps];
+            double trB = 0.0, Tt = 0.0;
+#pragma unroll
+            for (int i = 0; i < D; i++) trB += Bm[i * D + i];
+            for (int j = nst - 1; j >= 0; --j) {
+                const double h = dtp[j];
+                Tt += h;
+                double k1P[NH], k1n[D], kP[NH], kn[D], Ps[NH], ns[D], aP[NH], an[D];
+                pnu_rhs<D>(Bm, beta, at, Pm, nu, k1P, k1n);
+#pragma unroll
+                for (int i = 0; i < NH; i++) { Ps[i] = fma(-0.5 * h, k1P[i], Pm[i]); aP[i] = k1P[i]; }
+#pragma unroll
+                for (int i = 0; i < D; i++) { ns[i] = fma(-0.5 * h, k1n[i], nu[i]); an[i] = k1n[i]; }
+                pnu_rhs<D>(Bm, beta, at, Ps, ns, kP, kn);
+#pragma unroll
+                for (int i = 0; i < NH; i++) { Ps[i] = fma(-0.5 * h, kP[i], Pm[i]); aP[i] = fma(2.0, kP[i], aP[i]); }
+#pragma unroll
+                for (int i = 0; i < D; i++) { ns[i] = fma(-0.5 * h, kn[i], nu[i]); an[i] = fma(2.0, kn[i], an[i]); }
+                pnu_rhs<D>(Bm, beta, at, Ps, ns, kP, kn);
+#pragma unroll
+                for (int i = 0; i < NH; i++) { Ps[i] = fma(-h, kP[i], Pm[i]); aP[i] = fma(2.0, kP[i], aP[i]); }
+#pragma unroll
+                for (int i = 0; i < D; i++) { ns[i] = fma(-h, kn[i], nu[i]); an[i] = fma(2.0, kn[i], an[i]); }
+                pnu_rhs<D>(Bm, beta, at, Ps, ns, kP, kn);
+#pragma unroll
+                for (int i = 0; i < NH; i++) Pm[i] = fma(-h / 6.0, aP[i] + kP[i], Pm[i]);
+#pragma unroll
+                for (int i = 0; i < D; i++) nu[i] = fma(-h / 6.0, an[i] + kn[i], nu[i]);
+                double logdet;
+                spd_inverse<D>(Pm, H, logdet);
+#pragma unroll
+                for (int i = 0; i < D; i++) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int q = 0; q < D; q++) s = fma(H[sidx<D>(i, q)], nu[q], s);
+                    F[i] = s;
+                }
+                double *gp = Gp + (size_t)(j >> 2) * NG * gstr + (j & 3);
+#pragma unroll
+                for (int i = 0; i < NH; i++) gp[(size_t)i * gstr] = H[i];
+#pragma unroll
+                for (int i = 0; i < D; i++) gp[(size_t)(NH + i) * gstr] = F[i];
+                if (j == 0) { // c = d/2 log 2pi + log det P / 2 + tr(B)(T-t) + nu'H nu / 2
+                    double nF = 0.0;
+#pragma unroll
+                    for (int i = 0; i < D; i++) nF = fma(nu[i], F[i], nF);
+                    cc = 0.5 * D * 1.8378770664093453 + 0.5 * logdet + trB * Tt + 0.5 * nF;
+                }
+            }
+        } else {
+            obs_jump<D>(cx.m, cx.obs[slot] + (size_t)k * (cx.m * D + cx.m * cx.m + cx.m) * P + ps, P, H, F, cc);
+            for (int j = nst - 1; j >= 0; --j) { // classical RK4 from t[j+1] back to t[j]
+                const double h = dtp[j];
+                double kH[NH], kF[D], kc, aH[NH], aF[D], ac, Hs[NH], Fs[D];
+                hfc_rhs<D>(Bm, beta, at, H, F, kH, kF, kc);
+#pragma unroll
+                for (int i = 0; i < NH; i++) { Hs[i] = fma(-0.5 * h, kH[i], H[i]); aH[i] = kH[i]; }
+#pragma unroll
+                for (int i = 0; i < D; i++) { Fs[i] = fma(-0.5 * h, kF[i], F[i]); aF[i] = kF[i]; }
+                ac = kc;
+                hfc_rhs<D>(Bm, beta, at, Hs, Fs, kH, kF, kc);
+#pragma unroll
+                for (int i = 0; i < NH; i++) { Hs[i] = fma(-0.5 * h, kH[i], H[i]); aH[i] = fma(2.0, kH[i], aH[i]); }
+#pragma unroll
+                for (int i = 0; i < D; i++) { Fs[i] = fma(-0.5 * h, kF[i], F[i]); aF[i] = fma(2.0, kF[i], aF[i]); }
+                ac = fma(2.0, kc, ac);
+                hfc_rhs<D>(Bm, beta, at, Hs, Fs, kH, kF, kc);
+#pragma unroll
+                for (int i = 0; i < NH; i++) { Hs[i] = fma(-h, kH[i], H[i]); aH[i] = fma(2.0, kH[i], aH[i]); }
+#pragma unroll
+                for (int i = 0; i < D; i++) { Fs[i] = fma(-h, kF[i], F[i]); aF[i] = fma(2.0, kF[i], aF[i]); }
+                ac = fma(2.0, kc, ac);
+                hfc_rhs<D>(Bm, beta, at, Hs, Fs, kH, kF, kc);
+                const double h6 = h / 6.0;
+#pragma unroll
+                for (int i = 0; i < NH; i++) H[i] = fma(-h6, aH[i] + kH[i], H[i]);
+#pragma unroll
+                for (int i = 0; i < D; i++) F[i] = fma(-h6, aF[i] + kF[i], F[i]);
+                cc = fma(-h6, ac + kc, cc);
+                double *gp = Gp + (size_t)(j >> 2) * NG * gstr + (j & 3);
+#pragma unroll
+                for (int i = 0; i < NH; i++) gp[(size_t)i * gstr] = H[i];
+#pragma unroll
+                for (int i = 0; i < D; i++) gp[(size_t)(NH + i) * gstr] = F[i];
+            }
+        }
+        cx.c0[slot][store][(size_t)k * P + ps] = cc;
+    }
+}
+
+// auxiliary law := Jacobian linearisation of the target at xbar (last paragraph)
+template <class MD>
+__global__ void aux_linearise_kernel(const DevCtx cx, int slot_side, int store, int k0, int k1, const double *xbar /*[k1-k0+1][D][P]*/) {
+    constexpr int D = MD::D, NPAR = MD::NPAR, NH = D * (D + 1) / 2, NAUX = D * D + D + NH;
+    const int ps = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = k0 + blockIdx.y;
+    if (ps >= cx.P || k > k1) return;
+    const size_t P = cx.P;
+    const int slot = slot_side ^ cx.parP[store][(size_t)k * P + ps];
+    double th[NPAR], xb[D], J[D * D], b[D], a[NH];
+#pragma unroll
+    for (int i = 0; i < NPAR; i++) th[i] = cx.theta[slot][store][((size_t)k * NPAR + i) * P + ps];
+#pragma unroll
+    for (int i = 0; i < D; i++) xb[i] = xbar[((size_t)(k - k0) * D + i) * P + ps];
+    const typename MD::Par par(th);
+    MD::jac(par, xb, J);
+    MD::drift(par, xb, b);
+    const typename MD::Diff df(par, xb);
+    df.a_sym(a);
+    double *ap = cx.aux[slot][store] + (size_t)k * NAUX * P + ps;
+#pragma unroll
+    for (int i = 0; i < D * D; i++) ap[(size_t)i * P] = J[i];
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+        double s = b[i];
+#pragma unroll
+        for (int j = 0; j < D; j++) s -= J[i * D + j] * xb[j];
+        ap[(size_t)(D * D + i) * P] = s;
+    }
+#pragma unroll
+    for (int i = 0; i < NH; i++) ap[(size_t)(D * D + D + i) * P] = a[i];
+}
+
+// =========================================================================================== model-independent kernels
+
+// K7  GP.set_obs!(bb)  src/biblock.jl:275-278: artificial obs of b.P_last AND b°.P_last := b.XX[end].x[end]
+__global__ void set_artificial_obs_kernel(const DevCtx cx, const LayoutDev ly, int D) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (c >= cx.M || ly.last[b]) return;
+    const size_t M = cx.M, P = cx.P;
+    const int k = ly.i1[b], ps = cx.pset[c];
+    const int j = cx.nsteps[k] - 1;
+    const int sl = cx.parX[(size_t)k * M + c];
+    const double *xp = cx.X + (size_t)sl * cx.Xbuf + (((size_t)(cx.tile0[k] + (j >> 2)) * D) * M + c) * 4 + (j & 3);
+    for (int i = 0; i < D; i++) {
+        const double v = xp[(size_t)i * M * 4];
+        cx.vart[0][((size_t)k * D + i) * P + ps] = v;
+        if (cx.two_sided) cx.vart[1][((size_t)k * D + i) * P + ps] = v;
+    }
+}
+
+// K6  accept_reject_proposal_path!(bb, i)  src/biblock.jl:121-127
+__global__ void accept_kernel(const DevCtx cx, const LayoutDev ly, uint32_t iter, const double *E /*[nb][M] or null*/) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (c >= cx.M) return;
+    const size_t M = cx.M, idx = (size_t)b * M + c;
+    const double ll = ly.ll[idx], llo = ly.ll[(size_t)ly.nb * M + idx];
+    const double e = E ? E[idx] : accept_exponential(cx.seed, cx.chain_offset + (uint32_t)c, (uint32_t)b, iter, (uint32_t)ly.id);
+    const bool acc = e > -(llo - ll); // IEEE: NaN => false => reject
+    if (acc) {                        // swap_paths!: XX and WW of every interval of the block
+        for (int k = ly.i0[b]; k <= ly.i1[b]; ++k) {
+            cx.parX[(size_t)k * M + c] ^= 1;
+            cx.parW[(size_t)k * M + c] ^= 1;
+        }
+    }
+    ly.last_acc[idx] = acc;
+    if (ly.acc_hist && iter < (uint32_t)ly.hist_len) { // set_accepted!, save_ll! BEFORE swap_ll!
+        ly.acc_hist[(size_t)iter * ly.nb * M + idx] = acc;
+        ly.ll_hist[((size_t)iter * 2 + 0) * ly.nb * M + idx] = ll;
+        ly.ll_hist[((size_t)iter * 2 + 1) * ly.nb * M + idx] = llo;
+    }
+    if (acc) { ly.ll[idx] = llo; ly.ll[(size_t)ly.nb * M + idx] = ll; }
+}
+
+__global__ void save_ll_kernel(const DevCtx cx, const LayoutDev ly, uint32_t iter) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (c >= cx.M || !ly.ll_hist || iter >= (uint32_t)ly.hist_len) return;
+    const size_t M = cx.M, idx = (size_t)b * M + c;
+    ly.ll_hist[((size_t)iter * 2 + 0) * ly.nb * M + idx] = ly.ll[idx];
+    ly.ll_hist[((size_t)iter * 2 + 1) * ly.nb * M + idx] = ly.ll[(size_t)ly.nb * M + idx];
+}
+
+// swap_XX!/swap_WW!/swap_ll! (src/biblock.jl:158-173,206-208) per (chain, block)
+__global__ void swap_paths_kernel(const DevCtx cx, const LayoutDev ly, int what, const uint8_t *mask) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (c >= cx.M || (mask && !mask[c])) return;
+    const size_t M = cx.M, idx = (size_t)b * M + c;
+    for (int k = ly.i0[b]; k <= ly.i1[b]; ++k) {
+        if (what & 1) cx.parX[(size_t)k * M + c] ^= 1;
+        if (what & 2) cx.parW[(size_t)k * M + c] ^= 1;
+    }
+    if (what & 8) {
+        const double a = ly.ll[idx], o = ly.ll[(size_t)ly.nb * M + idx];
+        ly.ll[idx] = o;
+        ly.ll[(size_t)ly.nb * M + idx] = a;
+    }
+}
+// swap_PP! (src/biblock.jl:182-199) per (pset, block): terminal: PP[i0..i1]; non-terminal: PP[i0..i1] (PP + P_excl) and
+// PPb[i0..i1] (Pb_excl + P_last)
+__global__ void swap_laws_kernel(const DevCtx cx, const LayoutDev ly, const uint8_t *mask) {
+    const int ps = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (ps >= cx.P || (mask && !mask[ps])) return;
+    const size_t P = cx.P;
+    for (int k = ly.i0[b]; k <= ly.i1[b]; ++k) {
+        cx.parP[0][(size_t)k * P + ps] ^= 1;
+        if (!ly.last[b]) cx.parP[1][(size_t)k * P + ps] ^= 1;
+    }
+}
+
+// natural [point][dim][chain] <-> tiled, parity-resolved.  dir 0: device tiles -> out, 1: in -> device tiles
+__global__ void xfer_X_kernel(const DevCtx cx, int side, int D, double *nat, int dir) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+    if (c >= cx.M) return;
+    const size_t M = cx.M;
+    const int sl = side ^ cx.parX[(size_t)k * M + c];
+    const int nst = cx.nsteps[k], p0 = cx.pt0[k], t0 = cx.tile0[k];
+    for (int i = 0; i < D; i++) {
+        double *x0 = cx.X0 + (size_t)sl * cx.X0buf + ((size_t)k * D + i) * M + c;
+        double *np0 = nat + ((size_t)p0 * D + i) * M + c;
+        if (dir) *x0 = *np0; else *np0 = *x0;
+        for (int j = 0; j < nst; j++) {
+            double *xp = cx.X + (size_t)sl * cx.Xbuf + (((size_t)(t0 + (j >> 2)) * D + i) * M + c) * 4 + (j & 3);
+            double *np = nat + ((size_t)(p0 + j + 1) * D + i) * M + c;
+            if (dir) *xp = *np; else *np = *xp;
+        }
+    }
+}
+__global__ void xfer_W_kernel(const DevCtx cx, int side, int DW, double *nat, int dir) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+    if (c >= cx.M) return;
+    const size_t M = cx.M;
+    const int sl = side ^ cx.parW[(size_t)k * M + c];
+    const int nst = cx.nsteps[k], s0 = cx.step0[k], t0 = cx.tile0[k];
+    for (int i = 0; i < DW; i++)
+        for (int j = 0; j < nst; j++) {
+            double *wp = cx.W + (size_t)sl * cx.Wbuf + (((size_t)(t0 + (j >> 2)) * DW + i) * M + c) * 4 + (j & 3);
+            double *np = nat + ((size_t)(s0 + j) * DW + i) * M + c;
+            if (dir) *wp = *np; else *np = *wp;
+        }
+}
+// u° = deepcopy(u)  (src/sampling_pair.jl:51): accepted X, X0, W -> proposal buffers, sector by sector
+__global__ void copy_acc_to_prop_kernel(const DevCtx cx, int D, int DW) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+    if (c >= cx.M) return;
+    const size_t M = cx.M;
+    const int sx = cx.parX[(size_t)k * M + c], sw = cx.parW[(size_t)k * M + c];
+    const int t0 = cx.tile0[k], ntl = (cx.nsteps[k] + 3) >> 2;
+    for (int i = 0; i < D; i++) {
+        cx.X0[(size_t)(sx ^ 1) * cx.X0buf + ((size_t)k * D + i) * M + c] = cx.X0[(size_t)sx * cx.X0buf + ((size_t)k * D + i) * M + c];
+        for (int q = 0; q < ntl; q++) {
+            double v[4];
+            const size_t o = (((size_t)(t0 + q) * D + i) * M + c) * 4;
+            ld256(cx.X + (size_t)sx * cx.Xbuf + o, v);
+            st256(cx.X + (size_t)(sx ^ 1) * cx.Xbuf + o, v);
+        }
+    }
+    for (int i = 0; i < DW; i++)
+        for (int q = 0; q < ntl; q++) {
+            double v[4];
+            const size_t o = (((size_t)(t0 + q) * DW + i) * M + c) * 4;
+            ld256(cx.W + (size_t)sw * cx.Wbuf + o, v);
+            st256(cx.W + (size_t)(sw ^ 1) * cx.Wbuf + o, v);
+        }
+}
+
+// guiding term natural [n_k][d*d][P], [n_k][d][P], [n_k][P] <-> packed tiles of interval k.  dir 0: get, 1: upload
+__global__ void xfer_guiding_kernel(const DevCtx cx, int side, int store, int k, int D, double *Hn, double *Fn, double *cn, int dir) {
+    const int ps = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ps >= cx.P) return;
+    const size_t P = cx.P;
+    const int NH = D * (D + 1) / 2, NG = NH + D;
+    const int slot = side ^ cx.parP[store][(size_t)k * P + ps];
+    const int nst = cx.nsteps[k];
+    const int gt0 = store ? cx.ppb_tile0[k] : cx.tile0[k];
+    double *Gp = cx.G[slot][store] + ((size_t)gt0 * NG * P + ps) * 4;
+    for (int j = 0; j < nst; j++) {
+        double *gp = Gp + (size_t)(j >> 2) * NG * P * 4 + (j & 3);
+        for (int a = 0; a < D; a++) {
+            for (int bq = 0; bq < D; bq++) {
+                const int lo = a < bq ? a : bq, hi = a < bq ? bq : a;
+                const int si = lo * D - lo * (lo - 1) / 2 + (hi - lo);
+                double *hn = Hn + ((size_t)j * D * D + a * D + bq) * P + ps;
+                if (dir) { if (a <= bq) gp[(size_t)si * P * 4] = *hn; } else *hn = gp[(size_t)si * P * 4];
+            }
+            double *fn = Fn + ((size_t)j * D + a) * P + ps;
+            if (dir) gp[(size_t)(NH + a) * P * 4] = *fn; else *fn = gp[(size_t)(NH + a) * P * 4];
+        }
+    }
+    double *c0 = &cx.c0[slot][store][(size_t)k * P + ps];
+    if (dir) *c0 = cn[ps];
+    else {
+        cn[ps] = *c0;
+        for (int j = 1; j <= nst; j++) cn[(size_t)j * P + ps] = NAN; // only c at the interval start is kept
+        for (int q = 0; q < D * D; q++) Hn[((size_t)nst * D * D + q) * P + ps] = NAN;
+        for (int q = 0; q < D; q++) Fn[((size_t)nst * D + q) * P + ps] = NAN;
+    }
+}
+
+// fetch_ll / fetch_ll° / accept counts (src/block_ensemble.jl:140,152,175-179): fixed-order tree reduction
+// (warp shuffle + shared memory) over chains -> partial[3][nb][ncta] = (sum ll, sum ll°, #accepted of the last decision)
+__global__ void __launch_bounds__(256) reduce_stats_kernel(const double *ll, const uint8_t *last_acc, int M, int nb, double *partial) {
+    __shared__ double sm[3][8];
+    const int b = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    double v[3] = {0.0, 0.0, 0.0};
+    if (c < M) {
+        v[0] = ll[(size_t)b * M + c];
+        v[1] = ll[((size_t)nb + b) * M + c];
+        v[2] = (double)last_acc[(size_t)b * M + c];
+    }
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_down_sync(0xffffffffu, v[q], o);
+        if ((threadIdx.x & 31) == 0) sm[q][threadIdx.x >> 5] = v[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            double t = (threadIdx.x < (blockDim.x >> 5)) ? sm[q][threadIdx.x] : 0.0;
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+            if (threadIdx.x == 0) partial[((size_t)q * nb + b) * gridDim.x + blockIdx.x] = t;
+        }
+    }
+}
+// second stage (one CTA): per-block sums of the CTA partials in index order, then totals over blocks in index order.
+// out[0]=sum ll, out[1]=sum ll°, out[2..2+nb)=accept counts, out[2+nb..2+2nb)=per-block ll, out[2+2nb..2+3nb)=per-block ll°
+__global__ void finish_stats_kernel(const double *partial, int ncta, int nb, double *out) {
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+        double s[3] = {0.0, 0.0, 0.0};
+        for (int q = 0; q < 3; q++)
+            for (int i = 0; i < ncta; i++) s[q] += partial[((size_t)q * nb + b) * ncta + i];
+        out[2 + b] = s[2];
+        out[2 + nb + b] = s[0];
+        out[2 + 2 * nb + b] = s[1];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, o = 0.0;
+        for (int i = 0; i < nb; i++) { a += out[2 + nb + i]; o += out[2 + 2 * nb + i]; }
+        out[0] = a; out[1] = o;
+    }
+}
+__global__ void accept_counts_kernel(const uint8_t *acc_hist, int nb, int M, uint32_t it0, uint32_t it1, unsigned long long *counts) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    unsigned long long n = 0;
+    if (c < M)
+        for (uint32_t it = it0; it <= it1; ++it) n += acc_hist[((size_t)it * nb + b) * M + c];
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_down_sync(0xffffffffu, n, o);
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(&counts[b], n);
+}
+
+} // namespace dmt

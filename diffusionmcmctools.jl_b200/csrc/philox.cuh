@@ -1,0 +1,66 @@
+// philox.cuh — counter-based Philox4x32-10 (Salmon, Moraes, Dror, Shaw 2011) and the FP64 normal / exponential
+// transforms for the pCN refresh (K3) and the Metropolis test (K6).
+// Replaces `Wnr`-driven sampling inside GP.rand! (/root/reference/src/biblock.jl:95-98) and
+// rand(Exponential(1.0)) (/root/reference/src/biblock.jl:122).  Counter layout (documented in DESIGN.md §4; the test oracle restates it):
+//   pCN   : ctr = (global chain, global tile, iteration, STREAM_PCN<<8 | call), call = 0 .. 2*DW-1
+//   accept: ctr = (global chain, block,       iteration, STREAM_ACC<<8 | layout)
+//   key   = (seed lo, seed hi)
+// One call -> 128 bits -> two 53-bit uniforms -> one Box–Muller pair.  Z never touches HBM.
+#pragma once
+#include <stdint.h>
+
+namespace dmt {
+
+constexpr uint32_t STREAM_PCN = 3u, STREAM_ACC = 4u;
+
+struct u32x4 { uint32_t x, y, z, w; };
+
+__host__ __device__ __forceinline__ u32x4 philox4x32_10(u32x4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+#ifdef __CUDA_ARCH__
+        uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+#else
+        uint64_t p0 = (uint64_t)0xD2511F53u * c.x, p1 = (uint64_t)0xCD9E8D57u * c.z;
+        uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+#endif
+        u32x4 n;
+        n.x = hi1 ^ c.y ^ k0; n.y = lo1; n.z = hi0 ^ c.w ^ k1; n.w = lo0;
+        c = n;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return c;
+}
+
+// two N(0,1) from one Philox block: u1 in (0,1], u2 in [0,1)
+__device__ __forceinline__ void box_muller(u32x4 o, double &z0, double &z1) {
+    uint64_t w0 = ((uint64_t)o.y << 32) | o.x, w1 = ((uint64_t)o.w << 32) | o.z;
+    double u1 = (double)((w0 >> 11) + 1ull) * 0x1.0p-53;
+    double u2 = (double)(w1 >> 11) * 0x1.0p-53;
+    double r = sqrt(-2.0 * log(u1));
+    double s, c;
+    sincospi(2.0 * u2, &s, &c);
+    z0 = r * c;
+    z1 = r * s;
+}
+
+// 4*DW standard normals of one tile (4 EM steps): normal n = slot*DW + j lives in call n/2 (even: cos, odd: sin)
+template <int DW>
+__device__ __forceinline__ void tile_normals(uint64_t seed, uint32_t chain, uint32_t gtile, uint32_t iter, double *z) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int call = 0; call < 2 * DW; call++) {
+        u32x4 c = {chain, gtile, iter, (STREAM_PCN << 8) | (uint32_t)call};
+        box_muller(philox4x32_10(c, k0, k1), z[2 * call], z[2 * call + 1]);
+    }
+}
+
+__device__ __forceinline__ double accept_exponential(uint64_t seed, uint32_t chain, uint32_t block, uint32_t iter, uint32_t layout) {
+    u32x4 c = {chain, block, iter, (STREAM_ACC << 8) | layout};
+    u32x4 o = philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    uint64_t w0 = ((uint64_t)o.y << 32) | o.x;
+    return -log((double)((w0 >> 11) + 1ull) * 0x1.0p-53);
+}
+
+} // namespace dmt

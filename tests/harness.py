@@ -1,0 +1,163 @@
+"""Twin runner: the same Problem pushed into the CUDA library (through the C ABI) and into the CPU oracle, with every
+reference operation mirrored on both so tests can compare after each call.
+
+Oracle side = one `orc.Pair` per chain (the reference's per-recording object graph, pointer swaps included).
+"""
+import numpy as np
+
+import dmt_b200
+from dmt_b200 import _lib
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    both_inf = np.isinf(a) & np.isinf(b) & (np.sign(a) == np.sign(b))
+    diff = np.where(both_inf, 0.0, np.abs(a - b))
+    scale = max(1e-300, np.nanmax(np.abs(np.where(np.isfinite(b), b, 0.0))))
+    return float(np.nanmax(diff) / scale) if diff.size else 0.0
+
+
+class OracleEnsemble:
+    def __init__(self, orc, olib, prob, seed=0, chain_offset=0):
+        self.orc, self.olib, self.prob = orc, olib, prob
+        self.seed, self.chain_offset = seed, chain_offset
+        self.pairs = []
+        ps_of = prob.pset_of_chain if prob.pset_of_chain is not None else (np.arange(prob.M) if prob.P == prob.M else np.zeros(prob.M, int))
+        self.ps_of = ps_of
+        for c in range(prob.M):
+            ps = int(ps_of[c])
+            P = orc.Pair(olib, prob.model, prob.n_pts, prob.tt, prob.m, prob.eps)
+            P.set_theta(prob.theta)
+            for k in range(prob.K):
+                B, beta, at = orc.linearise(olib, prob.model, prob.theta, prob.xbar[k, :, ps])
+                P.set_aux(k, B, beta, at)
+                P.set_obs(k, prob.L, prob.Sigma, prob.v[k, :, ps])
+            P.set_start(prob.x0[:, c])
+            self.pairs.append(P)
+        self.layouts = []
+        for ranges, rho in prob.layouts:
+            nb = len(ranges)
+            rhos = np.broadcast_to(np.asarray(rho, float), (nb,))
+            self.layouts.append([[P.biblock(r[0], r[1], b == nb - 1, float(rhos[b])) for b, r in enumerate(ranges)] for P in self.pairs])
+
+    # ---- mirrored ops (layout l)
+    def each(self, l):
+        for c, P in enumerate(self.pairs):
+            for b, bb in enumerate(self.layouts[l][c]):
+                yield c, b, P, bb
+
+    def set_artificial_obs(self, l):
+        for c, b, P, bb in self.each(l):
+            P.set_artificial_obs(bb)
+
+    def recompute_guiding_term(self, l, sides=(0,)):
+        for c, b, P, bb in self.each(l):
+            for s in sides:
+                P.recompute_guiding_term(bb, s)
+
+    def find_W_for_X(self, l):
+        for c, b, P, bb in self.each(l):
+            P.find_W_for_X(bb)
+
+    def loglikhd(self, l, side=0, skip=0):
+        for c, b, P, bb in self.each(l):
+            P.loglikhd(bb, side, skip)
+
+    def draw(self, l, it, Z=None):
+        """Z: [S][dw][M] natural layout or None (Philox)."""
+        ok = np.zeros((len(self.layouts[l][0]), self.prob.M), bool)
+        step0 = np.concatenate([[0], np.cumsum(self.prob.n_pts - 1)])
+        for c, b, P, bb in self.each(l):
+            zb = None
+            if Z is not None:
+                zb = np.ascontiguousarray(Z[step0[bb.i0]:step0[bb.i1 + 1], :, c])
+            ok[b, c] = P.draw_proposal_path(bb, zb, seed=self.seed, chain=self.chain_offset + c, it=it)
+        return ok
+
+    def recompute_path(self, l, law_side, w_side, skip=0):
+        ok = np.zeros((len(self.layouts[l][0]), self.prob.M), bool)
+        for c, b, P, bb in self.each(l):
+            ok[b, c] = P.recompute_path(bb, law_side, w_side, skip)
+        return ok
+
+    def accept(self, l, it, E=None):
+        nb = len(self.layouts[l][0])
+        acc = np.zeros((nb, self.prob.M), bool)
+        hist = np.zeros((2, nb, self.prob.M))
+        for c, b, P, bb in self.each(l):
+            e = E[b, c] if E is not None else self.olib.orc_accept_exponential(self.seed, self.chain_offset + c, b, it, l)
+            acc[b, c], h = P.accept_reject(bb, float(e))
+            hist[:, b, c] = h
+        return acc, hist
+
+    def swap(self, l, what, mask=None):
+        for c, b, P, bb in self.each(l):
+            if mask is not None and not mask[c]:
+                continue
+            if what & 1: P.swap_XX(bb)
+            if what & 2: P.swap_WW(bb)
+            if what & 4: P.swap_PP(bb)
+            if what & 8: P.swap_ll(bb)
+
+    # ---- state in the C ABI's natural layouts
+    def ll(self, l, side):
+        nb = len(self.layouts[l][0])
+        out = np.zeros((nb, self.prob.M))
+        for c, b, P, bb in self.each(l):
+            out[b, c] = bb.ll[side]
+        return out
+
+    def set_ll(self, l, side, ll):
+        for c, b, P, bb in self.each(l):
+            bb.ll[side] = ll[b, c]
+
+    def X(self, side):
+        return np.stack([np.concatenate([P.get_X(side, k) for k in range(self.prob.K)]) for P in self.pairs], axis=2)
+
+    def W(self, side):
+        return np.stack([np.concatenate([P.get_W(side, k) for k in range(self.prob.K)]) for P in self.pairs], axis=2)
+
+    def set_W(self, side, W):
+        step0 = np.concatenate([[0], np.cumsum(self.prob.n_pts - 1)])
+        for c, P in enumerate(self.pairs):
+            for k in range(self.prob.K):
+                P.set_W(side, k, W[step0[k]:step0[k + 1], :, c])
+
+    def set_X(self, side, X):
+        pt0 = np.concatenate([[0], np.cumsum(self.prob.n_pts)])
+        for c, P in enumerate(self.pairs):
+            for k in range(self.prob.K):
+                P.set_X(side, k, X[pt0[k]:pt0[k + 1], :, c])
+
+    def guiding(self, k, side=0, store=0):
+        """H [n,d,d,P], F [n,d,P], c [n,P] using, for each pset, the first chain that maps to it"""
+        prob = self.prob
+        n, d = int(prob.n_pts[k]), prob.d
+        H = np.zeros((n, d, d, prob.P)); F = np.zeros((n, d, prob.P)); cc = np.zeros((n, prob.P))
+        seen = set()
+        for c, P in enumerate(self.pairs):
+            ps = int(self.ps_of[c])
+            if ps in seen:
+                continue
+            seen.add(ps)
+            h, f, c_ = P.get_HFc(side, store, k)
+            H[..., ps], F[..., ps], cc[:, ps] = h, f, c_
+        return H, F, cc
+
+
+def make_ctx(prob, seed=0, chain_offset=0, two_sided=False, ll_hist_len=0, n_layouts=None):
+    ctx = dmt_b200.Ctx(prob.model, prob.n_pts, prob.tt, prob.M, prob.P, obs_dim=prob.m, two_sided_laws=two_sided,
+                       ll_hist_len=ll_hist_len, n_layouts=n_layouts or max(1, len(prob.layouts)), chain_offset=chain_offset,
+                       seed=seed, artificial_noise=prob.eps, pset_of_chain=prob.pset_of_chain)
+    dmt_b200.configs.upload(prob, ctx, sides=(0, 1) if two_sided else (0,))
+    return ctx
+
+
+def compare_guiding(ctx, ora, k, side=0, store=0, tol=1e-10):
+    H, F, c = ctx.get_guiding_term(k, side, store)
+    Ho, Fo, co = ora.guiding(k, side, store)
+    n = H.shape[0]
+    eH = rel_err(H[:n - 1], Ho[:n - 1]); eF = rel_err(F[:n - 1], Fo[:n - 1])
+    ec = abs(c[0] - co[0]).max() / max(1.0, np.abs(co[0]).max())
+    assert eH < tol and eF < tol and ec < tol, (k, side, store, eH, eF, ec)
+    return max(eH, eF, ec)

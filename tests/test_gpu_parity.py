@@ -1,0 +1,301 @@
+"""GPU parity tests proper: the sm_100a kernels, called through the C ABI, against the CPU oracle on identical inputs.
+
+Tolerances (BASELINE.json north_star): paths and log-likelihoods within 1e-10 relative in Float64, accept/reject
+decisions exactly equal.  Sizes are chosen so the oracle finishes in seconds; n-1 = 10 or 11 steps per interval makes the
+last 4-step tile of every interval partial, M = 40/70 leaves a partial warp / CTA.
+"""
+import numpy as np
+import pytest
+
+import dmt_b200
+from dmt_b200 import _lib, configs
+from harness import OracleEnsemble, compare_guiding, make_ctx, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+NAMES = ["fhn", "lv", "lorenz", "prok", "jr", "ou2"]
+
+
+def small_problem(name, M=40, K=4, P=None, layouts=None, seed=1, nsteps=10):
+    obs_dt = 0.01 if name == "jr" else 0.1
+    return configs.make_problem(name, M, P=P, K=K, obs_dt=obs_dt, dt=obs_dt / nsteps, seed=seed, layouts=layouts, rho=0.7)
+
+
+def random_W(prob, rng, scale=1.0):
+    dt = np.diff(prob.tt)
+    mask = np.ones(len(prob.tt) - 1, bool)
+    mask[np.cumsum(prob.n_pts)[:-1] - 1] = False
+    sq = np.sqrt(dt[mask])
+    return scale * sq[:, None, None] * rng.normal(size=(prob.steps_per_chain, prob.dw, prob.M))
+
+
+@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("nsteps", [10, 11])
+def test_single_block_pipeline(orc, olib, name, nsteps):
+    """K1 -> recompute_path -> loglikhd -> draw (host Z) -> accept (host E) -> draw (Philox) -> accept (Philox)"""
+    prob = small_problem(name, nsteps=nsteps)
+    ctx = make_ctx(prob, seed=77, ll_hist_len=4)
+    ora = OracleEnsemble(orc, olib, prob, seed=77)
+    rng = np.random.default_rng(5)
+
+    # K1
+    ctx.recompute_guiding_term(0, _lib.P_ONLY)
+    ora.recompute_guiding_term(0)
+    for k in range(prob.K):
+        compare_guiding(ctx, ora, k, tol=TOL)
+
+    # K2+K4 from given noise
+    W = random_W(prob, rng)
+    ctx.set_W(W, 0); ora.set_W(0, W)
+    assert np.array_equal(ctx.get_W(0), W)
+    ctx.recompute_path(0, law_side=0, noise_side=0)
+    ok_o = ora.recompute_path(0, 0, 0)
+    assert np.array_equal(ctx.get_success(0), ok_o)
+    assert rel_err(ctx.get_X(0), ora.X(0)) < TOL
+    assert rel_err(ctx.get_ll(0, 0), ora.ll(0, 0)) < TOL
+
+    # K4 alone, with skip
+    for skip in (0, 2):
+        ctx.loglikhd(0, 0, skip); ora.loglikhd(0, 0, skip)
+        assert rel_err(ctx.get_ll(0, 0), ora.ll(0, 0)) < TOL
+    ctx.loglikhd(0, 0, 0); ora.loglikhd(0, 0, 0)
+
+    # K3+K2+K4 with the oracle's ("the reference's own") normals fed to both
+    for it in range(2):
+        Z = rng.normal(size=(prob.steps_per_chain, prob.dw, prob.M))
+        ctx.draw_proposal_path(0, it, Z)
+        ok_o = ora.draw(0, it, Z)
+        assert np.array_equal(ctx.get_success(0), ok_o)
+        good = ok_o[0]
+        assert rel_err(ctx.get_W(1)[:, :, good], ora.W(1)[:, :, good]) < TOL
+        assert rel_err(ctx.get_X(1)[:, :, good], ora.X(1)[:, :, good]) < TOL
+        assert rel_err(ctx.get_ll(0, 1), ora.ll(0, 1)) < TOL
+        # K6 with shared E
+        E = rng.exponential(size=(1, prob.M))
+        ctx.accept_reject_path(0, it, E)
+        acc_o, hist_o = ora.accept(0, it, E)
+        assert np.array_equal(ctx.get_last_accept(0), acc_o)
+        assert rel_err(ctx.get_ll(0, 0), ora.ll(0, 0)) < TOL and rel_err(ctx.get_ll(0, 1), ora.ll(0, 1)) < TOL
+        assert rel_err(ctx.get_X(0), ora.X(0)) < TOL and rel_err(ctx.get_W(0), ora.W(0)) < TOL
+        assert rel_err(ctx.get_ll_history(0, 0, it, it)[0], hist_o[0]) < TOL
+        assert rel_err(ctx.get_ll_history(0, 1, it, it)[0], hist_o[1]) < TOL
+        assert np.array_equal(ctx.get_accept_history(0, it, it)[0], acc_o)
+
+    # Philox path: device RNG vs the oracle's independent Philox + libm Box-Muller
+    for it in range(2, 4):
+        ctx.draw_proposal_path(0, it)
+        ok_o = ora.draw(0, it)
+        assert np.array_equal(ctx.get_success(0), ok_o)
+        good = ok_o[0]
+        Wd, Wo = ctx.get_W(1), ora.W(1)
+        assert rel_err(Wd[:, :, good], Wo[:, :, good]) < 1e-12
+        assert rel_err(ctx.get_X(1)[:, :, good], ora.X(1)[:, :, good]) < TOL
+        assert rel_err(ctx.get_ll(0, 1), ora.ll(0, 1)) < TOL
+        ctx.accept_reject_path(0, it)
+        acc_o, _ = ora.accept(0, it)
+        assert np.array_equal(ctx.get_last_accept(0), acc_o)
+        assert rel_err(ctx.get_X(0), ora.X(0)) < TOL
+    # fetch_ll == fixed-order sum of the per-chain values
+    tot, pb = ctx.fetch_ll(0, 0)
+    assert abs(tot - ora.ll(0, 0).sum()) <= 1e-12 * max(1.0, abs(tot)) or not np.isfinite(tot)
+    cnt = ctx.accept_counts(0, 0, 3)
+    assert cnt[0] == ctx.get_accept_history(0, 0, 3).sum()
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", ["fhn", "lorenz", "prok", "jr"])
+def test_find_W_for_X_roundtrip(orc, olib, name):
+    prob = small_problem(name, M=33, K=3)
+    ctx = make_ctx(prob, seed=3)
+    ora = OracleEnsemble(orc, olib, prob, seed=3)
+    ctx.recompute_guiding_term(0, _lib.P_ONLY); ora.recompute_guiding_term(0)
+    nf = ctx.init_paths(0, iter0=100, max_tries=50)
+    assert nf == 0
+    X, W = ctx.get_X(0), ctx.get_W(0)
+    assert np.array_equal(ctx.get_X(1), X) and np.array_equal(ctx.get_W(1), W)      # u° = deepcopy(u)
+    ora.set_X(0, X); ora.set_W(0, W)
+    # K5 on both: W recovered from X
+    ctx.find_W_for_X(0); ora.find_W_for_X(0)
+    Wd, Wo = ctx.get_W(0), ora.W(0)
+    scale = np.abs(W).max()
+    assert np.abs(Wd - Wo).max() < 1e-9 * scale
+    assert np.abs(Wd - W).max() < 1e-8 * scale                 # invsolve o solve == identity
+    # fused K5+K4 gives the same W and ll as the two separate calls
+    ctx.loglikhd(0, 0, 0)
+    ll_sep = ctx.get_ll(0, 0)
+    ctx.set_W(W, 0)
+    ctx.find_W_and_loglikhd(0)
+    assert np.array_equal(ctx.get_W(0), Wd) and np.array_equal(ctx.get_ll(0, 0), ll_sep)
+    ora.loglikhd(0, 0, 0)
+    assert rel_err(ll_sep, ora.ll(0, 0)) < TOL
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", ["fhn", "lorenz", "prok"])
+def test_blocking_sweeps(orc, olib, name):
+    """Two staggered block layouts alternated (docs/src/tutorials/biblock/smoothing_with_blocking.md:32-59):
+    set_obs! -> recompute_guiding_term!(P only) -> find_W_for_X! -> loglikhd! -> draw -> accept, compared after each call."""
+    K = 8
+    layouts = [([(0, 2), (3, 5), (6, 7)], [0.6, 0.7, 0.8]), ([(0, 3), (4, 7)], 0.5)]
+    prob = small_problem(name, M=37, K=K, layouts=layouts, seed=4)
+    ctx = make_ctx(prob, seed=9, ll_hist_len=6, n_layouts=3)
+    ora = OracleEnsemble(orc, olib, prob, seed=9)
+    # initial path: whole-path guiding term on a single terminal block (layout 2), fresh noise
+    ctx.set_blocks(2, [(0, K - 1)], 0.0)
+    ctx.recompute_guiding_term(2, _lib.P_ONLY)
+    assert ctx.init_paths(2, iter0=1000, max_tries=50) == 0
+    X, W = ctx.get_X(0), ctx.get_W(0)
+    for s in (0, 1):
+        ora.set_X(s, X); ora.set_W(s, W)
+    rng = np.random.default_rng(0)
+    n_acc = 0
+    for it in range(6):
+        l = it % 2
+        ctx.set_artificial_obs(l); ora.set_artificial_obs(l)
+        ctx.recompute_guiding_term(l, _lib.P_ONLY); ora.recompute_guiding_term(l)
+        for (i0, i1) in prob.layouts[l][0]:
+            last = (i1 == K - 1)
+            for k in range(i0, i1 + 1):
+                store = 1 if (k == i1 and not last) else 0
+                compare_guiding(ctx, ora, k, 0, store, tol=TOL)
+        ctx.find_W_for_X(l); ora.find_W_for_X(l)
+        Wd, Wo = ctx.get_W(0), ora.W(0)
+        assert np.abs(Wd - Wo).max() < 1e-9 * np.abs(Wo).max()
+        ora.set_W(0, Wd)   # continue both from the SAME noise (K5 amplifies rounding by 1/sigma/sqrt(dt))
+        ctx.loglikhd(l, 0, 0); ora.loglikhd(l, 0, 0)
+        assert rel_err(ctx.get_ll(l, 0), ora.ll(l, 0)) < 1e-9
+        ora.set_ll(l, 0, ctx.get_ll(l, 0))
+        if it < 3:
+            Z = rng.normal(size=(prob.steps_per_chain, prob.dw, prob.M))
+            ctx.draw_proposal_path(l, it, Z); ok_o = ora.draw(l, it, Z)
+        else:
+            ctx.draw_proposal_path(l, it); ok_o = ora.draw(l, it)
+        assert np.array_equal(ctx.get_success(l), ok_o)
+        lld, llo = ctx.get_ll(l, 1), ora.ll(l, 1)
+        assert rel_err(lld, llo) < 1e-9
+        # ll° - ll is what decides; compare it directly too
+        dd, do = lld - ctx.get_ll(l, 0), llo - ora.ll(l, 0)
+        assert np.allclose(dd[np.isfinite(do)], do[np.isfinite(do)], rtol=0, atol=1e-7 * max(1.0, np.abs(do[np.isfinite(do)]).max()))
+        if it < 3:
+            E = rng.exponential(size=(len(prob.layouts[l][0]), prob.M))
+            ctx.accept_reject_path(l, it, E); acc_o, _ = ora.accept(l, it, E)
+        else:
+            ctx.accept_reject_path(l, it); acc_o, _ = ora.accept(l, it)
+        assert np.array_equal(ctx.get_last_accept(l), acc_o)
+        n_acc += acc_o.sum()
+        assert rel_err(ctx.get_X(0), ora.X(0)) < 1e-9
+        assert rel_err(ctx.get_W(0), ora.W(0)) < 1e-9
+    assert n_acc > 0
+    ctx.close()
+
+
+def test_rho_one_reproduces_accepted_path_bit_exactly():
+    prob = small_problem("lorenz", M=64, K=3)
+    prob.layouts = [([(0, 2)], 1.0)]
+    ctx = make_ctx(prob, seed=1)
+    ctx.recompute_guiding_term(0, _lib.P_ONLY)
+    assert ctx.init_paths(0, 0, 20) == 0
+    ctx.loglikhd(0, 0, 0)
+    ctx.draw_proposal_path(0, 5)
+    assert np.array_equal(ctx.get_X(1), ctx.get_X(0)) and np.array_equal(ctx.get_W(1), ctx.get_W(0))
+    assert np.array_equal(ctx.get_ll(0, 1), ctx.get_ll(0, 0))
+    ctx.close()
+
+
+def test_shared_pset_matches_per_chain_psets(orc, olib):
+    """P = 1 (all chains share data and guiding term; broadcast loads) vs the same problem replicated P = M."""
+    p1 = small_problem("lorenz", M=48, K=3, P=1)
+    pm = small_problem("lorenz", M=48, K=3, P=48)
+    pm.v[:] = p1.v; pm.xbar[:] = p1.xbar; pm.x0[:] = p1.x0
+    c1, cm = make_ctx(p1, seed=2), make_ctx(pm, seed=2)
+    for c in (c1, cm):
+        c.recompute_guiding_term(0, _lib.P_ONLY)
+        assert c.init_paths(0, 0, 20) == 0
+        c.loglikhd(0, 0, 0)
+        c.draw_proposal_path(0, 3)
+    assert np.array_equal(c1.get_X(1), cm.get_X(1)) and np.array_equal(c1.get_ll(0, 1), cm.get_ll(0, 1))
+    c1.close(); cm.close()
+
+
+def test_sharding_is_bitwise_invariant():
+    """one contiguous slice of chains per GPU: per-chain results do not depend on the partition."""
+    full = small_problem("lv", M=48, K=3, seed=6)
+    cf = make_ctx(full, seed=11)
+    cf.recompute_guiding_term(0, _lib.P_ONLY)
+    assert cf.init_paths(0, 0, 50) == 0
+    cf.loglikhd(0, 0, 0); cf.draw_proposal_path(0, 1); cf.accept_reject_path(0, 1)
+    Xf, accf = cf.get_X(0), cf.get_last_accept(0)
+    for lo, hi in [(0, 16), (16, 48)]:
+        part = small_problem("lv", M=48, K=3, seed=6)
+        part.M = part.P = hi - lo
+        part.v = full.v[:, :, lo:hi].copy(); part.xbar = full.xbar[:, :, lo:hi].copy(); part.x0 = full.x0[:, lo:hi].copy()
+        cp = make_ctx(part, seed=11, chain_offset=lo)
+        cp.recompute_guiding_term(0, _lib.P_ONLY)
+        assert cp.init_paths(0, 0, 50) == 0
+        cp.loglikhd(0, 0, 0); cp.draw_proposal_path(0, 1); cp.accept_reject_path(0, 1)
+        assert np.array_equal(cp.get_X(0), Xf[:, :, lo:hi]) and np.array_equal(cp.get_last_accept(0), accf[:, lo:hi])
+        cp.close()
+    cf.close()
+
+
+def test_parameter_update_path(orc, olib):
+    """set_proposal_law! flow (src/biblock.jl:334-344): theta° on the proposal laws, K1 on b°, recompute_path!(b°, b.WW),
+    then the tutorial's accept: swap_XX!, swap_PP!, save_ll!, swap_ll! (docs/src/tutorials/block_ensemble/inference.md:61-68)."""
+    prob = small_problem("fhn", M=35, K=4, seed=8)
+    ctx = make_ctx(prob, seed=5, two_sided=True, ll_hist_len=2)
+    ora = OracleEnsemble(orc, olib, prob, seed=5)
+    ctx.recompute_guiding_term(0, _lib.P_BOTH); ora.recompute_guiding_term(0, sides=(0, 1))
+    assert ctx.init_paths(0, 0, 20) == 0
+    X, W = ctx.get_X(0), ctx.get_W(0)
+    for s in (0, 1):
+        ora.set_X(s, X); ora.set_W(s, W)
+    ctx.loglikhd(0, 0, 0); ora.loglikhd(0, 0, 0)
+    th_o = prob.theta.copy(); th_o[2] = 1.7                         # gamma° (the tutorials update gamma only)
+    ctx.set_params(th_o, side=1, stores=3)
+    ctx.set_aux_linearised(prob.xbar, side=1, store=0); ctx.set_aux_linearised(prob.xbar, side=1, store=1)
+    for c, P in enumerate(ora.pairs):
+        P.set_theta(th_o, side=1)
+        for k in range(prob.K):
+            B, beta, at = orc.linearise(olib, prob.model, th_o, prob.xbar[k, :, c])
+            P.set_aux(k, B, beta, at, side=1)
+    ctx.set_proposal_law(0, critical_change=True, skip=0)
+    ora.recompute_guiding_term(0, sides=(1,)); ok_o = ora.recompute_path(0, 1, 0)
+    assert np.array_equal(ctx.get_success(0), ok_o)
+    for k in range(prob.K):
+        compare_guiding(ctx, ora, k, side=1, tol=TOL)
+    assert rel_err(ctx.get_X(1), ora.X(1)) < TOL and rel_err(ctx.get_ll(0, 1), ora.ll(0, 1)) < TOL
+    llo, _ = ctx.fetch_ll(0, 1); ll, _ = ctx.fetch_ll(0, 0)
+    assert abs(llo - ora.ll(0, 1).sum()) < 1e-9 * abs(llo) and abs(ll - ora.ll(0, 0).sum()) < 1e-9 * abs(ll)
+    # accept for half of the chains only (per-recording accept), W is NOT swapped
+    mask = (np.arange(prob.M) % 2 == 0)
+    ctx.save_ll(0, 0)
+    ctx.swap(0, _lib.SWAP_XX | _lib.SWAP_PP | _lib.SWAP_LL, mask); ora.swap(0, 1 | 4 | 8, mask)
+    assert rel_err(ctx.get_X(0), ora.X(0)) < TOL and rel_err(ctx.get_X(1), ora.X(1)) < TOL
+    assert np.array_equal(ctx.get_W(0), W)
+    assert rel_err(ctx.get_ll(0, 0), ora.ll(0, 0)) < TOL
+    for k in range(prob.K):  # laws followed the swap
+        compare_guiding(ctx, ora, k, side=0, tol=TOL)
+        compare_guiding(ctx, ora, k, side=1, tol=TOL)
+    # the next path update uses the (partly new) accepted laws
+    ctx.draw_proposal_path(0, 9); ora.draw(0, 9)
+    assert rel_err(ctx.get_X(1), ora.X(1)) < TOL and rel_err(ctx.get_ll(0, 1), ora.ll(0, 1)) < TOL
+    ctx.close()
+
+
+def test_failure_is_per_chain_not_an_error(orc, olib):
+    """domain violation => success false, ll = -Inf, certain reject (src/block.jl:181, src/biblock.jl:81-82)"""
+    prob = small_problem("lv", M=32, K=2, seed=2)
+    ctx = make_ctx(prob, seed=4)
+    ora = OracleEnsemble(orc, olib, prob, seed=4)
+    ctx.recompute_guiding_term(0, _lib.P_ONLY); ora.recompute_guiding_term(0)
+    rng = np.random.default_rng(1)
+    W = random_W(prob, rng)
+    W[3, 0, ::4] = -80.0           # huge negative increment => x1 < 0 for every 4th chain
+    ctx.set_W(W, 0); ora.set_W(0, W)
+    ctx.recompute_path(0, 0, 0); ok_o = ora.recompute_path(0, 0, 0)
+    ok = ctx.get_success(0)
+    assert np.array_equal(ok, ok_o) and (~ok[0, ::4]).all() and ok[0, 1::4].all()
+    ll = ctx.get_ll(0, 0)
+    assert np.isneginf(ll[0, ::4]).all() and np.isfinite(ll[0, 1::4]).all()
+    ctx.close()
