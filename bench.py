@@ -32,8 +32,8 @@ ALGO_BYTES = {  # per chain per EM step of draw_proposal_path!
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--config", default="c3")
     ap.add_argument("--chains", type=int, default=None, help="chains PER GPU (default: the config's M)")
     ap.add_argument("--psets", type=int, default=None)
@@ -121,9 +121,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=0.0, t1=1e300):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -133,7 +133,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for ts, r in self.rows:
+            if not (t0 <= ts <= t1 + 0.15):
+                continue
             try:
                 sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
                 for nme, val in zip(names, r[4:8]):
@@ -213,19 +215,20 @@ def gpu_arm(a):
             dist.barrier()
         ctx.sync(); torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()  # nvidia-smi takes a moment to start: launch it before the warm-up, keep only the timed window
     for it in range(a.warmup):
         sweep(it, False)
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
     e_start = torch.cuda.Event(enable_timing=True); e_stop = torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
     e_start.record(stream)
     last = None
     for it in range(a.warmup, a.warmup + a.steps):
         last = sweep(it, True)
     e_stop.record(stream)
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_wall0, time.time())
     ms = torch.tensor([e_start.elapsed_time(e_stop)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -289,7 +292,7 @@ def gpu_arm(a):
                    if a.config == "c3" else "config %s: model %s, %d chains per GPU, K=%d" % (a.config, _lib.MODEL_NAMES[prob.model], prob.M, prob.K),
                    "config_id": a.config, "chains_per_gpu": prob.M, "steps_per_chain": prob.steps_per_chain,
                    "l2": "inputs (paths %.1f GB + guiding term %.1f GB per GPU) are far larger than the 126 MB L2"
-                         % (2 * 8 * 4 * ctx.S * (prob.d + prob.dw) * prob.M / 1e9, 8 * 4 * ctx.S * (prob.d * (prob.d + 1) // 2 + prob.d) * prob.P / 1e9),
+                         % (2 * 8 * ctx.S * (prob.d + prob.dw) * prob.M / 1e9, 8 * ctx.S * (prob.d * (prob.d + 1) // 2 + prob.d) * prob.P / 1e9),
                    "step": "one blocking sweep over one layout" if blocking else "draw + accept"},
         "roofline": roofline, "kernel_ms": kern_ms, "gpu_launches": launches_per_step * a.steps, "clocks": clocks,
         "last_stats": {"sum_ll": float(last[0]), "sum_ll_prop": float(last[1]), "accept_frac": float(np.sum(last[2:]) / (len(last[2:]) * prob.M * world))},

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdmt.so")
+LIB_PATH = os.environ.get("DMT_LIB") or os.path.join(_HERE, "libdmt.so")  # DMT_LIB: a tuning variant built by build.py --tag
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)

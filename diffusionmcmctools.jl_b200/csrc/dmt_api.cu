@@ -14,6 +14,13 @@
 
 using namespace dmt;
 
+// tuning builds may compile a single model (-DDMT_ONLY_MODEL=2) to cut nvcc time; the shipped library has all six
+#ifdef DMT_ONLY_MODEL
+#define DMT_FOR_MODELS(X) X(DMT_ONLY_MODEL)
+#else
+#define DMT_FOR_MODELS(X) X(M_FHN) X(M_LV) X(M_LORENZ) X(M_PROK) X(M_JR) X(M_OU2)
+#endif
+
 namespace {
 
 struct DmtError : std::runtime_error {
@@ -167,7 +174,8 @@ template <int OP> void launch_fwd(dmt_ctx *c, Layout &L, const FwdArgs &fa) {
 #define DMT_CASE(MID)                                                                                              \
     case MID: fwd_kernel<Model<MID>, OP><<<grid, FWD_TPB, 0, c->stream>>>(c->dev, L.dev, fa); break;
     switch (c->cfg.model) {
-        DMT_CASE(M_FHN) DMT_CASE(M_LV) DMT_CASE(M_LORENZ) DMT_CASE(M_PROK) DMT_CASE(M_JR) DMT_CASE(M_OU2)
+        DMT_FOR_MODELS(DMT_CASE)
+        default: throw DmtError(DMT_ERR_UNSUPPORTED, "model not compiled into this build of libdmt");
     }
 #undef DMT_CASE
     CK(cudaGetLastError());
@@ -178,7 +186,8 @@ void launch_bwd(dmt_ctx *c, Layout &L, int side_mask) {
 #define DMT_CASE(MID)                                                                                              \
     case MID: bwd_kernel<Model<MID>><<<grid, BWD_TPB, 0, c->stream>>>(c->dev, L.dev, side_mask); break;
     switch (c->cfg.model) {
-        DMT_CASE(M_FHN) DMT_CASE(M_LV) DMT_CASE(M_LORENZ) DMT_CASE(M_PROK) DMT_CASE(M_JR) DMT_CASE(M_OU2)
+        DMT_FOR_MODELS(DMT_CASE)
+        default: throw DmtError(DMT_ERR_UNSUPPORTED, "model not compiled into this build of libdmt");
     }
 #undef DMT_CASE
     CK(cudaGetLastError());
@@ -461,7 +470,8 @@ int32_t dmt_set_aux_linearised(dmt_ctx *ctx, int32_t side, int32_t store, int32_
 #define DMT_CASE(MID)                                                                                              \
     case MID: aux_linearise_kernel<Model<MID>><<<grid, 128, 0, ctx->stream>>>(ctx->dev, side, store, k0, k1, tmp); break;
         switch (ctx->cfg.model) {
-            DMT_CASE(M_FHN) DMT_CASE(M_LV) DMT_CASE(M_LORENZ) DMT_CASE(M_PROK) DMT_CASE(M_JR) DMT_CASE(M_OU2)
+            DMT_FOR_MODELS(DMT_CASE)
+        default: throw DmtError(DMT_ERR_UNSUPPORTED, "model not compiled into this build of libdmt");
         }
 #undef DMT_CASE
         CK(cudaGetLastError());

@@ -20,7 +20,20 @@
 
 namespace dmt {
 
-constexpr int FWD_TPB = 64;
+// tuning knobs (defaults = the measured best, profiles/; overridable with -D for experiments)
+#ifndef DMT_FWD_TPB
+#define DMT_FWD_TPB 64
+#endif
+#ifndef DMT_FWD_MINB
+#define DMT_FWD_MINB 1 // min resident CTAs per SM promised to ptxas (caps registers)
+#endif
+#ifndef DMT_PF_DIST
+#define DMT_PF_DIST 2 // L2 prefetch distance in tiles (0 = off)
+#endif
+#ifndef DMT_EVICT_FIRST
+#define DMT_EVICT_FIRST 0 // 1: streamed sectors are marked L2::evict_first
+#endif
+constexpr int FWD_TPB = DMT_FWD_TPB;
 constexpr int BWD_TPB = 32;
 
 struct DevCtx {
@@ -70,13 +83,21 @@ struct FwdArgs {
 
 // ------------------------------------------------------------------------------------------- 256-bit sector access
 __device__ __forceinline__ void ld256(const double *p, double *v) { // streaming read-only sector
+#if DMT_EVICT_FIRST
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+#else
     asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+#endif
 }
 __device__ __forceinline__ void ld256u(const double *p, double *v) { // chain-uniform data (dt, sqrt dt): keep in L1
     asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
 }
 __device__ __forceinline__ void st256(double *p, const double *v) {
+#if DMT_EVICT_FIRST
+    asm volatile("st.global.L1::no_allocate.L2::evict_first.v4.f64 [%4], {%0,%1,%2,%3};" ::"d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]), "l"(p) : "memory");
+#else
     asm volatile("st.global.L1::no_allocate.v4.f64 [%4], {%0,%1,%2,%3};" ::"d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]), "l"(p) : "memory");
+#endif
 }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -135,7 +156,7 @@ __device__ __forceinline__ void guided_terms(const typename MD::Par &par, const 
 //   OP_INVSOLVE_LL both of the above in one pass over X
 //   OP_INIT        init_paths! / draw_proposal_path!(u::SamplingUnit)  src/sampling_unit.jl:83-87,118-120 (fresh noise, in place)
 template <class MD, int OP>
-__global__ void __launch_bounds__(FWD_TPB) fwd_kernel(const DevCtx cx, const LayoutDev ly, const FwdArgs fa) {
+__global__ void __launch_bounds__(FWD_TPB, DMT_FWD_MINB) fwd_kernel(const DevCtx cx, const LayoutDev ly, const FwdArgs fa) {
     constexpr int D = MD::D, DW = MD::DW, NPAR = MD::NPAR, NH = D * (D + 1) / 2, NG = NH + D, NAUX = D * D + D + NH;
     constexpr bool READS_X = (OP == OP_LOGLIK || OP == OP_INVSOLVE || OP == OP_INVSOLVE_LL);
     constexpr bool WRITES_X = (OP == OP_DRAW || OP == OP_RECOMPUTE || OP == OP_INIT);
@@ -245,16 +266,16 @@ __global__ void __launch_bounds__(FWD_TPB) fwd_kernel(const DevCtx cx, const Lay
             }
             ld256u(cx.dt + (size_t)(t0 + q) * 4, dt4);
             if (RNG) ld256u(cx.sqdt + (size_t)(t0 + q) * 4, sq4);
-            if (q + 2 < ntl) { // pull the tile after next into L2 while this one is computed
+            if (DMT_PF_DIST > 0 && q + DMT_PF_DIST < ntl) { // pull a later tile into L2 while this one is computed
 #pragma unroll
-                for (int i = 0; i < NG; i++) prefetch_l2(Gp + ((size_t)(q + 2) * NG + i) * gstr);
+                for (int i = 0; i < NG; i++) prefetch_l2(Gp + ((size_t)(q + DMT_PF_DIST) * NG + i) * gstr);
                 if (READS_W) {
 #pragma unroll
-                    for (int j = 0; j < DW; j++) prefetch_l2(Win + ((size_t)(q + 2) * DW + j) * M * 4);
+                    for (int j = 0; j < DW; j++) prefetch_l2(Win + ((size_t)(q + DMT_PF_DIST) * DW + j) * M * 4);
                 }
                 if (READS_X) {
 #pragma unroll
-                    for (int i = 0; i < D; i++) prefetch_l2(Xin + ((size_t)(q + 2) * D + i) * M * 4);
+                    for (int i = 0; i < D; i++) prefetch_l2(Xin + ((size_t)(q + DMT_PF_DIST) * D + i) * M * 4);
                 }
             }
             if (RNG) { // K3: dW° = rho dW + sqrt(1-rho^2) sqrt(dt) xi   (A.2)

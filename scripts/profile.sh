@@ -1,0 +1,20 @@
+#!/bin/bash
+# Profiling recipe (B200_PROFILING.md): plain run first, then the launch list, then ONE --set full capture of the
+# dominant kernels.  Outputs go to gpurun_out/ (scratch); summaries are copied into profiles/ by scripts/summarise_ncu.py.
+# usage: scripts/profile.sh <tag> [bench args...]
+set -u
+TAG=${1:-r01}; shift || true
+OUT=gpurun_out
+mkdir -p $OUT
+CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e $*"
+echo "== plain: $CMD"
+$CMD > $OUT/plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -20 $OUT/plain_$TAG.log; exit 1; }
+tail -1 $OUT/plain_$TAG.log | cut -c1-400
+echo "== launch list"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_launch_$TAG.log 2>&1
+echo "rc=$?"; tail -3 $OUT/ncu_launch_$TAG.log | cut -c1-300
+echo "== full capture of the sweep kernels (draw, invsolve_ll, bwd)"
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
+    -k 'regex:fwd_kernel|bwd_kernel' -s 4 -c 6 -o $OUT/prof_$TAG -f $CMD > $OUT/ncu_full_$TAG.log 2>&1
+echo "rc=$?"; tail -3 $OUT/ncu_full_$TAG.log | cut -c1-300
+ls -la $OUT

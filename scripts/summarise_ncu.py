@@ -1,0 +1,59 @@
+#!/usr/bin/env python
+"""Turn gpurun_out/launches_<tag>.csv and gpurun_out/prof_<tag>.ncu-rep into tracked summaries under profiles/.
+usage: python scripts/summarise_ncu.py <tag>"""
+import collections
+import csv
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1]
+out_dir = os.path.join(ROOT, "profiles")
+os.makedirs(out_dir, exist_ok=True)
+g = os.path.join(ROOT, "gpurun_out")
+lines = ["# ncu summary `%s`" % tag, ""]
+
+lpath = os.path.join(g, "launches_%s.csv" % tag)
+if os.path.exists(lpath):
+    shutil.copy(lpath, os.path.join(out_dir, "%s_launches.csv" % tag))
+    rows = list(csv.reader(open(lpath)))
+    hdr, agg = None, collections.OrderedDict()
+    for r in rows:
+        if "Kernel Name" in r:
+            hdr = r
+            continue
+        if hdr and len(r) == len(hdr):
+            d = dict(zip(hdr, r))
+            agg.setdefault(d["Kernel Name"], []).append(float(d["Metric Value"].replace(",", "")))
+    tot = sum(sum(v) for v in agg.values())
+    lines += ["## launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`; cold-cache, serialised: compare SHARES)", "",
+              "| kernel | launches | mean us | share |", "|---|---:|---:|---:|"]
+    for n, v in agg.items():
+        lines.append("| `%s` | %d | %.1f | %.1f%% |" % (n[:110], len(v), sum(v) / len(v) / 1e3, 100 * sum(v) / tot))
+    lines.append("")
+
+rep = os.path.join(g, "prof_%s.ncu-rep" % tag)
+if os.path.exists(rep):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sectors_srcunit_tex_op_read.sum",
+            "lts__t_sector_hit_rate.pct", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+            "launch__waves_per_multiprocessor", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+            "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+            "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio"]
+    ki = hdr.index("Kernel Name")
+    lines += ["## `ncu --set full --clock-control none` (per launch)", "", "| metric | unit | " + " | ".join(
+        "`%s`" % r[ki].replace("void ", "").split("(")[0][:40] for r in rows[2:]) + " |", "|---|---|" + "---:|" * len(rows[2:])]
+    for w in want:
+        if w in hdr:
+            i = hdr.index(w)
+            lines.append("| %s | %s | " % (w, units[i]) + " | ".join(r[i][:14] for r in rows[2:]) + " |")
+    lines.append("")
+open(os.path.join(out_dir, "%s_summary.md" % tag), "w").write("\n".join(lines))
+print("\n".join(lines))
