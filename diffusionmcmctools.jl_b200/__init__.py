@@ -2,5 +2,8 @@
 
 The directory name carries a dot, so import it through the shim at the repo root:  `import dmt_b200`.
 """
-from . import _lib, configs  # noqa: F401
+from . import _lib, configs, host  # noqa: F401
 from ._lib import Ctx, DmtError  # noqa: F401
+from .host import (BlockEnsemble, SamplingEnsemble, accept_reject_proposal_path, accpt_rate, draw_proposal_path,  # noqa: F401
+                   fetch_ll, fetch_ll_o, find_W_for_X, ll_of_accepted, loglikhd, loglikhd_o, recompute_guiding_term, save_ll,
+                   set_obs, set_proposal_law, shard_slice, swap_ll, swap_paths, swap_PP, swap_WW, swap_XX)

@@ -168,7 +168,7 @@ def make_problem(name, M, P=None, K=None, obs_dt=None, dt=None, seed=0, layouts=
     x0p = np.repeat(np.array(X0[model], dtype=np.float64)[:, None], P, axis=1)
     if model == LV:
         rng0 = np.random.default_rng([seed, 17])
-        x0p = x0p * (1.0 + 0.05 * rng0.normal(size=(d, P + chain_offset))[:, chain_offset:])
+        x0p = x0p * (1.0 + 0.05 * rng0.normal(size=(P + chain_offset, d)).T[:, chain_offset:])
     h = dt / sim_sub
     nsub = int(round(obs_dt / h))
     gens = [np.random.default_rng([seed, chain_offset + p]) for p in range(P)] if P <= 64 else None

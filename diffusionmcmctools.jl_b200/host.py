@@ -1,0 +1,288 @@
+"""Host-side mirror of the DiffusionMCMCTools.jl API over the device library (libdmt.so).
+
+Same names, argument meaning and call order as the reference (file:line into /root/reference/), with Julia's `f!` written
+`f` and `°` written `_o`.  Containers live on the GPU as structure-of-arrays; `Block`/`BiBlock` are index ranges; every
+method below is ONE batched kernel launch over all recordings x blocks instead of the reference's serial broadcasts
+(src/block_ensemble.jl:50 -> src/block_collection.jl:46 -> src/biblock.jl:80-99).
+
+Julia has no toolchain in this image, so this Python layer plays the role of the Julia glue in tests; the actual glue
+(julia/DiffusionMCMCToolsB200.jl) makes the same ccalls.
+
+Parameter-name translation (src/param_names_collections.jl) and the parameter proposal / prior / accept logic stay on the
+host (BASELINE.json north_star): `set_proposal_law` takes the already-translated pairs `pnames = [(i_theta°, j_model), ...]`.
+"""
+import numpy as np
+
+from . import _lib
+
+P_only, Po_only = "P_only", "P°_only"  # Val(:P_only), Val(:P°_only)  (src/DiffusionMCMCTools.jl:9-10)
+
+
+def shard_slice(n_total, rank, world):
+    """one contiguous slice of chains per GPU"""
+    base, rem = divmod(n_total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class SamplingEnsemble:
+    """SamplingEnsemble(aux_laws, recordings, tts, ...)  (src/sampling_ensemble.jl:17-41) — all recordings of one model on one
+    GPU.  `recordings` carries what ObservationSchemes' recordings + GuidedProposals' aux laws carry:
+        theta [npar] or [npar, P]; L [m, d]; Sigma [m, m]; v [K, m, P]; x0 [d, M];
+        xbar [K, d, P] (Jacobian-linearised auxiliary laws, evaluated on the device)  or  aux = (B [K,d,d,P], beta [K,d,P], atil [K,d,d,P]).
+    tts = (n_pts [K], tt [sum n_pts]) is OBS.setup_time_grids' output.  With (rank, world) given, this process keeps the
+    contiguous chain slice of `rank` (chains are independent: src/block_ensemble.jl:63-67)."""
+
+    def __init__(self, model, recordings, tts, *, aux_laws_blocking=None, artificial_noise=1e-11, device=0, seed=0, two_sided_laws=True,
+                 max_layouts=8, rank=0, world=1, pset_of_chain=None):
+        n_pts, tt = tts
+        x0 = np.asarray(recordings["x0"], dtype=np.float64)
+        M_tot = x0.shape[1]
+        v = np.asarray(recordings["v"], dtype=np.float64)
+        P_tot = v.shape[2]
+        self.rank, self.world = rank, world
+        lo, hi = shard_slice(M_tot, rank, world)
+        if P_tot == M_tot:
+            plo, phi = lo, hi
+        else:
+            if world > 1:
+                raise ValueError("sharding needs one parameter/data set per recording (P == M)")
+            plo, phi = 0, P_tot
+        self.chain_lo, self.chain_hi, self.M_total = lo, hi, M_tot
+        self.model = model
+        self.theta = np.asarray(recordings["theta"], dtype=np.float64)
+        if self.theta.ndim == 1:
+            self.theta = np.repeat(self.theta[:, None], phi - plo, axis=1)
+        else:
+            self.theta = self.theta[:, plo:phi].copy()
+        self.theta_o = self.theta.copy()
+        self.xbar = None
+        L, Sigma = recordings["L"], recordings["Sigma"]
+        self.ctx = _lib.Ctx(model, n_pts, tt, hi - lo, phi - plo, obs_dim=np.asarray(L).shape[-2] if np.asarray(L).ndim == 2 else np.asarray(L).shape[1],
+                            device=device, two_sided_laws=two_sided_laws, n_layouts=max_layouts, chain_offset=lo, seed=seed,
+                            artificial_noise=artificial_noise, pset_of_chain=pset_of_chain)
+        self.two_sided = two_sided_laws
+        self._next_layout = 0
+        self._init_layout = None
+        sides = (0, 1) if two_sided_laws else (0,)
+        for s in sides:
+            self.ctx.set_params(self.theta, side=s, stores=3)
+            self.ctx.set_obs(L, Sigma, v[:, :, plo:phi], side=s)
+        if "xbar" in recordings:
+            self.xbar = np.asarray(recordings["xbar"], dtype=np.float64)[:, :, plo:phi].copy()
+            self.xbar_blocking = self.xbar if aux_laws_blocking is None else np.asarray(aux_laws_blocking)[:, :, plo:phi].copy()
+            for s in sides:
+                self.ctx.set_aux_linearised(self.xbar, side=s, store=_lib.STORE_PP)
+                self.ctx.set_aux_linearised(self.xbar_blocking, side=s, store=_lib.STORE_PPB)
+        else:
+            B, beta, atil = recordings["aux"]
+            Bb, betab, atilb = aux_laws_blocking if aux_laws_blocking is not None else recordings["aux"]
+            for s in sides:
+                self.ctx.set_aux(B, beta, atil, side=s, store=_lib.STORE_PP)
+                self.ctx.set_aux(Bb, betab, atilb, side=s, store=_lib.STORE_PPB)
+        self.ctx.set_start(x0[:, lo:hi])
+
+    def init_paths(self, iter0=2 ** 24, max_tries=100):
+        """SamplingUnit ctor's init_paths! + u° = deepcopy(u)  (src/sampling_unit.jl:70,83-87; src/sampling_pair.jl:51)"""
+        if self._init_layout is None:
+            self._init_layout = self._alloc_layout()
+            self.ctx.set_blocks(self._init_layout, [(0, self.ctx.K - 1)], 0.0, ll_hist_len=0)
+        self.ctx.recompute_guiding_term(self._init_layout, _lib.P_ONLY)
+        nf = self.ctx.init_paths(self._init_layout, iter0, max_tries)
+        if nf:
+            raise RuntimeError("init_paths!: %d recordings still fail after %d tries" % (nf, max_tries))
+
+    def _alloc_layout(self):
+        if self._next_layout >= self.ctx.n_layouts:
+            raise RuntimeError("more block layouts than max_layouts=%d" % self.ctx.n_layouts)
+        self._next_layout += 1
+        return self._next_layout - 1
+
+    def comm_init(self, uid):
+        """join the NCCL communicator used for the small ll / accept-count allreduce"""
+        self.ctx.comm_init(self.world, self.rank, uid)
+        self._has_comm = True
+
+    def num_recordings(self):  # OBS.num_recordings(se)  src/sampling_ensemble.jl:46
+        return self.M_total
+
+
+class _BlockSide:
+    """bb.b / bb.b° of one (recording, block): read-only view"""
+
+    def __init__(self, be, rec, blk, side):
+        self._be, self._rec, self._blk, self._side = be, rec, blk, side
+
+    @property
+    def ll(self):
+        return float(self._be.ctx.get_ll(self._be.layout, self._side)[self._blk, self._rec])
+
+    @property
+    def ll_history(self):
+        return self._be.ctx.get_ll_history(self._be.layout, self._side, 0, self._be.ll_hist_len - 1)[:, self._blk, self._rec]
+
+
+class BiBlockView:
+    def __init__(self, be, rec, blk):
+        self.b, self.b_o = _BlockSide(be, rec, blk, 0), _BlockSide(be, rec, blk, 1)
+        self.rho = float(be.rho[blk])
+        self._be, self._rec, self._blk = be, rec, blk
+
+    @property
+    def accpt_history(self):
+        return self._be.ctx.get_accept_history(self._be.layout, 0, self._be.ll_hist_len - 1)[:, self._blk, self._rec]
+
+
+class BlockCollectionView:
+    def __init__(self, be, rec):
+        self.blocks = [BiBlockView(be, rec, b) for b in range(be.n_blocks)]
+
+
+class BlockEnsemble:
+    """BlockEnsemble(se, block_ranges, ρρ, ll_hist_len)  (src/block_ensemble.jl:17-34): the same block ranges for every
+    recording; the last range is the terminal block (src/block_collection.jl:29).  Ranges are 0-based inclusive pairs."""
+
+    def __init__(self, se, block_ranges, rho=0.0, ll_hist_len=0):
+        self.se, self.ctx = se, se.ctx
+        self.ranges = [tuple(r) for r in block_ranges]
+        self.n_blocks = len(self.ranges)
+        self.rho = np.broadcast_to(np.asarray(rho, dtype=np.float64), (self.n_blocks,)).copy()
+        self.ll_hist_len = ll_hist_len
+        self.layout = se._alloc_layout()
+        self.ctx.set_blocks(self.layout, self.ranges, self.rho, ll_hist_len=ll_hist_len)
+
+    @property
+    def recordings(self):
+        return [BlockCollectionView(self, c) for c in range(self.ctx.M)]
+
+    def num_recordings(self):  # src/block_ensemble.jl:36
+        return self.se.M_total
+
+
+# ---- imputation --------------------------------------------------------------------------------------------------------
+def draw_proposal_path(be, mcmciter=0, Z=None):
+    """draw_proposal_path!(be)  src/block_ensemble.jl:50.  `mcmciter` only seeds the counter-based generator."""
+    be.ctx.draw_proposal_path(be.layout, mcmciter, Z)
+
+
+def accept_reject_proposal_path(be, mcmciter, E=None):
+    """accept_reject_proposal_path!(be, mcmciter)  src/block_ensemble.jl:63-67 (0-based iteration index)"""
+    be.ctx.accept_reject_path(be.layout, mcmciter, E)
+
+
+# ---- swaps (src/block_ensemble.jl:79-112 -> src/biblock.jl:148-209) -------------------------------------------------
+def swap_paths(be, mask=None):
+    be.ctx.swap(be.layout, _lib.SWAP_XX | _lib.SWAP_WW, mask)
+
+
+def swap_XX(be, mask=None):
+    be.ctx.swap(be.layout, _lib.SWAP_XX, mask)
+
+
+def swap_WW(be, mask=None):
+    be.ctx.swap(be.layout, _lib.SWAP_WW, mask)
+
+
+def swap_PP(be, mask=None):
+    be.ctx.swap(be.layout, _lib.SWAP_PP, mask)
+    if mask is None:
+        be.se.theta, be.se.theta_o = be.se.theta_o, be.se.theta
+    else:
+        m = np.asarray(mask, bool)
+        t = be.se.theta[:, m].copy(); be.se.theta[:, m] = be.se.theta_o[:, m]; be.se.theta_o[:, m] = t
+
+
+def swap_ll(be, mask=None):
+    be.ctx.swap(be.layout, _lib.SWAP_LL, mask)
+
+
+# ---- utility (src/block_ensemble.jl:121-179) ---------------------------------------------------------------------------
+def loglikhd(be, skip=0):
+    be.ctx.loglikhd(be.layout, _lib.ACCEPTED, skip)
+
+
+def loglikhd_o(be, skip=0):
+    be.ctx.loglikhd(be.layout, _lib.PROPOSAL, skip)
+
+
+def dist_sum(arr):
+    """sum a small float64 vector over all ranks of the default torch.distributed group (gloo: CPU tensor, nccl: GPU tensor)"""
+    import torch
+    import torch.distributed as dist
+    t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64).copy())
+    if dist.get_backend() == "nccl":
+        t = t.cuda()
+    dist.all_reduce(t)
+    return t.cpu().numpy()
+
+
+def _global_stats(be):
+    """[sum ll, sum ll°, accept counts...] over ALL recordings: the one small allreduce of the path"""
+    st = be.ctx.allreduce_stats(be.layout)  # NCCL inside libdmt when a communicator was initialised, local sums otherwise
+    if be.se.world > 1 and not getattr(be.se, "_has_comm", False):
+        st = dist_sum(st)
+    return st
+
+
+def fetch_ll(be):
+    """fetch_ll(be) = sum over recordings and blocks of b.ll  (src/block_ensemble.jl:140, src/block_collection.jl:144)"""
+    return float(_global_stats(be)[0])
+
+
+def fetch_ll_o(be):
+    return float(_global_stats(be)[1])
+
+
+def save_ll(be, mcmciter):
+    be.ctx.save_ll(be.layout, mcmciter)
+
+
+def ll_of_accepted(be, i):
+    """[recording][block] log-likelihood of the path accepted at iteration i  (src/biblock.jl:222-224)"""
+    acc = be.ctx.get_accept_history(be.layout, i, i)[0]
+    ll = be.ctx.get_ll_history(be.layout, 0, i, i)[0]
+    llo = be.ctx.get_ll_history(be.layout, 1, i, i)[0]
+    return np.where(acc, llo, ll).T
+
+
+def accpt_rate(be, rng):
+    """acceptance rate per block over the inclusive iteration range, LOCAL recordings  (src/biblock.jl:232)"""
+    i0, i1 = rng
+    return be.ctx.accept_counts(be.layout, i0, i1) / float((i1 - i0 + 1) * be.ctx.M)
+
+
+# ---- blocking (src/block_ensemble.jl:192-221) --------------------------------------------------------------------------
+def set_obs(be):
+    be.ctx.set_artificial_obs(be.layout)
+
+
+def recompute_guiding_term(be, which=None):
+    w = {None: _lib.P_BOTH if be.se.two_sided else _lib.P_ONLY, P_only: _lib.P_ONLY, Po_only: _lib.PO_ONLY}[which]
+    be.ctx.recompute_guiding_term(be.layout, w)
+
+
+def find_W_for_X(be):
+    be.ctx.find_W_for_X(be.layout)
+
+
+# ---- parameters (src/block_ensemble.jl:226-255 -> src/biblock.jl:334-371) -------------------------------------------
+def is_critical_update(be, pnames):
+    raise NotImplementedError("the reference's is_critical_update reads fields no ParamNames struct has (src/biblock.jl:315-317, "
+                              "SURVEY Appendix C.2); pass critical_change explicitly, as every tutorial does")
+
+
+def set_proposal_law(be, theta_o, pnames, critical_change, skip=0):
+    """set_proposal_law!(be, θ°, pnames, critical_change; skip)  src/block_ensemble.jl:242-255.
+    pnames: already-translated pairs (index into θ°, index into the model's parameter vector); theta_o: [len] or [len, P]."""
+    se = be.se
+    th = se.theta.copy()                      # equalize_law_params!: everything not updated is shared with the accepted law
+    theta_o = np.asarray(theta_o, dtype=np.float64)
+    for i_src, j_dst in pnames:
+        th[j_dst, :] = theta_o[i_src]
+    se.theta_o = th
+    be.ctx.equalize_laws(3)                   # GP.equalize_obs_params! / equalize_law_params!  (src/biblock.jl:384-443)
+    be.ctx.set_params(th, side=_lib.PROPOSAL, stores=3)
+    if critical_change and se.xbar is not None:
+        be.ctx.set_aux_linearised(se.xbar, side=_lib.PROPOSAL, store=_lib.STORE_PP)
+        be.ctx.set_aux_linearised(se.xbar_blocking, side=_lib.PROPOSAL, store=_lib.STORE_PPB)
+    be.ctx.set_proposal_law(be.layout, critical_change, skip)

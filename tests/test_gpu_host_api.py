@@ -1,0 +1,127 @@
+"""The reference's tutorials, run through the reference-shaped host API (dmt_b200.host) on the GPU and, call by call, on the
+CPU oracle with the same counter-based random streams: accept/reject histories must be IDENTICAL, paths agree to 1e-9.
+
+Tutorials mirrored (/root/reference/docs/src/tutorials/):
+  biblock/smoothing.md:25-58                      simple_smoothing
+  block_collection/inference_with_blocking.md     blocking sweep over alternating layouts
+  block_ensemble/inference.md:44-75               path update + parameter update with swap_XX!/swap_PP!/save_ll!/swap_ll!
+"""
+import numpy as np
+import pytest
+
+import dmt_b200
+from dmt_b200 import _lib, configs
+from dmt_b200 import host as H
+from harness import OracleEnsemble, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def recordings_of(prob):
+    return dict(theta=prob.theta, L=prob.L, Sigma=prob.Sigma, v=prob.v, x0=prob.x0, xbar=prob.xbar)
+
+
+def test_simple_smoothing_tutorial(orc, olib):
+    nit = 12
+    prob = configs.make_problem("fhn", 33, K=10, dt=0.005, seed=100, rho=0.96)
+    se = H.SamplingEnsemble(prob.model, recordings_of(prob), (prob.n_pts, prob.tt), seed=100, two_sided_laws=False)
+    se.init_paths()
+    bb = H.BlockEnsemble(se, [(0, prob.K - 1)], 0.96, nit)                # BiBlock(sp, 1:length(recording.obs), ρ, true, num_steps)
+    H.recompute_guiding_term(bb, H.P_only)
+    H.loglikhd(bb)
+    ora = OracleEnsemble(orc, olib, prob, seed=100)
+    X, W = se.ctx.get_X(0), se.ctx.get_W(0)
+    for s in (0, 1):
+        ora.set_X(s, X); ora.set_W(s, W)
+    ora.recompute_guiding_term(0); ora.loglikhd(0)
+    for i in range(nit):
+        H.draw_proposal_path(bb, i)
+        H.accept_reject_proposal_path(bb, i)
+        ora.draw(0, i); ora.accept(0, i)
+    acc_dev = se.ctx.get_accept_history(bb.layout, 0, nit - 1)
+    assert 0.05 < acc_dev.mean() < 0.99
+    # oracle history from its ll bookkeeping: replay equality through the final state
+    assert rel_err(se.ctx.get_X(0), ora.X(0)) < 1e-9 and rel_err(se.ctx.get_W(0), ora.W(0)) < 1e-9
+    assert rel_err(se.ctx.get_ll(bb.layout, 0), ora.ll(0, 0)) < 1e-9
+    r = H.accpt_rate(bb, (0, nit - 1))
+    assert r.shape == (1,) and abs(r[0] - acc_dev.mean()) < 1e-12
+    lla = H.ll_of_accepted(bb, nit - 1)
+    assert lla.shape == (33, 1) and np.allclose(lla[:, 0], se.ctx.get_ll(bb.layout, 0)[0], rtol=1e-12)
+    v = bb.recordings[3].blocks[0]
+    assert v.rho == 0.96 and v.accpt_history.shape == (nit,) and abs(v.b.ll - se.ctx.get_ll(bb.layout, 0)[0, 3]) == 0
+    se.ctx.close()
+
+
+def test_blocking_tutorial(orc, olib):
+    K, nit = 12, 4
+    layouts = [([(0, 2), (3, 8), (9, 11)], 0.9), ([(0, 5), (6, 11)], 0.9)]      # [[1:25,26:75,76:100],[1:50,51:100]] scaled down
+    prob = configs.make_problem("lorenz", 24, K=K, dt=0.01, seed=3, layouts=layouts)
+    se = H.SamplingEnsemble(prob.model, recordings_of(prob), (prob.n_pts, prob.tt), seed=8, two_sided_laws=False)
+    se.init_paths()
+    blocks = [H.BlockEnsemble(se, r, rho, nit) for r, rho in layouts]
+    ora = OracleEnsemble(orc, olib, prob, seed=8)
+    X, W = se.ctx.get_X(0), se.ctx.get_W(0)
+    for s in (0, 1):
+        ora.set_X(s, X); ora.set_W(s, W)
+    for i in range(nit):
+        for l, B in enumerate(blocks):
+            H.set_obs(B); ora.set_artificial_obs(l)
+            H.recompute_guiding_term(B, H.P_only); ora.recompute_guiding_term(l)
+            H.find_W_for_X(B); ora.find_W_for_X(l)
+            ora.set_W(0, se.ctx.get_W(0))
+            H.loglikhd(B); ora.loglikhd(l)
+            ora.set_ll(l, 0, se.ctx.get_ll(B.layout, 0))
+            H.draw_proposal_path(B, i); ora.draw(l, i)
+            H.accept_reject_proposal_path(B, i)
+            acc_o, _ = ora.accept(l, i)
+            assert np.array_equal(se.ctx.get_last_accept(B.layout), acc_o)
+            assert rel_err(se.ctx.get_X(0), ora.X(0)) < 1e-9
+    assert all((H.accpt_rate(B, (0, nit - 1)) > 0).all() for B in blocks)
+    se.ctx.close()
+
+
+def test_inference_tutorial_parameter_update(orc, olib):
+    """block_ensemble/inference.md: alternate path imputation and a random-walk update of gamma shared by all recordings"""
+    nit = 6
+    prob = configs.make_problem("fhn", 16, K=6, dt=0.005, seed=5, rho=0.9)
+    se = H.SamplingEnsemble(prob.model, recordings_of(prob), (prob.n_pts, prob.tt), seed=21, two_sided_laws=True)
+    se.init_paths()
+    be = H.BlockEnsemble(se, [(0, prob.K - 1)], 0.9, nit)
+    H.recompute_guiding_term(be)
+    H.loglikhd(be)
+    ora = OracleEnsemble(orc, olib, prob, seed=21)
+    X, W = se.ctx.get_X(0), se.ctx.get_W(0)
+    for s in (0, 1):
+        ora.set_X(s, X); ora.set_W(s, W)
+    ora.recompute_guiding_term(0, sides=(0, 1)); ora.loglikhd(0)
+    rng = np.random.default_rng(0)
+    gamma = prob.theta[2]
+    pnames = [(0, 2)]                                                   # θ°[1] -> :γ
+    n_par_acc = 0
+    for i in range(nit):
+        H.draw_proposal_path(be, i); H.accept_reject_proposal_path(be, i)
+        ora.draw(0, i); ora.accept(0, i)
+        # parameter update
+        g_o = gamma + 2 * 0.3 * (rng.random() - 0.5)
+        H.set_proposal_law(be, [g_o], pnames, True)
+        th_o = prob.theta.copy(); th_o[2] = g_o
+        th_a = prob.theta.copy(); th_a[2] = gamma
+        for c, P in enumerate(ora.pairs):
+            for k in range(prob.K):   # equalize + set on the proposal side
+                P.set_theta(th_o, side=1, k=k)
+                Bm, beta, at = orc.linearise(olib, prob.model, th_o, prob.xbar[k, :, c])
+                P.set_aux(k, Bm, beta, at, side=1)
+        ora.recompute_guiding_term(0, sides=(1,)); ora.recompute_path(0, 1, 0)
+        ll, ll_o = H.fetch_ll(be), H.fetch_ll_o(be)
+        assert abs(ll - ora.ll(0, 0).sum()) < 1e-8 * abs(ll) and abs(ll_o - ora.ll(0, 1).sum()) < 1e-8 * max(1.0, abs(ll_o))
+        accepted = rng.exponential() > -(ll_o - ll)                       # flat prior, symmetric kernel
+        if accepted:
+            H.swap_XX(be); H.swap_PP(be); ora.swap(0, 1 | 4)
+            gamma = g_o
+            n_par_acc += 1
+        H.save_ll(be, i)
+        if accepted:
+            H.swap_ll(be); ora.swap(0, 8)
+        assert np.allclose(se.theta[2], gamma)
+        assert rel_err(se.ctx.get_X(0), ora.X(0)) < 1e-9 and rel_err(se.ctx.get_ll(be.layout, 0), ora.ll(0, 0)) < 1e-9
+    se.ctx.close()
