@@ -80,12 +80,14 @@ class OracleEnsemble:
             ok[b, c] = P.recompute_path(bb, law_side, w_side, skip)
         return ok
 
-    def accept(self, l, it, E=None):
+    def accept(self, l, it, E=None, layout_id=None):
+        """layout_id: the id the device library registered this layout under (part of the accept stream's counter)"""
         nb = len(self.layouts[l][0])
         acc = np.zeros((nb, self.prob.M), bool)
         hist = np.zeros((2, nb, self.prob.M))
+        lid = l if layout_id is None else layout_id
         for c, b, P, bb in self.each(l):
-            e = E[b, c] if E is not None else self.olib.orc_accept_exponential(self.seed, self.chain_offset + c, b, it, l)
+            e = E[b, c] if E is not None else self.olib.orc_accept_exponential(self.seed, self.chain_offset + c, b, it, lid)
             acc[b, c], h = P.accept_reject(bb, float(e))
             hist[:, b, c] = h
         return acc, hist

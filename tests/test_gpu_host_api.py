@@ -37,7 +37,7 @@ def test_simple_smoothing_tutorial(orc, olib):
     for i in range(nit):
         H.draw_proposal_path(bb, i)
         H.accept_reject_proposal_path(bb, i)
-        ora.draw(0, i); ora.accept(0, i)
+        ora.draw(0, i); ora.accept(0, i, layout_id=bb.layout)
     acc_dev = se.ctx.get_accept_history(bb.layout, 0, nit - 1)
     assert 0.05 < acc_dev.mean() < 0.99
     # oracle history from its ll bookkeeping: replay equality through the final state
@@ -73,7 +73,7 @@ def test_blocking_tutorial(orc, olib):
             ora.set_ll(l, 0, se.ctx.get_ll(B.layout, 0))
             H.draw_proposal_path(B, i); ora.draw(l, i)
             H.accept_reject_proposal_path(B, i)
-            acc_o, _ = ora.accept(l, i)
+            acc_o, _ = ora.accept(l, i, layout_id=B.layout)
             assert np.array_equal(se.ctx.get_last_accept(B.layout), acc_o)
             assert rel_err(se.ctx.get_X(0), ora.X(0)) < 1e-9
     assert all((H.accpt_rate(B, (0, nit - 1)) > 0).all() for B in blocks)
@@ -100,7 +100,7 @@ def test_inference_tutorial_parameter_update(orc, olib):
     n_par_acc = 0
     for i in range(nit):
         H.draw_proposal_path(be, i); H.accept_reject_proposal_path(be, i)
-        ora.draw(0, i); ora.accept(0, i)
+        ora.draw(0, i); ora.accept(0, i, layout_id=be.layout)
         # parameter update
         g_o = gamma + 2 * 0.3 * (rng.random() - 0.5)
         H.set_proposal_law(be, [g_o], pnames, True)
