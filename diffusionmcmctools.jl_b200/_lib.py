@@ -79,6 +79,8 @@ SIGNATURES = {
     "dmt_get_last_accept": (C.c_int32, [_vp, C.c_int32, _bp]),
     "dmt_get_guiding_term": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _dp]),
     "dmt_upload_guiding_term": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _dp]),
+    "dmt_debug_normals": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, _dp]),
+    "dmt_debug_exponentials": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, _dp]),
     "dmt_nccl_unique_id": (C.c_int32, [_bp]),
     "dmt_comm_init": (C.c_int32, [_vp, C.c_int32, C.c_int32, _bp]),
     "dmt_allreduce_stats": (C.c_int32, [_vp, C.c_int32, _dp]),
@@ -364,6 +366,17 @@ class Ctx:
         n, d = int(self.n_pts[k]), self.d
         H = _f64(H, (n, d, d, self.P)); F = _f64(F, (n, d, self.P)); c = _f64(c, (n, self.P))
         self._ck(self.lib.dmt_upload_guiding_term(self.h, side, store, k, _p(H), _p(F), _p(c)))
+
+    # -- test hooks
+    def debug_normals(self, chain0, tile0, it, n_chains, n_tiles):
+        out = np.empty((n_chains, n_tiles, 4 * self.dw))
+        self._ck(self.lib.dmt_debug_normals(self.h, chain0, tile0, it, n_chains, n_tiles, _p(out)))
+        return out
+
+    def debug_exponentials(self, chain0, it, layout, n_chains, n_blocks):
+        out = np.empty((n_chains, n_blocks))
+        self._ck(self.lib.dmt_debug_exponentials(self.h, chain0, it, layout, n_chains, n_blocks, _p(out)))
+        return out
 
     # -- multi-GPU
     @staticmethod

@@ -2,6 +2,7 @@
 // No torch types, no CPU fallback: every compute entry point launches sm_100a kernels or fails.
 #include "../../include/dmt.h"
 #include "kernels.cuh"
+#include "fwd_kernel.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -169,10 +170,21 @@ void check_range(dmt_ctx *c, int k0, int k1) { REQUIRE(0 <= k0 && k0 <= k1 && k1
 dim3 chain_grid(dmt_ctx *c, int ny, int tpb) { return dim3((c->M + tpb - 1) / tpb, ny, 1); }
 dim3 pset_grid(dmt_ctx *c, int ny, int tpb, int nz = 1) { return dim3((c->P + tpb - 1) / tpb, ny, nz); }
 
+template <class MD, int OP> void launch_fwd_model(dmt_ctx *c, Layout &L, const FwdArgs &fa) {
+    constexpr int TPB = (MD::D >= 6) ? 32 : FWD_TPB; // wide guiding terms: smaller CTAs keep the smem ring under 64 KB
+    constexpr size_t smem = fwd_smem_bytes<MD, TPB>();
+    static bool attr_done[64] = {};
+    const int dev = c->cfg.device & 63;
+    if (!attr_done[dev]) {
+        CK(cudaFuncSetAttribute(fwd_kernel<MD, OP, TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done[dev] = true;
+    }
+    fwd_kernel<MD, OP, TPB><<<chain_grid(c, L.nb, TPB), TPB, smem, c->stream>>>(c->dev, L.dev, fa);
+}
+
 template <int OP> void launch_fwd(dmt_ctx *c, Layout &L, const FwdArgs &fa) {
-    dim3 grid = chain_grid(c, L.nb, FWD_TPB);
 #define DMT_CASE(MID)                                                                                              \
-    case MID: fwd_kernel<Model<MID>, OP><<<grid, FWD_TPB, 0, c->stream>>>(c->dev, L.dev, fa); break;
+    case MID: launch_fwd_model<Model<MID>, OP>(c, L, fa); break;
     switch (c->cfg.model) {
         DMT_FOR_MODELS(DMT_CASE)
         default: throw DmtError(DMT_ERR_UNSUPPORTED, "model not compiled into this build of libdmt");
@@ -320,6 +332,12 @@ int32_t dmt_create(const dmt_config *cfg, const int32_t *n_pts, const double *tt
         REQUIRE(cfg->device >= 0 && cfg->device < ndev, DMT_ERR_ARG, "device ordinal out of range");
         CK(cudaSetDevice(cfg->device));
         CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        {   // every lane streams whole 32-byte sectors that it alone owns (kernels.cuh): ask L2 not to promote DRAM fetches to
+            // 64/128 B, which only drags in sectors of the other accepted/proposal buffer.  DMT_L2_FETCH overrides (tuning).
+            size_t gran = 32;
+            if (const char *e = getenv("DMT_L2_FETCH")) gran = (size_t)atoi(e);
+            if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+        }
 
         // ---- time grid -> tiles
         const int K = c->K;
@@ -831,6 +849,39 @@ int32_t dmt_get_guiding_term(dmt_ctx *ctx, int32_t side, int32_t store, int32_t 
 }
 int32_t dmt_upload_guiding_term(dmt_ctx *ctx, int32_t side, int32_t store, int32_t k, const double *H, const double *F, const double *c) {
     return guarded(ctx, [&] { xfer_guiding(ctx, side, store, k, (double *)H, (double *)F, (double *)c, true); });
+}
+
+// ---------------------------------------------------------------------------------------------------------------- test hooks
+int32_t dmt_debug_normals(dmt_ctx *ctx, uint32_t chain0, uint32_t tile0, uint32_t iter, int32_t n_chains, int32_t n_tiles, double *out) {
+    return guarded(ctx, [&] {
+        REQUIRE(out && n_chains > 0 && n_tiles > 0, DMT_ERR_ARG, "bad arguments");
+        const size_t n = (size_t)n_chains * n_tiles * 4 * ctx->DW;
+        DevBuf<double> d;
+        d.alloc(n, false);
+        const int tot = n_chains * n_tiles;
+        dim3 grid((tot + 127) / 128);
+        switch (ctx->DW) {
+        case 1: debug_normals_kernel<1><<<grid, 128, 0, ctx->stream>>>(ctx->cfg.seed, chain0, tile0, iter, n_chains, n_tiles, d.p); break;
+        case 2: debug_normals_kernel<2><<<grid, 128, 0, ctx->stream>>>(ctx->cfg.seed, chain0, tile0, iter, n_chains, n_tiles, d.p); break;
+        case 3: debug_normals_kernel<3><<<grid, 128, 0, ctx->stream>>>(ctx->cfg.seed, chain0, tile0, iter, n_chains, n_tiles, d.p); break;
+        default: debug_normals_kernel<4><<<grid, 128, 0, ctx->stream>>>(ctx->cfg.seed, chain0, tile0, iter, n_chains, n_tiles, d.p); break;
+        }
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(out, d.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    });
+}
+int32_t dmt_debug_exponentials(dmt_ctx *ctx, uint32_t chain0, uint32_t iter, uint32_t layout, int32_t n_chains, int32_t n_blocks, double *out) {
+    return guarded(ctx, [&] {
+        REQUIRE(out && n_chains > 0 && n_blocks > 0, DMT_ERR_ARG, "bad arguments");
+        const int tot = n_chains * n_blocks;
+        DevBuf<double> d;
+        d.alloc(tot, false);
+        debug_exponentials_kernel<<<(tot + 127) / 128, 128, 0, ctx->stream>>>(ctx->cfg.seed, chain0, iter, layout, n_chains, n_blocks, d.p);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(out, d.p, tot * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    });
 }
 
 // ---------------------------------------------------------------------------------------------------------------- multi-GPU

@@ -1,0 +1,250 @@
+// fwd_kernel.cuh — the forward kernel (K2/K3/K4/K5).
+//
+// Memory discipline (measured with scripts/stream_pattern.cu on B200, profiles/r01_stream_pattern.txt): the
+// [tile][component][chain][4] layout streams at 7.0 TB/s when EVERY SECTOR CROSSES L2 EXACTLY ONCE, i.e. one 256-bit
+// LDG/STG per lane per sector.  Anything that touches a sector twice at L2 loses: cp.async in 16-byte pieces caps at
+// 4.6 TB/s, prefetch.global.L2 followed by the demand load costs a second L2 access (5.3-5.7 vs 6.9 TB/s at equal thread
+// count).  So the tile's sectors are loaded straight into registers at the top of the tile, all at once (up to
+// d(d+1)/2 + 2d + dw independent 256-bit loads in flight per lane), and the refreshed noise is streamed out before the
+// recursion starts so the stores overlap the arithmetic.
+#pragma once
+#include "kernels.cuh"
+
+namespace dmt {
+
+template <int NG> struct GTile { // where the guiding term of interval k lives for this thread's pset / law side
+    const double *base;          // tile 0, component 0, this pset
+    int store, slot;
+};
+template <int NG>
+__device__ __forceinline__ GTile<NG> g_tile_of(const DevCtx &cx, int k, int i1, bool last, int law_side, int ps) {
+    GTile<NG> t;
+    t.store = (k == i1 && !last) ? 1 : 0; // P_last comes from PPb (src/block.jl:68)
+    t.slot = law_side ^ cx.parP[t.store][(size_t)k * cx.P + ps];
+    const int gt0 = t.store ? cx.ppb_tile0[k] : cx.tile0[k];
+    t.base = cx.G[t.slot][t.store] + ((size_t)gt0 * NG * cx.P + ps) * 4;
+    return t;
+}
+
+// One thread = one (chain, block).  grid = (ceil(M/TPB), n_blocks).  Replaces, per OP:
+//   OP_DRAW        draw_proposal_path!(bb)            src/biblock.jl:80-106   (pCN + guided EM + ll, fused; K3+K2+K4)
+//   OP_RECOMPUTE   recompute_path!(b°, b.WW; skip)    src/block.jl:161-187    (K2+K4)
+//   OP_LOGLIK      loglikhd!(b)                       src/block.jl:140-152    (K4)
+//   OP_INVSOLVE    find_W_for_X!(b)                   src/block.jl:120-131    (K5)
+//   OP_INVSOLVE_LL both of the above in one pass over X
+//   OP_INIT        init_paths! / draw_proposal_path!(u::SamplingUnit)  src/sampling_unit.jl:83-87,118-120 (fresh noise, in place)
+#ifdef DMT_FWD_MAXREG
+#define DMT_FWD_BOUNDS __maxnreg__(DMT_FWD_MAXREG)
+#else
+#define DMT_FWD_BOUNDS __launch_bounds__(TPB, DMT_FWD_MINB)
+#endif
+template <class MD, int OP, int TPB>
+__global__ void DMT_FWD_BOUNDS fwd_kernel(const DevCtx cx, const LayoutDev ly, const FwdArgs fa) {
+    constexpr int D = MD::D, DW = MD::DW, NPAR = MD::NPAR, NH = D * (D + 1) / 2, NG = NH + D, NAUX = D * D + D + NH;
+    constexpr bool READS_X = (OP == OP_LOGLIK || OP == OP_INVSOLVE || OP == OP_INVSOLVE_LL);
+    constexpr bool WRITES_X = (OP == OP_DRAW || OP == OP_RECOMPUTE || OP == OP_INIT);
+    constexpr bool READS_W = (OP == OP_DRAW || OP == OP_RECOMPUTE);
+    constexpr bool WRITES_W = (OP == OP_DRAW || OP == OP_INIT || OP == OP_INVSOLVE || OP == OP_INVSOLVE_LL);
+    constexpr bool WANT_LL = (OP != OP_INVSOLVE);
+    constexpr bool RNG = (OP == OP_DRAW || OP == OP_INIT);
+
+    const int c = blockIdx.x * TPB + threadIdx.x;
+    const int b = blockIdx.y;
+    if (c >= cx.M) return;
+    const size_t M = cx.M, P = cx.P;
+    if (OP == OP_INIT && ly.ok[(size_t)b * M + c]) return; // retry only the chains that failed so far
+    const int ps = cx.pset[c];
+    const int i0 = ly.i0[b], i1 = ly.i1[b];
+    const bool last = ly.last[b] != 0;
+
+    const int law_side = (OP == OP_RECOMPUTE || OP == OP_LOGLIK) ? fa.law_side : 0;
+    const int xin_side = law_side;
+    const int xout_side = (OP == OP_DRAW) ? 1 : law_side;
+    const int win_side = (OP == OP_RECOMPUTE) ? fa.w_side : 0;
+    const int wout_side = (OP == OP_DRAW) ? 1 : 0;
+    const int ll_side = (OP == OP_DRAW) ? 1 : law_side;
+    const double rho = (OP == OP_DRAW) ? ly.rho[b] : 0.0;
+    const double crho = (OP == OP_DRAW) ? sqrt(1.0 - rho * rho) : 1.0;
+    const int skip = fa.skip;
+    const size_t gstr = P * 4; // doubles between components of one tile
+
+    double x[D];
+    {   // y1 = XX[1].x[1] of the block  (src/biblock.jl:96, src/block.jl:177)
+        const int sl = xin_side ^ cx.parX[(size_t)i0 * M + c];
+#pragma unroll
+        for (int i = 0; i < D; i++) x[i] = cx.X0[sl * cx.X0buf + ((size_t)i0 * D + i) * M + c];
+    }
+    double ll = 0.0;
+    bool ok = true;
+
+    for (int k = i0; k <= i1 && ok; ++k) {
+        const GTile<NG> gt = g_tile_of<NG>(cx, k, i1, last, law_side, ps);
+        const int store = gt.store, slotL = gt.slot;
+        const double *Gp = gt.base;
+        double th[NPAR];
+        {
+            const double *tp = cx.theta[slotL][store] + (size_t)k * NPAR * P + ps;
+#pragma unroll
+            for (int i = 0; i < NPAR; i++) th[i] = tp[(size_t)i * P];
+        }
+        const typename MD::Par par(th);
+        double Bm[D * D], beta[D], at[NH];
+        if (WANT_LL) {
+            const double *ap = cx.aux[slotL][store] + (size_t)k * NAUX * P + ps;
+#pragma unroll
+            for (int i = 0; i < D * D; i++) Bm[i] = ap[(size_t)i * P];
+#pragma unroll
+            for (int i = 0; i < D; i++) beta[i] = ap[(size_t)(D * D + i) * P];
+            if (!MD::CONSTDIFF) {
+#pragma unroll
+                for (int i = 0; i < NH; i++) at[i] = ap[(size_t)(D * D + D + i) * P];
+            }
+        }
+        const int nst = cx.nsteps[k];
+        const int t0 = cx.tile0[k];
+        const uint8_t pw = cx.parW[(size_t)k * M + c], px = cx.parX[(size_t)k * M + c];
+        const double *Win = cx.W + (size_t)(win_side ^ pw) * cx.Wbuf + ((size_t)t0 * DW * M + c) * 4;
+        double *Wout = cx.W + (size_t)(wout_side ^ pw) * cx.Wbuf + ((size_t)t0 * DW * M + c) * 4;
+        const double *Xin = cx.X + (size_t)(xin_side ^ px) * cx.Xbuf + ((size_t)t0 * D * M + c) * 4;
+        double *Xout = cx.X + (size_t)(xout_side ^ px) * cx.Xbuf + ((size_t)t0 * D * M + c) * 4;
+        if (READS_X && k > i0) { // an existing path: interval k starts at ITS OWN XX[k].x[1]
+#pragma unroll
+            for (int i = 0; i < D; i++) x[i] = cx.X0[(size_t)(xin_side ^ px) * cx.X0buf + ((size_t)k * D + i) * M + c];
+        }
+        if (WRITES_X) { // XX°[k].x[1] = y1
+            double *x0p = cx.X0 + (size_t)(xout_side ^ px) * cx.X0buf + (size_t)k * D * M + c;
+#pragma unroll
+            for (int i = 0; i < D; i++) x0p[(size_t)i * M] = x[i];
+        }
+
+        const int ntl = (nst + 3) >> 2;
+        for (int q = 0; q < ntl; ++q) {
+            double g[NG][4], w[DW][4], xt[D][4], dt4[4], sq4[4];
+            // ---- every sector of the tile, once, straight into registers
+            if (READS_W) {
+#pragma unroll
+                for (int j = 0; j < DW; j++) ld256(Win + ((size_t)q * DW + j) * M * 4, w[j]);
+            }
+#pragma unroll
+            for (int a = 0; a < NG; a++) ld256(Gp + ((size_t)q * NG + a) * gstr, g[a]);
+            if (READS_X) {
+#pragma unroll
+                for (int i = 0; i < D; i++) ld256(Xin + ((size_t)q * D + i) * M * 4, xt[i]);
+            }
+            ld256u(cx.dt + (size_t)(t0 + q) * 4, dt4);
+            if (RNG) ld256u(cx.sqdt + (size_t)(t0 + q) * 4, sq4);
+
+            if (RNG) { // K3: dW° = rho dW + sqrt(1-rho^2) sqrt(dt) xi   (A.2) — needs only W: runs while H,F are in flight
+                double z[4 * DW];
+                if (fa.Z) {
+#pragma unroll
+                    for (int s = 0; s < 4; s++)
+#pragma unroll
+                        for (int j = 0; j < DW; j++) {
+                            const int i = 4 * q + s;
+                            z[s * DW + j] = (i < nst) ? fa.Z[((size_t)(cx.step0[k] + i) * DW + j) * M + c] : 0.0;
+                        }
+                } else {
+#if defined(DMT_EXP_NORNG) // (experiment only: time the kernel without the generator)
+#pragma unroll
+                    for (int s = 0; s < 4 * DW; s++) z[s] = 0.5;
+#else
+                    tile_normals<DW>(cx.seed, cx.chain_offset + (uint32_t)c, (uint32_t)(t0 + q), fa.iter, z);
+#endif
+                }
+#pragma unroll
+                for (int s = 0; s < 4; s++)
+#pragma unroll
+                    for (int j = 0; j < DW; j++) {
+                        if (OP == OP_DRAW) w[j][s] = rho * w[j][s] + crho * sq4[s] * z[s * DW + j];
+                        else w[j][s] = sq4[s] * z[s * DW + j];
+                    }
+#pragma unroll
+                for (int j = 0; j < DW; j++) st256(Wout + ((size_t)q * DW + j) * M * 4, w[j]); // final: stream out now
+            }
+
+            if (WANT_LL && k == i0 && q == 0) { // loglikhd_obs(PP[1], y1) = -c - y'Hy/2 + F'y  (src/block.jl:178)
+                double s0 = -cx.c0[slotL][store][(size_t)k * P + ps];
+#pragma unroll
+                for (int i = 0; i < D; i++) {
+                    double hx = 0.0;
+#pragma unroll
+                    for (int j = 0; j < D; j++) hx = fma(g[sidx<D>(i, j)][0], x[j], hx);
+                    s0 += x[i] * (g[NH + i][0] - 0.5 * hx);
+                }
+                ll = s0;
+            }
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                const int i = 4 * q + s;
+                if (i < nst && ok) {
+                    double Hs[NH], F[D], gd[D], G = 0.0;
+#pragma unroll
+                    for (int a = 0; a < NH; a++) Hs[a] = g[a][s];
+#pragma unroll
+                    for (int a = 0; a < D; a++) F[a] = g[NH + a][s];
+                    const typename MD::Diff df(par, x);
+#if defined(DMT_EXP_NOEM) // (experiment only: time the kernel without the drift / guiding arithmetic)
+#pragma unroll
+                    for (int a = 0; a < D; a++) gd[a] = Hs[a] + F[a];
+#else
+                    guided_terms<MD, WANT_LL>(par, df, Bm, beta, at, Hs, F, x, gd, G);
+#endif
+                    if (WANT_LL && i < nst - skip) ll = fma(G, dt4[s], ll);
+                    double xn[D];
+                    if (WRITES_X) { // K2: x' = x + (b + a r) dt + sigma dW   (A.3)
+                        double dwv[DW], sw[D];
+#pragma unroll
+                        for (int j = 0; j < DW; j++) dwv[j] = w[j][s];
+                        df.sig_mul(dwv, sw);
+#pragma unroll
+                        for (int a = 0; a < D; a++) xn[a] = fma(gd[a], dt4[s], x[a]) + sw[a];
+                        bool fin = df.ok();
+#pragma unroll
+                        for (int a = 0; a < D; a++) fin = fin && isfinite(xn[a]);
+                        if (!(fin && MD::bound_ok(par, xn))) { ok = false; ll = -INFINITY; } // src/block.jl:181
+#pragma unroll
+                        for (int a = 0; a < D; a++) xt[a][s] = xn[a];
+                    } else {
+#pragma unroll
+                        for (int a = 0; a < D; a++) xn[a] = xt[a][s];
+                        if (OP == OP_INVSOLVE || OP == OP_INVSOLVE_LL) { // K5: dW = sigma^+ (x' - x - (b + a r) dt)   (A.5)
+                            double res[D], dwv[DW];
+#pragma unroll
+                            for (int a = 0; a < D; a++) res[a] = xn[a] - x[a] - gd[a] * dt4[s];
+                            df.inv_sig(res, dwv);
+#pragma unroll
+                            for (int j = 0; j < DW; j++) w[j][s] = dwv[j];
+                        }
+                    }
+#pragma unroll
+                    for (int a = 0; a < D; a++) x[a] = xn[a];
+                } else {
+                    if (WRITES_X) {
+#pragma unroll
+                        for (int a = 0; a < D; a++) xt[a][s] = 0.0;
+                    }
+                    if (WRITES_W && !RNG) {
+#pragma unroll
+                        for (int j = 0; j < DW; j++) w[j][s] = 0.0;
+                    }
+                }
+            }
+            if (WRITES_W && !RNG) {
+#pragma unroll
+                for (int j = 0; j < DW; j++) st256(Wout + ((size_t)q * DW + j) * M * 4, w[j]);
+            }
+            if (WRITES_X) {
+#pragma unroll
+                for (int i = 0; i < D; i++) st256(Xout + ((size_t)q * D + i) * M * 4, xt[i]);
+            }
+            if (!ok) break;
+        }
+    }
+    if (WANT_LL) ly.ll[((size_t)ll_side * ly.nb + b) * M + c] = ll;
+    if (WRITES_X) ly.ok[(size_t)b * M + c] = ok ? 1 : 0;
+}
+
+template <class MD, int TPB> constexpr size_t fwd_smem_bytes() { return 0; }
+
+} // namespace dmt

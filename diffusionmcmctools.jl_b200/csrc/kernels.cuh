@@ -155,8 +155,10 @@ __device__ __forceinline__ void guided_terms(const typename MD::Par &par, const 
 //   OP_INVSOLVE    find_W_for_X!(b)                   src/block.jl:120-131    (K5)
 //   OP_INVSOLVE_LL both of the above in one pass over X
 //   OP_INIT        init_paths! / draw_proposal_path!(u::SamplingUnit)  src/sampling_unit.jl:83-87,118-120 (fresh noise, in place)
+// (v1: whole tile in registers, no shared memory.  Superseded by fwd_kernel in fwd_kernel.cuh, which stages the guiding
+//  term through a cp.async shared-memory pipeline; kept as the A/B reference: build with -DDMT_FWD_V1=1.)
 template <class MD, int OP>
-__global__ void __launch_bounds__(FWD_TPB, DMT_FWD_MINB) fwd_kernel(const DevCtx cx, const LayoutDev ly, const FwdArgs fa) {
+__global__ void __launch_bounds__(FWD_TPB, DMT_FWD_MINB) fwd_kernel_v1(const DevCtx cx, const LayoutDev ly, const FwdArgs fa) {
     constexpr int D = MD::D, DW = MD::DW, NPAR = MD::NPAR, NH = D * (D + 1) / 2, NG = NH + D, NAUX = D * D + D + NH;
     constexpr bool READS_X = (OP == OP_LOGLIK || OP == OP_INVSOLVE || OP == OP_INVSOLVE_LL);
     constexpr bool WRITES_X = (OP == OP_DRAW || OP == OP_RECOMPUTE || OP == OP_INIT);
@@ -366,48 +368,60 @@ __global__ void __launch_bounds__(FWD_TPB, DMT_FWD_MINB) fwd_kernel(const DevCtx
 }
 
 // =========================================================================================== K1 backward filter
-template <int D>
+template <int D, bool DIAG>
 __device__ __forceinline__ void hfc_rhs(const double *Bm, const double *beta, const double *at, const double *H, const double *F,
                                         double *dH, double *dF, double &dc) {
-    // dH = -B'H - HB + H at H ; dF = -B'F + H at F + H beta ; dc = beta'F + F' at F/2 - tr(H at)/2   (A.1)
-    double M1[D][D], N[D][D];
+    // dH = -B'H - HB + H at H ; dF = -B'F + H at F + H beta ; dc = beta'F + F' at F/2 - tr(H at)/2   (A.1), arranged as
+    //   N = at H,  C = B - N/2,  C2 = B - N :   dH = -(HC + (HC)'),   dF = H beta - C2'F      (H, at symmetric)
+    // which needs one d^3 product instead of three; DIAG: at is diagonal, N is a row scaling of H.
+    double C[D][D], C2[D][D], tr = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; k++)
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+            double n;
+            if (DIAG) n = at[sidx<D>(k, k)] * H[sidx<D>(k, j)];
+            else {
+                n = 0.0;
+#pragma unroll
+                for (int l = 0; l < D; l++) n = fma(at[sidx<D>(k, l)], H[sidx<D>(l, j)], n);
+            }
+            C2[k][j] = Bm[k * D + j] - n;
+            C[k][j] = fma(-0.5, n, Bm[k * D + j]);
+            if (k == j) tr += n;
+        }
+    double Mx[D][D];
 #pragma unroll
     for (int i = 0; i < D; i++)
 #pragma unroll
         for (int j = 0; j < D; j++) {
-            double s1 = 0.0, s2 = 0.0;
+            double s = 0.0;
 #pragma unroll
-            for (int k = 0; k < D; k++) {
-                s1 = fma(H[sidx<D>(i, k)], Bm[k * D + j], s1);
-                s2 = fma(H[sidx<D>(i, k)], at[sidx<D>(k, j)], s2);
-            }
-            M1[i][j] = s1;
-            N[i][j] = s2;
+            for (int k = 0; k < D; k++) s = fma(H[sidx<D>(i, k)], C[k][j], s);
+            Mx[i][j] = s;
         }
 #pragma unroll
     for (int i = 0; i < D; i++)
 #pragma unroll
-        for (int j = i; j < D; j++) {
-            double s = -(M1[i][j] + M1[j][i]);
-#pragma unroll
-            for (int k = 0; k < D; k++) s = fma(N[i][k], H[sidx<D>(k, j)], s);
-            dH[sidx<D>(i, j)] = s;
-        }
-    double tr = 0.0, bF = 0.0, FaF = 0.0;
+        for (int j = i; j < D; j++) dH[sidx<D>(i, j)] = -(Mx[i][j] + Mx[j][i]);
+    double bF = 0.0, FaF = 0.0;
 #pragma unroll
     for (int i = 0; i < D; i++) {
-        double s = 0.0, aF = 0.0;
+        double s = 0.0;
 #pragma unroll
         for (int k = 0; k < D; k++) {
-            s = fma(-Bm[k * D + i], F[k], s);
-            s = fma(N[i][k], F[k], s);
             s = fma(H[sidx<D>(i, k)], beta[k], s);
-            aF = fma(at[sidx<D>(i, k)], F[k], aF);
+            s = fma(-C2[k][i], F[k], s);
         }
         dF[i] = s;
-        tr += N[i][i];
         bF = fma(beta[i], F[i], bF);
-        FaF = fma(F[i], aF, FaF);
+        if (DIAG) FaF = fma(at[sidx<D>(i, i)] * F[i], F[i], FaF);
+        else {
+            double aF = 0.0;
+#pragma unroll
+            for (int k = 0; k < D; k++) aF = fma(at[sidx<D>(i, k)], F[k], aF);
+            FaF = fma(F[i], aF, FaF);
+        }
     }
     dc = bF + 0.5 * FaF - 0.5 * tr;
 }
@@ -587,98 +601,118 @@ __global__ void __launch_bounds__(BWD_TPB) bwd_kernel(const DevCtx cx, const Lay
         const size_t gstr = P * 4;
         const double *dtp = cx.dt + (size_t)t0 * 4;
 
+        // one grid step back of each formulation, as lambdas so that the time loop below can be written twice (see BUF)
+        double Pm[NH], nu[D], trB = 0.0, Tt = 0.0, logdet = 0.0;
+        auto step_pnu = [&](double h) { // covariance form on an exact-observation interval: RK4 on (P, nu), then H = P^-1, F = H nu
+            Tt += h;
+            double k1P[NH], k1n[D], kP[NH], kn[D], Ps[NH], ns[D], aP[NH], an[D];
+            pnu_rhs<D>(Bm, beta, at, Pm, nu, k1P, k1n);
+#pragma unroll
+            for (int i = 0; i < NH; i++) { Ps[i] = fma(-0.5 * h, k1P[i], Pm[i]); aP[i] = k1P[i]; }
+#pragma unroll
+            for (int i = 0; i < D; i++) { ns[i] = fma(-0.5 * h, k1n[i], nu[i]); an[i] = k1n[i]; }
+            pnu_rhs<D>(Bm, beta, at, Ps, ns, kP, kn);
+#pragma unroll
+            for (int i = 0; i < NH; i++) { Ps[i] = fma(-0.5 * h, kP[i], Pm[i]); aP[i] = fma(2.0, kP[i], aP[i]); }
+#pragma unroll
+            for (int i = 0; i < D; i++) { ns[i] = fma(-0.5 * h, kn[i], nu[i]); an[i] = fma(2.0, kn[i], an[i]); }
+            pnu_rhs<D>(Bm, beta, at, Ps, ns, kP, kn);
+#pragma unroll
+            for (int i = 0; i < NH; i++) { Ps[i] = fma(-h, kP[i], Pm[i]); aP[i] = fma(2.0, kP[i], aP[i]); }
+#pragma unroll
+            for (int i = 0; i < D; i++) { ns[i] = fma(-h, kn[i], nu[i]); an[i] = fma(2.0, kn[i], an[i]); }
+            pnu_rhs<D>(Bm, beta, at, Ps, ns, kP, kn);
+#pragma unroll
+            for (int i = 0; i < NH; i++) Pm[i] = fma(-h / 6.0, aP[i] + kP[i], Pm[i]);
+#pragma unroll
+            for (int i = 0; i < D; i++) nu[i] = fma(-h / 6.0, an[i] + kn[i], nu[i]);
+            spd_inverse<D>(Pm, H, logdet);
+#pragma unroll
+            for (int i = 0; i < D; i++) {
+                double sacc = 0.0;
+#pragma unroll
+                for (int q = 0; q < D; q++) sacc = fma(H[sidx<D>(i, q)], nu[q], sacc);
+                F[i] = sacc;
+            }
+        };
+        auto step_hfc = [&](double h) { // classical RK4 on (H, F, c) from t[j+1] back to t[j]
+            double kH[NH], kF[D], kc, aH[NH], aF[D], ac, Hs[NH], Fs[D];
+            hfc_rhs<D, MD::ATIL_DIAG>(Bm, beta, at, H, F, kH, kF, kc);
+#pragma unroll
+            for (int i = 0; i < NH; i++) { Hs[i] = fma(-0.5 * h, kH[i], H[i]); aH[i] = kH[i]; }
+#pragma unroll
+            for (int i = 0; i < D; i++) { Fs[i] = fma(-0.5 * h, kF[i], F[i]); aF[i] = kF[i]; }
+            ac = kc;
+            hfc_rhs<D, MD::ATIL_DIAG>(Bm, beta, at, Hs, Fs, kH, kF, kc);
+#pragma unroll
+            for (int i = 0; i < NH; i++) { Hs[i] = fma(-0.5 * h, kH[i], H[i]); aH[i] = fma(2.0, kH[i], aH[i]); }
+#pragma unroll
+            for (int i = 0; i < D; i++) { Fs[i] = fma(-0.5 * h, kF[i], F[i]); aF[i] = fma(2.0, kF[i], aF[i]); }
+            ac = fma(2.0, kc, ac);
+            hfc_rhs<D, MD::ATIL_DIAG>(Bm, beta, at, Hs, Fs, kH, kF, kc);
+#pragma unroll
+            for (int i = 0; i < NH; i++) { Hs[i] = fma(-h, kH[i], H[i]); aH[i] = fma(2.0, kH[i], aH[i]); }
+#pragma unroll
+            for (int i = 0; i < D; i++) { Fs[i] = fma(-h, kF[i], F[i]); aF[i] = fma(2.0, kF[i], aF[i]); }
+            ac = fma(2.0, kc, ac);
+            hfc_rhs<D, MD::ATIL_DIAG>(Bm, beta, at, Hs, Fs, kH, kF, kc);
+            const double h6 = h / 6.0;
+#pragma unroll
+            for (int i = 0; i < NH; i++) H[i] = fma(-h6, aH[i] + kH[i], H[i]);
+#pragma unroll
+            for (int i = 0; i < D; i++) F[i] = fma(-h6, aF[i] + kF[i], F[i]);
+            cc = fma(-h6, ac + kc, cc);
+        };
         if (store) { // exact artificial observation (guid_prop_for_blocking, src/sampling_unit.jl:61-66)
-            double Pm[NH], nu[D];
 #pragma unroll
             for (int i = 0; i < D; i++)
 #pragma unroll
                 for (int j = i; j < D; j++) Pm[sidx<D>(i, j)] = (i == j) ? cx.eps : 0.0;
 #pragma unroll
             for (int i = 0; i < D; i++) nu[i] = cx.vart[slot][((size_t)k * D + i) * P + ps];
-            double trB = 0.0, Tt = 0.0;
 #pragma unroll
             for (int i = 0; i < D; i++) trB += Bm[i * D + i];
-            for (int j = nst - 1; j >= 0; --j) {
-                const double h = dtp[j];
-                Tt += h;
-                double k1P[NH], k1n[D], kP[NH], kn[D], Ps[NH], ns[D], aP[NH], an[D];
-                pnu_rhs<D>(Bm, beta, at, Pm, nu, k1P, k1n);
-#pragma unroll
-                for (int i = 0; i < NH; i++) { Ps[i] = fma(-0.5 * h, k1P[i], Pm[i]); aP[i] = k1P[i]; }
-#pragma unroll
-                for (int i = 0; i < D; i++) { ns[i] = fma(-0.5 * h, k1n[i], nu[i]); an[i] = k1n[i]; }
-                pnu_rhs<D>(Bm, beta, at, Ps, ns, kP, kn);
-#pragma unroll
-                for (int i = 0; i < NH; i++) { Ps[i] = fma(-0.5 * h, kP[i], Pm[i]); aP[i] = fma(2.0, kP[i], aP[i]); }
-#pragma unroll
-                for (int i = 0; i < D; i++) { ns[i] = fma(-0.5 * h, kn[i], nu[i]); an[i] = fma(2.0, kn[i], an[i]); }
-                pnu_rhs<D>(Bm, beta, at, Ps, ns, kP, kn);
-#pragma unroll
-                for (int i = 0; i < NH; i++) { Ps[i] = fma(-h, kP[i], Pm[i]); aP[i] = fma(2.0, kP[i], aP[i]); }
-#pragma unroll
-                for (int i = 0; i < D; i++) { ns[i] = fma(-h, kn[i], nu[i]); an[i] = fma(2.0, kn[i], an[i]); }
-                pnu_rhs<D>(Bm, beta, at, Ps, ns, kP, kn);
-#pragma unroll
-                for (int i = 0; i < NH; i++) Pm[i] = fma(-h / 6.0, aP[i] + kP[i], Pm[i]);
-#pragma unroll
-                for (int i = 0; i < D; i++) nu[i] = fma(-h / 6.0, an[i] + kn[i], nu[i]);
-                double logdet;
-                spd_inverse<D>(Pm, H, logdet);
-#pragma unroll
-                for (int i = 0; i < D; i++) {
-                    double s = 0.0;
-#pragma unroll
-                    for (int q = 0; q < D; q++) s = fma(H[sidx<D>(i, q)], nu[q], s);
-                    F[i] = s;
-                }
-                double *gp = Gp + (size_t)(j >> 2) * NG * gstr + (j & 3);
-#pragma unroll
-                for (int i = 0; i < NH; i++) gp[(size_t)i * gstr] = H[i];
-#pragma unroll
-                for (int i = 0; i < D; i++) gp[(size_t)(NH + i) * gstr] = F[i];
-                if (j == 0) { // c = d/2 log 2pi + log det P / 2 + tr(B)(T-t) + nu'H nu / 2
-                    double nF = 0.0;
-#pragma unroll
-                    for (int i = 0; i < D; i++) nF = fma(nu[i], F[i], nF);
-                    cc = 0.5 * D * 1.8378770664093453 + 0.5 * logdet + trB * Tt + 0.5 * nF;
-                }
-            }
         } else {
             obs_jump<D>(cx.m, cx.obs[slot] + (size_t)k * (cx.m * D + cx.m * cx.m + cx.m) * P + ps, P, H, F, cc);
-            for (int j = nst - 1; j >= 0; --j) { // classical RK4 from t[j+1] back to t[j]
-                const double h = dtp[j];
-                double kH[NH], kF[D], kc, aH[NH], aF[D], ac, Hs[NH], Fs[D];
-                hfc_rhs<D>(Bm, beta, at, H, F, kH, kF, kc);
+        }
+        // BUF: collect the 4 grid points of a tile in registers and write whole 32-byte sectors (one STG.256 per component)
+        // instead of 4 partial-sector stores; needs the time loop unrolled by 4, affordable for the small models only.
+        constexpr bool BUF = (NG <= 14);
+        if (BUF) {
+            for (int q = ((nst + 3) >> 2) - 1; q >= 0; --q) {
+                double tb[NG][4], dt4[4];
+                ld256u(dtp + (size_t)q * 4, dt4);
 #pragma unroll
-                for (int i = 0; i < NH; i++) { Hs[i] = fma(-0.5 * h, kH[i], H[i]); aH[i] = kH[i]; }
+                for (int sl = 3; sl >= 0; --sl) {
+                    if (4 * q + sl < nst) {
+                        if (store) step_pnu(dt4[sl]); else step_hfc(dt4[sl]);
 #pragma unroll
-                for (int i = 0; i < D; i++) { Fs[i] = fma(-0.5 * h, kF[i], F[i]); aF[i] = kF[i]; }
-                ac = kc;
-                hfc_rhs<D>(Bm, beta, at, Hs, Fs, kH, kF, kc);
+                        for (int i = 0; i < NH; i++) tb[i][sl] = H[i];
 #pragma unroll
-                for (int i = 0; i < NH; i++) { Hs[i] = fma(-0.5 * h, kH[i], H[i]); aH[i] = fma(2.0, kH[i], aH[i]); }
+                        for (int i = 0; i < D; i++) tb[NH + i][sl] = F[i];
+                    } else {
 #pragma unroll
-                for (int i = 0; i < D; i++) { Fs[i] = fma(-0.5 * h, kF[i], F[i]); aF[i] = fma(2.0, kF[i], aF[i]); }
-                ac = fma(2.0, kc, ac);
-                hfc_rhs<D>(Bm, beta, at, Hs, Fs, kH, kF, kc);
+                        for (int i = 0; i < NG; i++) tb[i][sl] = 0.0;
+                    }
+                }
 #pragma unroll
-                for (int i = 0; i < NH; i++) { Hs[i] = fma(-h, kH[i], H[i]); aH[i] = fma(2.0, kH[i], aH[i]); }
-#pragma unroll
-                for (int i = 0; i < D; i++) { Fs[i] = fma(-h, kF[i], F[i]); aF[i] = fma(2.0, kF[i], aF[i]); }
-                ac = fma(2.0, kc, ac);
-                hfc_rhs<D>(Bm, beta, at, Hs, Fs, kH, kF, kc);
-                const double h6 = h / 6.0;
-#pragma unroll
-                for (int i = 0; i < NH; i++) H[i] = fma(-h6, aH[i] + kH[i], H[i]);
-#pragma unroll
-                for (int i = 0; i < D; i++) F[i] = fma(-h6, aF[i] + kF[i], F[i]);
-                cc = fma(-h6, ac + kc, cc);
+                for (int i = 0; i < NG; i++) st256(Gp + ((size_t)q * NG + i) * gstr, tb[i]);
+            }
+        } else {
+            for (int j = nst - 1; j >= 0; --j) {
+                if (store) step_pnu(dtp[j]); else step_hfc(dtp[j]);
                 double *gp = Gp + (size_t)(j >> 2) * NG * gstr + (j & 3);
 #pragma unroll
                 for (int i = 0; i < NH; i++) gp[(size_t)i * gstr] = H[i];
 #pragma unroll
                 for (int i = 0; i < D; i++) gp[(size_t)(NH + i) * gstr] = F[i];
             }
+        }
+        if (store) { // c = d/2 log 2pi + log det P / 2 + tr(B)(T-t) + nu'H nu / 2 at the interval start
+            double nF = 0.0;
+#pragma unroll
+            for (int i = 0; i < D; i++) nF = fma(nu[i], F[i], nF);
+            cc = 0.5 * D * 1.8378770664093453 + 0.5 * logdet + trB * Tt + 0.5 * nF;
         }
         cx.c0[slot][store][(size_t)k * P + ps] = cc;
     }
@@ -880,6 +914,22 @@ __global__ void xfer_guiding_kernel(const DevCtx cx, int side, int store, int k,
         for (int q = 0; q < D * D; q++) Hn[((size_t)nst * D * D + q) * P + ps] = NAN;
         for (int q = 0; q < D; q++) Fn[((size_t)nst * D + q) * P + ps] = NAN;
     }
+}
+
+// test hook: the device's Philox -> N(0,1) / Exp(1) streams for given counters (checked against the oracle's libm versions)
+template <int DW>
+__global__ void debug_normals_kernel(uint64_t seed, uint32_t chain0, uint32_t tile0, uint32_t iter, int n_chains, int n_tiles, double *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_chains * n_tiles) return;
+    const int c = i / n_tiles, q = i % n_tiles;
+    double z[4 * DW];
+    tile_normals<DW>(seed, chain0 + (uint32_t)c, tile0 + (uint32_t)q, iter, z);
+    for (int k = 0; k < 4 * DW; k++) out[(size_t)i * 4 * DW + k] = z[k];
+}
+__global__ void debug_exponentials_kernel(uint64_t seed, uint32_t chain0, uint32_t iter, uint32_t layout, int n_chains, int n_blocks, double *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_chains * n_blocks) return;
+    out[i] = accept_exponential(seed, chain0 + (uint32_t)(i / n_blocks), (uint32_t)(i % n_blocks), iter, layout);
 }
 
 // fetch_ll / fetch_ll° / accept counts (src/block_ensemble.jl:140,152,175-179): fixed-order tree reduction

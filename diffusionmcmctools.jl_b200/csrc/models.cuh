@@ -22,6 +22,7 @@ template <int MODEL> struct Model;
 template <> struct Model<M_FHN> {
     static constexpr int D = 2, DW = 1, NPAR = 5;
     static constexpr bool CONSTDIFF = true;
+    static constexpr bool ATIL_DIAG = true; // a = sigma sigma' of this law is diagonal => so is the auxiliary atilde (K1 exploits it)
     struct Par {
         double ieps, s, gam, bet, sig, sig2, isig;
         __device__ explicit Par(const double *th) : ieps(1.0 / th[0]), s(th[1]), gam(th[2]), bet(th[3]), sig(th[4]), sig2(th[4] * th[4]), isig(1.0 / th[4]) {}
@@ -50,6 +51,7 @@ template <> struct Model<M_FHN> {
 template <> struct Model<M_LV> {
     static constexpr int D = 2, DW = 2, NPAR = 6;
     static constexpr bool CONSTDIFF = true;
+    static constexpr bool ATIL_DIAG = true; // a = sigma sigma' of this law is diagonal => so is the auxiliary atilde (K1 exploits it)
     struct Par {
         double al, be, ga, de, s1, s2;
         __device__ explicit Par(const double *th) : al(th[0]), be(th[1]), ga(th[2]), de(th[3]), s1(th[4]), s2(th[5]) {}
@@ -78,6 +80,7 @@ template <> struct Model<M_LV> {
 template <> struct Model<M_LORENZ> {
     static constexpr int D = 3, DW = 3, NPAR = 4;
     static constexpr bool CONSTDIFF = true;
+    static constexpr bool ATIL_DIAG = true; // a = sigma sigma' of this law is diagonal => so is the auxiliary atilde (K1 exploits it)
     struct Par {
         double t1, t2, t3, s, s2, is;
         __device__ explicit Par(const double *th) : t1(th[0]), t2(th[1]), t3(th[2]), s(th[3]), s2(th[3] * th[3]), is(1.0 / th[3]) {}
@@ -109,6 +112,7 @@ template <> struct Model<M_LORENZ> {
 template <> struct Model<M_PROK> {
     static constexpr int D = 4, DW = 4, NPAR = 9;
     static constexpr bool CONSTDIFF = false;
+    static constexpr bool ATIL_DIAG = false;
     struct Par {
         double c[8], K;
         __device__ explicit Par(const double *th) {
@@ -229,6 +233,7 @@ template <> struct Model<M_PROK> {
 template <> struct Model<M_JR> {
     static constexpr int D = 6, DW = 1, NPAR = 10;
     static constexpr bool CONSTDIFF = true;
+    static constexpr bool ATIL_DIAG = true; // a = sigma sigma' of this law is diagonal => so is the auxiliary atilde (K1 exploits it)
     struct Par {
         double A, a, B, b, C1, C2, C3, C4, numax, v0, r, mu, sigy, sigy2, isigy;
         __device__ explicit Par(const double *th)
@@ -280,6 +285,7 @@ template <> struct Model<M_JR> {
 template <> struct Model<M_OU2> {
     static constexpr int D = 2, DW = 2, NPAR = 8;
     static constexpr bool CONSTDIFF = true;
+    static constexpr bool ATIL_DIAG = true; // a = sigma sigma' of this law is diagonal => so is the auxiliary atilde (K1 exploits it)
     struct Par {
         double B[4], be[2], s1, s2;
         __device__ explicit Par(const double *th) : s1(th[6]), s2(th[7]) {

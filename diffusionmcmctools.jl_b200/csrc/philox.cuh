@@ -8,6 +8,10 @@
 // One call -> 128 bits -> two 53-bit uniforms -> one Box–Muller pair.  Z never touches HBM.
 #pragma once
 #include <stdint.h>
+#ifndef DMT_LIBDEVICE_MATH
+#define DMT_LIBDEVICE_MATH 0 // 1: libdevice log/sqrt/sincospi (reference for the custom versions in fastmath.cuh)
+#endif
+#include "fastmath.cuh"
 
 namespace dmt {
 
@@ -38,9 +42,15 @@ __device__ __forceinline__ void box_muller(u32x4 o, double &z0, double &z1) {
     uint64_t w0 = ((uint64_t)o.y << 32) | o.x, w1 = ((uint64_t)o.w << 32) | o.z;
     double u1 = (double)((w0 >> 11) + 1ull) * 0x1.0p-53;
     double u2 = (double)(w1 >> 11) * 0x1.0p-53;
+#if DMT_LIBDEVICE_MATH
     double r = sqrt(-2.0 * log(u1));
     double s, c;
     sincospi(2.0 * u2, &s, &c);
+#else
+    double r = sqrt_nonneg(-2.0 * log_pos_normal(u1));
+    double s, c;
+    sincospi_02(u2 + u2, s, c);
+#endif
     z0 = r * c;
     z1 = r * s;
 }
@@ -60,7 +70,11 @@ __device__ __forceinline__ double accept_exponential(uint64_t seed, uint32_t cha
     u32x4 c = {chain, block, iter, (STREAM_ACC << 8) | layout};
     u32x4 o = philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
     uint64_t w0 = ((uint64_t)o.y << 32) | o.x;
+#if DMT_LIBDEVICE_MATH
     return -log((double)((w0 >> 11) + 1ull) * 0x1.0p-53);
+#else
+    return -log_pos_normal((double)((w0 >> 11) + 1ull) * 0x1.0p-53);
+#endif
 }
 
 } // namespace dmt

@@ -162,6 +162,13 @@ int32_t dmt_get_last_accept(dmt_ctx *ctx, int32_t layout, uint8_t *acc);
 int32_t dmt_get_guiding_term(dmt_ctx *ctx, int32_t side, int32_t store, int32_t k, double *H, double *F, double *c);
 int32_t dmt_upload_guiding_term(dmt_ctx *ctx, int32_t side, int32_t store, int32_t k, const double *H, const double *F, const double *c);
 
+/* ---- test hooks: the device's counter-based random streams for given counters ------------------------------- */
+/* out[n_chains][n_tiles][4*dw]: the N(0,1) draws the pCN refresh (K3) uses for chains chain0.., tiles tile0.., iteration iter.
+ * Replaces nothing in the reference (its Wnr/randn draws are not reproducible elsewhere); lets tests pin the generator. */
+int32_t dmt_debug_normals(dmt_ctx *ctx, uint32_t chain0, uint32_t tile0, uint32_t iter, int32_t n_chains, int32_t n_tiles, double *out);
+/* out[n_chains][n_blocks]: the Exp(1) draws of accept_reject_proposal_path! (src/biblock.jl:122) */
+int32_t dmt_debug_exponentials(dmt_ctx *ctx, uint32_t chain0, uint32_t iter, uint32_t layout, int32_t n_chains, int32_t n_blocks, double *out);
+
 /* ---- multi-GPU: the small allreduce of ll sums / accept counts ----------------------------- */
 /* NCCL is dlopen'ed at first use.  unique_id: the 128-byte ncclUniqueId from dmt_nccl_unique_id on rank 0. */
 int32_t dmt_nccl_unique_id(uint8_t *id128);
