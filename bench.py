@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--cpu-chains", type=int, default=None, help="chains in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--separate", action="store_true", help="blocking sweep with the three separate passes instead of the fused one")
     return ap.parse_args()
 
 
@@ -185,8 +186,12 @@ def gpu_arm(a):
         ctx.comm_init(world, rank, uid.cpu().numpy())
     stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
 
-    names = (["set_obs", "bwd_filter", "invsolve_ll"] if blocking else []) + ["draw", "accept", "stats"]
-    launches_per_step = (3 if blocking else 0) + 1 + 1 + 2
+    fused = blocking and not a.separate  # find_W_for_X! + loglikhd! + draw_proposal_path! in one pass (dmt_find_W_loglikhd_draw)
+    if fused:
+        names = ["set_obs", "bwd_filter", "sweep_fused", "accept", "stats"]
+    else:
+        names = (["set_obs", "bwd_filter", "invsolve_ll"] if blocking else []) + ["draw", "accept", "stats"]
+    launches_per_step = len(names) + 1  # stats = reduce + finish kernels
     ev = {n: [] for n in names}
 
     def sweep(it, timed):
@@ -200,8 +205,12 @@ def gpu_arm(a):
         if blocking:
             ctx.set_artificial_obs(l); mark()
             ctx.recompute_guiding_term(l, _lib.P_ONLY); mark()
-            ctx.find_W_and_loglikhd(l); mark()
-        ctx.draw_proposal_path(l, it); mark()
+            if fused:
+                ctx.find_W_loglikhd_draw(l, it); mark()
+            else:
+                ctx.find_W_and_loglikhd(l); mark()
+        if not fused:
+            ctx.draw_proposal_path(l, it); mark()
         ctx.accept_reject_path(l, it); mark()
         stats = ctx.allreduce_stats(l); mark()        # [sum ll, sum ll°, accept counts...] (NCCL allreduce when N > 1)
         if timed:
@@ -246,16 +255,24 @@ def gpu_arm(a):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     bsh, bper = ALGO_BYTES[a.config]
     bpu = bper if prob.P == prob.M else bsh
+    kname, kop = "draw", "OP_DRAW"
+    if fused:
+        # the fused pass reads X_acc and H,F and writes W_acc, W°, X°; the accepted noise never leaves registers, so it moves
+        # 8(2d + 2dw) + 8(d(d+1)/2 + d) = 168 B per step for Lorenz — LESS than SURVEY §8(d)'s draw (144) + K5/K4 (48) figures
+        bpu = 8 * (2 * prob.d + 2 * prob.dw) + (8 * (prob.d * (prob.d + 1) // 2 + prob.d) if prob.P == prob.M else 0)
+        kname, kop = "sweep_fused", "OP_SWEEP"
     algo_bytes = bpu * prob.M * prob.steps_per_chain
-    achieved = algo_bytes / (kern_ms["draw"] * 1e-3) / 1e9
-    roofline = {"kernel": "fwd_kernel<%s, OP_DRAW>" % _lib.MODEL_NAMES[prob.model], "bound": "hbm", "achieved": achieved, "peak": peak,
+    achieved = algo_bytes / (kern_ms[kname] * 1e-3) / 1e9
+    roofline = {"kernel": "fwd_kernel<%s, %s>" % (_lib.MODEL_NAMES[prob.model], kop), "bound": "hbm", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-                "algorithmic_bytes_per_unit": bpu, "units_per_launch": prob.M * prob.steps_per_chain, "launch_ms": kern_ms["draw"]}
+                "algorithmic_bytes_per_unit": bpu, "units_per_launch": prob.M * prob.steps_per_chain, "launch_ms": kern_ms[kname]}
     if blocking:  # the whole sweep also moves the K1 write and the K5+K4 pass (reported separately)
         d, dw = prob.d, prob.dw
         nh = d * (d + 1) // 2
-        sweep_bytes = (bpu + 8 * (nh + d) + 8 * (d + dw) + 8 * (nh + d)) * prob.M * prob.steps_per_chain
+        # K1 writes H,F; then either the fused pass (bpu above) or the K5+K4 pass (X, H,F in; W out) followed by the draw
+        per_step = 8 * (nh + d) + (bpu if fused else (8 * (d + dw) + 8 * (nh + d)) + bpu)
+        sweep_bytes = per_step * prob.M * prob.steps_per_chain
         roofline["sweep"] = {"algorithmic_bytes_per_unit": sweep_bytes // (prob.M * prob.steps_per_chain),
                              "achieved": sweep_bytes / (ms_total / a.steps * 1e-3) / 1e9, "frac": sweep_bytes / (ms_total / a.steps * 1e-3) / 1e9 / peak}
 

@@ -64,6 +64,7 @@ SIGNATURES = {
     "dmt_loglikhd": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32]),
     "dmt_find_W_and_loglikhd": (C.c_int32, [_vp, C.c_int32]),
     "dmt_draw_proposal_path": (C.c_int32, [_vp, C.c_int32, C.c_uint32, _dp]),
+    "dmt_find_W_loglikhd_draw": (C.c_int32, [_vp, C.c_int32, C.c_uint32, _dp]),
     "dmt_recompute_path": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "dmt_set_proposal_law": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32]),
     "dmt_accept_reject_path": (C.c_int32, [_vp, C.c_int32, C.c_uint32, _dp]),
@@ -291,6 +292,13 @@ class Ctx:
             Z = _f64(Z, (self.S, self.dw, self.M))
             zp = _p(Z)
         self._ck(self.lib.dmt_draw_proposal_path(self.h, layout, it, zp))
+
+    def find_W_loglikhd_draw(self, layout, it, Z=None):
+        zp = None
+        if Z is not None:
+            Z = _f64(Z, (self.S, self.dw, self.M))
+            zp = _p(Z)
+        self._ck(self.lib.dmt_find_W_loglikhd_draw(self.h, layout, it, zp))
 
     def recompute_path(self, layout, law_side=PROPOSAL, noise_side=ACCEPTED, skip=0):
         self._ck(self.lib.dmt_recompute_path(self.h, layout, law_side, noise_side, skip))

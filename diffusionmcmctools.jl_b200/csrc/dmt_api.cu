@@ -676,6 +676,21 @@ int32_t dmt_draw_proposal_path(dmt_ctx *ctx, int32_t layout, uint32_t iter, cons
     });
 }
 
+int32_t dmt_find_W_loglikhd_draw(dmt_ctx *ctx, int32_t layout, uint32_t iter, const double *Z) {
+    return guarded(ctx, [&] {
+        Layout &L = layout_of(ctx, layout);
+        FwdArgs fa{iter, 0, 0, 0, nullptr};
+        if (Z) {
+            const size_t n = (size_t)ctx->S * ctx->DW * ctx->M;
+            double *tmp = ctx->scratch(n);
+            CK(cudaMemcpyAsync(tmp, Z, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            fa.Z = tmp;
+        }
+        launch_fwd<OP_SWEEP>(ctx, L, fa);
+        if (Z) CK(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
 int32_t dmt_recompute_path(dmt_ctx *ctx, int32_t layout, int32_t law_side, int32_t noise_side, int32_t skip) {
     return guarded(ctx, [&] {
         check_law_side(ctx, law_side); check_side(ctx, noise_side);

@@ -14,18 +14,26 @@ namespace dmt {
 
 template <int NG> struct GTile { // where the guiding term of interval k lives for this thread's pset / law side
     const double *base;          // tile 0, component 0, this pset
+    const double *c0;            // c at the interval start, this pset
     int store, slot;
 };
 template <int NG>
-__device__ __forceinline__ GTile<NG> g_tile_of(const DevCtx &cx, int k, int i1, bool last, int law_side, int ps) {
+__device__ __forceinline__ GTile<NG> g_tile_of(const DevCtx &cx, const LayoutDev &ly, int k, int i1, bool last, int law_side, int ps) {
     GTile<NG> t;
     t.store = (k == i1 && !last) ? 1 : 0; // P_last comes from PPb (src/block.jl:68)
     t.slot = law_side ^ cx.parP[t.store][(size_t)k * cx.P + ps];
     const int gt0 = t.store ? cx.ppb_tile0[k] : cx.tile0[k];
-    t.base = cx.G[t.slot][t.store] + ((size_t)gt0 * NG * cx.P + ps) * 4;
+    const bool priv = (law_side == 0) && (ly.Gl[t.store] != nullptr); // layout-private (cached) accepted-law guiding term
+    t.base = (priv ? ly.Gl[t.store] : cx.G[t.slot][t.store]) + ((size_t)gt0 * NG * cx.P + ps) * 4;
+    t.c0 = (priv ? ly.c0l[t.store] : cx.c0[t.slot][t.store]) + (size_t)k * cx.P + ps;
     return t;
 }
 
+#ifdef DMT_FWD_MAXREG
+#define DMT_FWD_BOUNDS __maxnreg__(DMT_FWD_MAXREG)
+#else
+#define DMT_FWD_BOUNDS __launch_bounds__(TPB, DMT_FWD_MINB)
+#endif
 // One thread = one (chain, block).  grid = (ceil(M/TPB), n_blocks).  Replaces, per OP:
 //   OP_DRAW        draw_proposal_path!(bb)            src/biblock.jl:80-106   (pCN + guided EM + ll, fused; K3+K2+K4)
 //   OP_RECOMPUTE   recompute_path!(b°, b.WW; skip)    src/block.jl:161-187    (K2+K4)
@@ -33,20 +41,20 @@ __device__ __forceinline__ GTile<NG> g_tile_of(const DevCtx &cx, int k, int i1, 
 //   OP_INVSOLVE    find_W_for_X!(b)                   src/block.jl:120-131    (K5)
 //   OP_INVSOLVE_LL both of the above in one pass over X
 //   OP_INIT        init_paths! / draw_proposal_path!(u::SamplingUnit)  src/sampling_unit.jl:83-87,118-120 (fresh noise, in place)
-#ifdef DMT_FWD_MAXREG
-#define DMT_FWD_BOUNDS __maxnreg__(DMT_FWD_MAXREG)
-#else
-#define DMT_FWD_BOUNDS __launch_bounds__(TPB, DMT_FWD_MINB)
-#endif
+//   OP_SWEEP       find_W_for_X!(b); loglikhd!(b); draw_proposal_path!(bb) of the blocking sweep
+//                  (docs/src/tutorials/block_collection/inference_with_blocking.md:55-57) in ONE pass over the tiles: the
+//                  accepted noise recovered by K5 feeds the pCN refresh in registers (168 instead of 264 B per step).
 template <class MD, int OP, int TPB>
 __global__ void DMT_FWD_BOUNDS fwd_kernel(const DevCtx cx, const LayoutDev ly, const FwdArgs fa) {
     constexpr int D = MD::D, DW = MD::DW, NPAR = MD::NPAR, NH = D * (D + 1) / 2, NG = NH + D, NAUX = D * D + D + NH;
-    constexpr bool READS_X = (OP == OP_LOGLIK || OP == OP_INVSOLVE || OP == OP_INVSOLVE_LL);
+    constexpr bool SWEEP = (OP == OP_SWEEP);
+    constexpr bool READS_X = (OP == OP_LOGLIK || OP == OP_INVSOLVE || OP == OP_INVSOLVE_LL || SWEEP);
     constexpr bool WRITES_X = (OP == OP_DRAW || OP == OP_RECOMPUTE || OP == OP_INIT);
     constexpr bool READS_W = (OP == OP_DRAW || OP == OP_RECOMPUTE);
-    constexpr bool WRITES_W = (OP == OP_DRAW || OP == OP_INIT || OP == OP_INVSOLVE || OP == OP_INVSOLVE_LL);
+    constexpr bool WRITES_W = (OP == OP_DRAW || OP == OP_INIT || OP == OP_INVSOLVE || OP == OP_INVSOLVE_LL || SWEEP);
+    constexpr bool INV = (OP == OP_INVSOLVE || OP == OP_INVSOLVE_LL || SWEEP);
     constexpr bool WANT_LL = (OP != OP_INVSOLVE);
-    constexpr bool RNG = (OP == OP_DRAW || OP == OP_INIT);
+    constexpr bool RNG = (OP == OP_DRAW || OP == OP_INIT || SWEEP);
 
     const int c = blockIdx.x * TPB + threadIdx.x;
     const int b = blockIdx.y;
@@ -59,26 +67,30 @@ __global__ void DMT_FWD_BOUNDS fwd_kernel(const DevCtx cx, const LayoutDev ly, c
 
     const int law_side = (OP == OP_RECOMPUTE || OP == OP_LOGLIK) ? fa.law_side : 0;
     const int xin_side = law_side;
-    const int xout_side = (OP == OP_DRAW) ? 1 : law_side;
+    const int xout_side = (OP == OP_DRAW || SWEEP) ? 1 : law_side;
     const int win_side = (OP == OP_RECOMPUTE) ? fa.w_side : 0;
-    const int wout_side = (OP == OP_DRAW) ? 1 : 0;
+    const int wout_side = (OP == OP_DRAW) ? 1 : 0; // SWEEP writes both: accepted in place, proposal to the other buffer
     const int ll_side = (OP == OP_DRAW) ? 1 : law_side;
-    const double rho = (OP == OP_DRAW) ? ly.rho[b] : 0.0;
-    const double crho = (OP == OP_DRAW) ? sqrt(1.0 - rho * rho) : 1.0;
+    const double rho = (OP == OP_DRAW || SWEEP) ? ly.rho[b] : 0.0;
+    const double crho = (OP == OP_DRAW || SWEEP) ? sqrt(1.0 - rho * rho) : 1.0;
     const int skip = fa.skip;
     const size_t gstr = P * 4; // doubles between components of one tile
 
-    double x[D];
+    double x[D], xo[SWEEP ? D : 1]; // x: the path that is read or written; xo (SWEEP): the proposal path
     {   // y1 = XX[1].x[1] of the block  (src/biblock.jl:96, src/block.jl:177)
         const int sl = xin_side ^ cx.parX[(size_t)i0 * M + c];
 #pragma unroll
         for (int i = 0; i < D; i++) x[i] = cx.X0[sl * cx.X0buf + ((size_t)i0 * D + i) * M + c];
+        if (SWEEP) {
+#pragma unroll
+            for (int i = 0; i < D; i++) xo[i] = x[i];
+        }
     }
-    double ll = 0.0;
+    double ll = 0.0, llo = 0.0;
     bool ok = true;
 
-    for (int k = i0; k <= i1 && ok; ++k) {
-        const GTile<NG> gt = g_tile_of<NG>(cx, k, i1, last, law_side, ps);
+    for (int k = i0; k <= i1 && (ok || SWEEP); ++k) {
+        const GTile<NG> gt = g_tile_of<NG>(cx, ly, k, i1, last, law_side, ps);
         const int store = gt.store, slotL = gt.slot;
         const double *Gp = gt.base;
         double th[NPAR];
@@ -105,21 +117,23 @@ __global__ void DMT_FWD_BOUNDS fwd_kernel(const DevCtx cx, const LayoutDev ly, c
         const uint8_t pw = cx.parW[(size_t)k * M + c], px = cx.parX[(size_t)k * M + c];
         const double *Win = cx.W + (size_t)(win_side ^ pw) * cx.Wbuf + ((size_t)t0 * DW * M + c) * 4;
         double *Wout = cx.W + (size_t)(wout_side ^ pw) * cx.Wbuf + ((size_t)t0 * DW * M + c) * 4;
+        double *Wprop = cx.W + (size_t)(1 ^ pw) * cx.Wbuf + ((size_t)t0 * DW * M + c) * 4; // SWEEP only
         const double *Xin = cx.X + (size_t)(xin_side ^ px) * cx.Xbuf + ((size_t)t0 * D * M + c) * 4;
         double *Xout = cx.X + (size_t)(xout_side ^ px) * cx.Xbuf + ((size_t)t0 * D * M + c) * 4;
         if (READS_X && k > i0) { // an existing path: interval k starts at ITS OWN XX[k].x[1]
 #pragma unroll
             for (int i = 0; i < D; i++) x[i] = cx.X0[(size_t)(xin_side ^ px) * cx.X0buf + ((size_t)k * D + i) * M + c];
         }
-        if (WRITES_X) { // XX°[k].x[1] = y1
+        if (WRITES_X || SWEEP) { // XX°[k].x[1] = y1
             double *x0p = cx.X0 + (size_t)(xout_side ^ px) * cx.X0buf + (size_t)k * D * M + c;
 #pragma unroll
-            for (int i = 0; i < D; i++) x0p[(size_t)i * M] = x[i];
+            for (int i = 0; i < D; i++) x0p[(size_t)i * M] = SWEEP ? xo[i] : x[i];
         }
 
         const int ntl = (nst + 3) >> 2;
         for (int q = 0; q < ntl; ++q) {
             double g[NG][4], w[DW][4], xt[D][4], dt4[4], sq4[4];
+            double wo[SWEEP ? DW : 1][4], xot[SWEEP ? D : 1][4], z[RNG ? 4 * DW : 1];
             // ---- every sector of the tile, once, straight into registers
             if (READS_W) {
 #pragma unroll
@@ -134,8 +148,7 @@ __global__ void DMT_FWD_BOUNDS fwd_kernel(const DevCtx cx, const LayoutDev ly, c
             ld256u(cx.dt + (size_t)(t0 + q) * 4, dt4);
             if (RNG) ld256u(cx.sqdt + (size_t)(t0 + q) * 4, sq4);
 
-            if (RNG) { // K3: dW° = rho dW + sqrt(1-rho^2) sqrt(dt) xi   (A.2) — needs only W: runs while H,F are in flight
-                double z[4 * DW];
+            if (RNG) { // xi ~ N(0, I): independent of everything loaded above, runs while the sectors are in flight
                 if (fa.Z) {
 #pragma unroll
                     for (int s = 0; s < 4; s++)
@@ -152,19 +165,21 @@ __global__ void DMT_FWD_BOUNDS fwd_kernel(const DevCtx cx, const LayoutDev ly, c
                     tile_normals<DW>(cx.seed, cx.chain_offset + (uint32_t)c, (uint32_t)(t0 + q), fa.iter, z);
 #endif
                 }
+                if (!SWEEP) { // K3: dW° = rho dW + sqrt(1-rho^2) sqrt(dt) xi   (A.2)
 #pragma unroll
-                for (int s = 0; s < 4; s++)
+                    for (int s = 0; s < 4; s++)
 #pragma unroll
-                    for (int j = 0; j < DW; j++) {
-                        if (OP == OP_DRAW) w[j][s] = rho * w[j][s] + crho * sq4[s] * z[s * DW + j];
-                        else w[j][s] = sq4[s] * z[s * DW + j];
-                    }
+                        for (int j = 0; j < DW; j++) {
+                            if (OP == OP_DRAW) w[j][s] = rho * w[j][s] + crho * sq4[s] * z[s * DW + j];
+                            else w[j][s] = sq4[s] * z[s * DW + j];
+                        }
 #pragma unroll
-                for (int j = 0; j < DW; j++) st256(Wout + ((size_t)q * DW + j) * M * 4, w[j]); // final: stream out now
+                    for (int j = 0; j < DW; j++) st256(Wout + ((size_t)q * DW + j) * M * 4, w[j]); // final: stream out now
+                }
             }
 
             if (WANT_LL && k == i0 && q == 0) { // loglikhd_obs(PP[1], y1) = -c - y'Hy/2 + F'y  (src/block.jl:178)
-                double s0 = -cx.c0[slotL][store][(size_t)k * P + ps];
+                double s0 = -*gt.c0;
 #pragma unroll
                 for (int i = 0; i < D; i++) {
                     double hx = 0.0;
@@ -173,11 +188,12 @@ __global__ void DMT_FWD_BOUNDS fwd_kernel(const DevCtx cx, const LayoutDev ly, c
                     s0 += x[i] * (g[NH + i][0] - 0.5 * hx);
                 }
                 ll = s0;
+                llo = s0; // same law, same start point
             }
 #pragma unroll
             for (int s = 0; s < 4; s++) {
                 const int i = 4 * q + s;
-                if (i < nst && ok) {
+                if (i < nst && (ok || SWEEP)) {
                     double Hs[NH], F[D], gd[D], G = 0.0;
 #pragma unroll
                     for (int a = 0; a < NH; a++) Hs[a] = g[a][s];
@@ -208,7 +224,7 @@ __global__ void DMT_FWD_BOUNDS fwd_kernel(const DevCtx cx, const LayoutDev ly, c
                     } else {
 #pragma unroll
                         for (int a = 0; a < D; a++) xn[a] = xt[a][s];
-                        if (OP == OP_INVSOLVE || OP == OP_INVSOLVE_LL) { // K5: dW = sigma^+ (x' - x - (b + a r) dt)   (A.5)
+                        if (INV) { // K5: dW = sigma^+ (x' - x - (b + a r) dt)   (A.5)
                             double res[D], dwv[DW];
 #pragma unroll
                             for (int a = 0; a < D; a++) res[a] = xn[a] - x[a] - gd[a] * dt4[s];
@@ -219,6 +235,29 @@ __global__ void DMT_FWD_BOUNDS fwd_kernel(const DevCtx cx, const LayoutDev ly, c
                     }
 #pragma unroll
                     for (int a = 0; a < D; a++) x[a] = xn[a];
+                    if (SWEEP) { // the proposal: pCN from the noise just recovered, then the guided step from xo
+                        double dwo[DW], swo[D], gdo[D], Go = 0.0;
+#pragma unroll
+                        for (int j = 0; j < DW; j++) { dwo[j] = rho * w[j][s] + crho * sq4[s] * z[s * DW + j]; wo[j][s] = dwo[j]; }
+                        if (ok) {
+                            const typename MD::Diff dfo(par, xo);
+                            guided_terms<MD, true>(par, dfo, Bm, beta, at, Hs, F, xo, gdo, Go);
+                            llo = fma(Go, dt4[s], llo);
+                            dfo.sig_mul(dwo, swo);
+                            double xon[D];
+#pragma unroll
+                            for (int a = 0; a < D; a++) xon[a] = fma(gdo[a], dt4[s], xo[a]) + swo[a];
+                            bool fin = dfo.ok();
+#pragma unroll
+                            for (int a = 0; a < D; a++) fin = fin && isfinite(xon[a]);
+                            if (!(fin && MD::bound_ok(par, xon))) { ok = false; llo = -INFINITY; }
+#pragma unroll
+                            for (int a = 0; a < D; a++) { xot[a][s] = xon[a]; xo[a] = xon[a]; }
+                        } else {
+#pragma unroll
+                            for (int a = 0; a < D; a++) xot[a][s] = 0.0;
+                        }
+                    }
                 } else {
                     if (WRITES_X) {
 #pragma unroll
@@ -228,21 +267,34 @@ __global__ void DMT_FWD_BOUNDS fwd_kernel(const DevCtx cx, const LayoutDev ly, c
 #pragma unroll
                         for (int j = 0; j < DW; j++) w[j][s] = 0.0;
                     }
+                    if (SWEEP) {
+#pragma unroll
+                        for (int j = 0; j < DW; j++) { w[j][s] = 0.0; wo[j][s] = 0.0; }
+#pragma unroll
+                        for (int a = 0; a < D; a++) xot[a][s] = 0.0;
+                    }
                 }
             }
-            if (WRITES_W && !RNG) {
+            if (WRITES_W && (!RNG || SWEEP)) {
 #pragma unroll
                 for (int j = 0; j < DW; j++) st256(Wout + ((size_t)q * DW + j) * M * 4, w[j]);
+            }
+            if (SWEEP) {
+#pragma unroll
+                for (int j = 0; j < DW; j++) st256(Wprop + ((size_t)q * DW + j) * M * 4, wo[j]);
+#pragma unroll
+                for (int i = 0; i < D; i++) st256(Xout + ((size_t)q * D + i) * M * 4, xot[i]);
             }
             if (WRITES_X) {
 #pragma unroll
                 for (int i = 0; i < D; i++) st256(Xout + ((size_t)q * D + i) * M * 4, xt[i]);
             }
-            if (!ok) break;
+            if (!ok && !SWEEP) break;
         }
     }
     if (WANT_LL) ly.ll[((size_t)ll_side * ly.nb + b) * M + c] = ll;
-    if (WRITES_X) ly.ok[(size_t)b * M + c] = ok ? 1 : 0;
+    if (SWEEP) ly.ll[((size_t)ly.nb + b) * M + c] = llo;
+    if (WRITES_X || SWEEP) ly.ok[(size_t)b * M + c] = ok ? 1 : 0;
 }
 
 template <class MD, int TPB> constexpr size_t fwd_smem_bytes() { return 0; }

@@ -33,8 +33,14 @@ namespace dmt {
 #ifndef DMT_EVICT_FIRST
 #define DMT_EVICT_FIRST 0 // 1: streamed sectors are marked L2::evict_first
 #endif
+#ifndef DMT_BWD_MINB
+#define DMT_BWD_MINB 1
+#endif
+#ifndef DMT_BWD_TPB
+#define DMT_BWD_TPB 32
+#endif
 constexpr int FWD_TPB = DMT_FWD_TPB;
-constexpr int BWD_TPB = 32;
+constexpr int BWD_TPB = DMT_BWD_TPB;
 
 struct DevCtx {
     int M, P, K, NT, NTb, m, two_sided;
@@ -71,9 +77,12 @@ struct LayoutDev {
     uint8_t *acc_hist; // [hist_len][nb][M] or null
     double *ll_hist;   // [hist_len][2][nb][M] or null
     int hist_len;
+    // layout-private guiding term of the ACCEPTED laws (dmt_enable_guiding_cache): null => the shared store cx.G / cx.c0
+    double *Gl[2];     // [store] tiles like cx.G[slot][store]
+    double *c0l[2];    // [store] [K][P]
 };
 
-enum { OP_DRAW = 0, OP_RECOMPUTE = 1, OP_LOGLIK = 2, OP_INVSOLVE = 3, OP_INVSOLVE_LL = 4, OP_INIT = 5 };
+enum { OP_DRAW = 0, OP_RECOMPUTE = 1, OP_LOGLIK = 2, OP_INVSOLVE = 3, OP_INVSOLVE_LL = 4, OP_INIT = 5, OP_SWEEP = 6 };
 
 struct FwdArgs {
     uint32_t iter;
@@ -568,7 +577,7 @@ __device__ __forceinline__ void obs_jump(int m, const double *op, size_t P, doub
 // its exact artificial observation, Sigma = eps I) is integrated in covariance form (P = H^-1, nu = P F), which is a
 // linear non-stiff ODE, and converted to (H,F) per grid point; c has a closed form there.
 template <class MD>
-__global__ void __launch_bounds__(BWD_TPB) bwd_kernel(const DevCtx cx, const LayoutDev ly, const int side_mask) {
+__global__ void __launch_bounds__(BWD_TPB, DMT_BWD_MINB) bwd_kernel(const DevCtx cx, const LayoutDev ly, const int side_mask) {
     constexpr int D = MD::D, NH = D * (D + 1) / 2, NG = NH + D, NAUX = D * D + D + NH;
     const int ps = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y, side = blockIdx.z;

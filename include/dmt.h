@@ -127,6 +127,10 @@ int32_t dmt_find_W_and_loglikhd(dmt_ctx *ctx, int32_t layout);
  * Z == NULL: N(0,1) from Philox4x32-10, counter (chain, tile, iter, stream).  Z != NULL: host normals [S][dw][M]
  * (the parity hook: "feed the reference's own Wiener increments into both implementations"). */
 int32_t dmt_draw_proposal_path(dmt_ctx *ctx, int32_t layout, uint32_t iter, const double *Z);
+/* find_W_for_X!(be); loglikhd!(be); draw_proposal_path!(be) — the three consecutive calls of the blocking sweep
+ * (docs/src/tutorials/block_collection/inference_with_blocking.md:55-57) — in ONE pass over the path: the accepted noise
+ * recovered by K5 feeds the pCN refresh in registers.  Same results as the three calls up to FP64 rounding. (K5+K4+K3+K2+K4) */
+int32_t dmt_find_W_loglikhd_draw(dmt_ctx *ctx, int32_t layout, uint32_t iter, const double *Z);
 /* recompute_path!(b°, b.WW; skip) as used by set_proposal_law! (src/biblock.jl:343 -> src/block.jl:161-187):
  * law and X of `law_side`, noise of `noise_side`; sets ll[law_side].                                    (K2+K4) */
 int32_t dmt_recompute_path(dmt_ctx *ctx, int32_t layout, int32_t law_side, int32_t noise_side, int32_t skip);

@@ -193,6 +193,37 @@ def test_blocking_sweeps(orc, olib, name):
     ctx.close()
 
 
+@pytest.mark.parametrize("name", ["fhn", "lorenz", "prok", "lv"])
+def test_fused_sweep_pass_matches_the_three_separate_calls(name):
+    """dmt_find_W_loglikhd_draw == find_W_for_X!; loglikhd!; draw_proposal_path! (one pass instead of three)"""
+    K = 8
+    layouts = [([(0, 2), (3, 5), (6, 7)], [0.6, 0.7, 0.8]), ([(0, K - 1)], 0.0)]
+    prob = small_problem(name, M=41, K=K, layouts=layouts, seed=12, nsteps=11)
+    ctxs = [make_ctx(prob, seed=31) for _ in range(2)]
+    for ctx in ctxs:
+        ctx.recompute_guiding_term(1, _lib.P_ONLY)
+        assert ctx.init_paths(1, iter0=500, max_tries=50) == 0
+        ctx.set_artificial_obs(0)
+        ctx.recompute_guiding_term(0, _lib.P_ONLY)
+    a, b = ctxs
+    a.find_W_for_X(0); a.loglikhd(0, 0, 0); a.draw_proposal_path(0, 3)
+    b.find_W_loglikhd_draw(0, 3)
+    assert np.array_equal(a.get_success(0), b.get_success(0))
+    good = a.get_success(0)
+    sc = np.abs(a.get_W(0)).max()
+    assert np.abs(a.get_W(0) - b.get_W(0)).max() < 1e-12 * sc
+    assert rel_err(b.get_ll(0, 0), a.get_ll(0, 0)) < 1e-12 and rel_err(b.get_ll(0, 1), a.get_ll(0, 1)) < 1e-11
+    # proposals of the blocks that succeeded agree (interval ranges of failed blocks hold unspecified data)
+    step0 = np.concatenate([[0], np.cumsum(prob.n_pts - 1)]); pt0 = np.concatenate([[0], np.cumsum(prob.n_pts)])
+    Wa, Wb, Xa, Xb = a.get_W(1), b.get_W(1), a.get_X(1), b.get_X(1)
+    for bi, (i0, i1) in enumerate(layouts[0][0]):
+        g = good[bi]
+        assert np.abs(Wa[step0[i0]:step0[i1 + 1]][:, :, g] - Wb[step0[i0]:step0[i1 + 1]][:, :, g]).max() < 1e-11 * sc
+        assert rel_err(Xb[pt0[i0]:pt0[i1 + 1]][:, :, g], Xa[pt0[i0]:pt0[i1 + 1]][:, :, g]) < 1e-11
+    for ctx in ctxs:
+        ctx.close()
+
+
 def test_rho_one_reproduces_accepted_path_bit_exactly():
     prob = small_problem("lorenz", M=64, K=3)
     prob.layouts = [([(0, 2)], 1.0)]
