@@ -187,11 +187,15 @@ def gpu_arm(a):
     stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
 
     fused = blocking and not a.separate  # find_W_for_X! + loglikhd! + draw_proposal_path! in one pass (dmt_find_W_loglikhd_draw)
+    k1_each_step = (a.config == "c5")    # BASELINE C5: "each sweep = set_params -> K1 (P = M) -> K2" (backward-filter dominated)
+    theta_dev_host = np.repeat(prob.theta[:, None], prob.P, axis=1).copy()
     if fused:
         names = ["set_obs", "bwd_filter", "sweep_fused", "accept", "stats"]
+    elif k1_each_step:
+        names = ["set_params_aux", "bwd_filter", "draw", "accept", "stats"]
     else:
         names = (["set_obs", "bwd_filter", "invsolve_ll"] if blocking else []) + ["draw", "accept", "stats"]
-    launches_per_step = len(names) + 1  # stats = reduce + finish kernels
+    launches_per_step = len(names) + 1 + (1 if k1_each_step else 0)  # stats = reduce + finish kernels; c5: put_record + aux_linearise
     ev = {n: [] for n in names}
 
     def sweep(it, timed):
@@ -209,6 +213,10 @@ def gpu_arm(a):
                 ctx.find_W_loglikhd_draw(l, it); mark()
             else:
                 ctx.find_W_and_loglikhd(l); mark()
+        if k1_each_step:  # new parameters (theta jitter keeps the data valid), aux laws re-linearised on the device, K1, then the path update
+            ctx.set_params(theta_dev_host, side=0, stores=1)
+            ctx.set_aux_linearised(prob.xbar, side=0, store=_lib.STORE_PP); mark()
+            ctx.recompute_guiding_term(l, _lib.P_ONLY); mark()
         if not fused:
             ctx.draw_proposal_path(l, it); mark()
         ctx.accept_reject_path(l, it); mark()
@@ -245,6 +253,9 @@ def gpu_arm(a):
     units_per_step = prob.M * prob.steps_per_chain * world
     value = units_per_step * a.steps / (ms_total * 1e-3)
     kern_ms = {n: float(np.mean([e0.elapsed_time(e1) for e0, e1 in ev[n]])) for n in names}
+    its = list(range(a.warmup, a.warmup + a.steps))
+    kern_ms_by_layout = {n: [float(np.mean([e0.elapsed_time(e1) for (e0, e1), it in zip(ev[n], its) if it % nlay == l] or [0.0]))
+                             for l in range(nlay)] for n in names if n in ("bwd_filter", "sweep_fused", "draw", "invsolve_ll")}
 
     # ---- roofline of the dominant kernel of the unit of work: fwd_kernel<Lorenz, OP_DRAW> (pCN + guided EM + ll)
     peaks = {}
@@ -311,7 +322,7 @@ def gpu_arm(a):
                    "l2": "inputs (paths %.1f GB + guiding term %.1f GB per GPU) are far larger than the 126 MB L2"
                          % (2 * 8 * ctx.S * (prob.d + prob.dw) * prob.M / 1e9, 8 * ctx.S * (prob.d * (prob.d + 1) // 2 + prob.d) * prob.P / 1e9),
                    "step": "one blocking sweep over one layout" if blocking else "draw + accept"},
-        "roofline": roofline, "kernel_ms": kern_ms, "gpu_launches": launches_per_step * a.steps, "clocks": clocks,
+        "roofline": roofline, "kernel_ms": kern_ms, "kernel_ms_by_layout": kern_ms_by_layout, "gpu_launches": launches_per_step * a.steps, "clocks": clocks,
         "last_stats": {"sum_ll": float(last[0]), "sum_ll_prop": float(last[1]), "accept_frac": float(np.sum(last[2:]) / (len(last[2:]) * prob.M * world))},
     }
     if e2e:

@@ -99,7 +99,12 @@ __device__ __forceinline__ void ld256(const double *p, double *v) { // streaming
 #endif
 }
 __device__ __forceinline__ void ld256u(const double *p, double *v) { // chain-uniform data (dt, sqrt dt): keep in L1
+#if defined(DMT_DT_SCALAR)
+    const double2 a = __ldg(reinterpret_cast<const double2 *>(p)), b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+#else
     asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+#endif
 }
 __device__ __forceinline__ void st256(double *p, const double *v) {
 #if DMT_EVICT_FIRST

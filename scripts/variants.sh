@@ -16,7 +16,8 @@ t = sys.argv[1]
 try:
     j = json.loads(open("gpurun_out/var_%s.log" % t).read().strip().splitlines()[-1])
     print("%-26s ms/step %7.3f  value %.3e  draw_frac %.3f  " % (t, j["ms_per_step"], j["value"], j["roofline"]["frac"]) +
-          " ".join("%s=%.3f" % (k, v) for k, v in j["kernel_ms"].items()))
+          " ".join("%s=%.3f" % (k, v) for k, v in j["kernel_ms"].items()) + "  | by layout: " +
+          " ".join("%s=%s" % (k, "/".join("%.2f" % x for x in v)) for k, v in j.get("kernel_ms_by_layout", {}).items()))
 except Exception as e:
     print(t, "FAILED", e); print(open("gpurun_out/var_%s.log" % t).read()[-800:])
 EOF
