@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--cpu-chains", type=int, default=None, help="chains in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cache", action="store_true", help="blocking sweep with the full backward filter every sweep (no guiding cache)")
     ap.add_argument("--separate", action="store_true", help="blocking sweep with the three separate passes instead of the fused one")
     return ap.parse_args()
 
@@ -180,6 +181,9 @@ def gpu_arm(a):
     if not blocking:
         ctx.recompute_guiding_term(0, _lib.P_ONLY)
         ctx.loglikhd(0, 0, 0)
+    elif not a.no_cache:  # smoothing: the laws stay fixed, only the blocks' frozen end points move => K1 through the guiding cache
+        for l in range(nlay):
+            ctx.enable_guiding_cache(l)
     if world > 1:  # native NCCL communicator inside libdmt for the small stats allreduce
         uid = torch.from_numpy(ctx.nccl_unique_id() if rank == 0 else np.zeros(128, np.uint8)).to(dev)
         dist.broadcast(uid, 0)
@@ -282,7 +286,8 @@ def gpu_arm(a):
         d, dw = prob.d, prob.dw
         nh = d * (d + 1) // 2
         # K1 writes H,F; then either the fused pass (bpu above) or the K5+K4 pass (X, H,F in; W out) followed by the draw
-        per_step = 8 * (nh + d) + (bpu if fused else (8 * (d + dw) + 8 * (nh + d)) + bpu)
+        k1_bytes = 8 * (nh + d) if a.no_cache else 8 * (d + d * d) + 8 * d  # full K1 writes H,F; cached K1 reads F0,Psi and writes F
+        per_step = k1_bytes + (bpu if fused else (8 * (d + dw) + 8 * (nh + d)) + bpu)
         sweep_bytes = per_step * prob.M * prob.steps_per_chain
         roofline["sweep"] = {"algorithmic_bytes_per_unit": sweep_bytes // (prob.M * prob.steps_per_chain),
                              "achieved": sweep_bytes / (ms_total / a.steps * 1e-3) / 1e9, "frac": sweep_bytes / (ms_total / a.steps * 1e-3) / 1e9 / peak}

@@ -80,6 +80,8 @@ SIGNATURES = {
     "dmt_get_last_accept": (C.c_int32, [_vp, C.c_int32, _bp]),
     "dmt_get_guiding_term": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _dp]),
     "dmt_upload_guiding_term": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _dp]),
+    "dmt_enable_guiding_cache": (C.c_int32, [_vp, C.c_int32, C.c_int32]),
+    "dmt_get_layout_guiding_term": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _dp]),
     "dmt_debug_normals": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, _dp]),
     "dmt_debug_exponentials": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, _dp]),
     "dmt_nccl_unique_id": (C.c_int32, [_bp]),
@@ -374,6 +376,16 @@ class Ctx:
         n, d = int(self.n_pts[k]), self.d
         H = _f64(H, (n, d, d, self.P)); F = _f64(F, (n, d, self.P)); c = _f64(c, (n, self.P))
         self._ck(self.lib.dmt_upload_guiding_term(self.h, side, store, k, _p(H), _p(F), _p(c)))
+
+    # -- guiding cache
+    def enable_guiding_cache(self, layout, enable=True):
+        self._ck(self.lib.dmt_enable_guiding_cache(self.h, layout, int(bool(enable))))
+
+    def get_layout_guiding_term(self, layout, k, store=STORE_PP):
+        n, d = int(self.n_pts[k]), self.d
+        H = np.empty((n, d, d, self.P)); F = np.empty((n, d, self.P)); c = np.empty((n, self.P))
+        self._ck(self.lib.dmt_get_layout_guiding_term(self.h, layout, store, k, _p(H), _p(F), _p(c)))
+        return H, F, c
 
     # -- test hooks
     def debug_normals(self, chain0, tile0, it, n_chains, n_tiles):

@@ -87,6 +87,10 @@ struct Layout {
     DevBuf<uint8_t> d_last, d_ok, d_last_acc, d_acc_hist;
     DevBuf<double> d_rho, d_ll, d_ll_hist;
     LayoutDev dev{};
+    // guiding cache (dmt_enable_guiding_cache): layout-private accepted-law guiding term + its affine decomposition in v
+    bool cache_enabled = false, cache_valid = false;
+    DevBuf<double> d_Gl[2], d_c0l[2], d_FP[2], d_cq;
+    DevBuf<int> d_blk_of_k;
 };
 
 // ---- NCCL, resolved at run time so that libdmt.so has no link-time dependency on it
@@ -135,7 +139,7 @@ struct dmt_ctx {
     std::vector<Layout> layouts;
     std::string err;
     // device storage
-    DevBuf<int> d_tile0, d_step0, d_pt0, d_nsteps, d_ppb_tile0, d_pset;
+    DevBuf<int> d_tile0, d_step0, d_pt0, d_nsteps, d_ppb_tile0, d_pset, d_k_of_tile, d_k_of_ppbtile;
     DevBuf<double> d_dt, d_sqdt, d_X, d_W, d_X0;
     DevBuf<uint8_t> d_parX, d_parW, d_parP[2];
     DevBuf<double> d_G[2][2], d_c0[2][2], d_theta[2][2], d_aux[2][2], d_obs[2], d_vart[2];
@@ -193,16 +197,102 @@ template <int OP> void launch_fwd(dmt_ctx *c, Layout &L, const FwdArgs &fa) {
     CK(cudaGetLastError());
 }
 
-void launch_bwd(dmt_ctx *c, Layout &L, int side_mask) {
+void launch_bwd(dmt_ctx *c, Layout &L, int side_mask, const double *v_override = nullptr) {
     dim3 grid = pset_grid(c, L.nb, BWD_TPB, c->cfg.two_sided_laws ? 2 : 1);
+    BwdArgs ba{};
+    ba.side_mask = side_mask;
+    if (v_override) {
+        ba.use_override = 1;
+        for (int i = 0; i < c->D; i++) ba.v[i] = v_override[i];
+    }
 #define DMT_CASE(MID)                                                                                              \
-    case MID: bwd_kernel<Model<MID>><<<grid, BWD_TPB, 0, c->stream>>>(c->dev, L.dev, side_mask); break;
+    case MID: bwd_kernel<Model<MID>><<<grid, BWD_TPB, 0, c->stream>>>(c->dev, L.dev, ba); break;
     switch (c->cfg.model) {
         DMT_FOR_MODELS(DMT_CASE)
         default: throw DmtError(DMT_ERR_UNSUPPORTED, "model not compiled into this build of libdmt");
     }
 #undef DMT_CASE
     CK(cudaGetLastError());
+}
+
+// ---- guiding cache (see kernels.cuh "guiding cache"): build by probing bwd_kernel, apply per sweep
+#define DMT_D_SWITCH(Dval, ...)                                                                                    \
+    switch (Dval) {                                                                                                \
+    case 2: { constexpr int DD = 2; __VA_ARGS__; } break;                                                          \
+    case 3: { constexpr int DD = 3; __VA_ARGS__; } break;                                                          \
+    case 4: { constexpr int DD = 4; __VA_ARGS__; } break;                                                          \
+    case 6: { constexpr int DD = 6; __VA_ARGS__; } break;                                                          \
+    default: throw DmtError(DMT_ERR_UNSUPPORTED, "state dimension not supported by the guiding cache");          \
+    }
+
+void cache_set_private(Layout &L, bool on) {
+    for (int st = 0; st < 2; st++) {
+        L.dev.Gl[st] = on ? L.d_Gl[st].p : nullptr;
+        L.dev.c0l[st] = on ? L.d_c0l[st].p : nullptr;
+    }
+}
+void invalidate_caches(dmt_ctx *c) {
+    for (auto &L : c->layouts) {
+        L.cache_valid = false;
+        cache_set_private(L, false);
+    }
+}
+void cache_apply(dmt_ctx *c, Layout &L) { // the per-sweep K1: F = F0 + Psi v ; c = c0 + q.v + v'Qv/2
+    const dim3 g0((c->P + 127) / 128, c->NT), g1((c->P + 127) / 128, std::max(c->NTb, 1));
+    DMT_D_SWITCH(c->D,
+                 cache_apply_kernel<DD><<<g0, 128, 0, c->stream>>>(c->dev, L.dev, 0, c->d_k_of_tile.p);
+                 if (c->NTb > 0) cache_apply_kernel<DD><<<g1, 128, 0, c->stream>>>(c->dev, L.dev, 1, c->d_k_of_ppbtile.p);
+                 cache_apply_c_kernel<DD><<<pset_grid(c, L.nb, 128), 128, 0, c->stream>>>(c->dev, L.dev));
+    CK(cudaGetLastError());
+}
+void cache_build(dmt_ctx *c, Layout &L) {
+    const size_t P = c->P, NF = c->D + c->D * c->D, NC = 1 + c->D + c->NH;
+    const size_t nt[2] = {(size_t)c->NT, (size_t)std::max(c->NTb, 1)};
+    for (int st = 0; st < 2; st++) {
+        if (L.d_Gl[st].n != nt[st] * c->NG * P * 4) L.d_Gl[st].alloc(nt[st] * c->NG * P * 4);
+        if (L.d_FP[st].n != nt[st] * NF * P * 4) L.d_FP[st].alloc(nt[st] * NF * P * 4);
+        if (L.d_c0l[st].n != (size_t)c->K * P) L.d_c0l[st].alloc((size_t)c->K * P);
+        L.dev.FP[st] = L.d_FP[st].p;
+    }
+    if (L.d_cq.n != (size_t)L.nb * NC * P) L.d_cq.alloc((size_t)L.nb * NC * P);
+    L.dev.cq = L.d_cq.p;
+    {
+        std::vector<int> bk(c->K, 0);
+        for (int b = 0; b < L.nb; b++)
+            for (int k = L.i0[b]; k <= L.i1[b]; k++) bk[k] = b;
+        if (L.d_blk_of_k.n != (size_t)c->K) L.d_blk_of_k.alloc(c->K);
+        CK(cudaMemcpyAsync(L.d_blk_of_k.p, bk.data(), sizeof(int) * c->K, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        L.dev.blk_of_k = L.d_blk_of_k.p;
+    }
+    cache_set_private(L, true);
+    const int D = c->D, nruns = 1 + 2 * D + D * (D - 1) / 2;
+    const double s = 8.0; // probe scale (a power of two: exact scaling)
+    DevBuf<double> Crun;
+    Crun.alloc((size_t)nruns * L.nb * P);
+    const dim3 g0((c->P + 127) / 128, c->NT), g1((c->P + 127) / 128, std::max(c->NTb, 1));
+    std::vector<std::vector<double>> probes;
+    probes.push_back(std::vector<double>(6, 0.0));
+    for (int sign = 1; sign >= -1; sign -= 2)
+        for (int m = 0; m < D; m++) { std::vector<double> v(6, 0.0); v[m] = sign * s; probes.push_back(v); }
+    for (int m = 0; m < D; m++)
+        for (int n = m + 1; n < D; n++) { std::vector<double> v(6, 0.0); v[m] = s; v[n] = s; probes.push_back(v); }
+    for (int r = 0; r < nruns; r++) {
+        launch_bwd(c, L, DMT_P_ONLY, probes[r].data());
+        cache_collect_c_kernel<<<pset_grid(c, L.nb, 128), 128, 0, c->stream>>>(c->dev, L.dev, r, Crun.p);
+        if (r <= D) {
+            const int mode = r == 0 ? 0 : 1, m = r - 1;
+            DMT_D_SWITCH(c->D,
+                         cache_extract_kernel<DD><<<g0, 128, 0, c->stream>>>(c->dev, L.dev, 0, c->d_k_of_tile.p, mode, m, 1.0 / s);
+                         if (c->NTb > 0) cache_extract_kernel<DD><<<g1, 128, 0, c->stream>>>(c->dev, L.dev, 1, c->d_k_of_ppbtile.p, mode, m, 1.0 / s));
+        }
+        CK(cudaGetLastError());
+    }
+    DMT_D_SWITCH(c->D, cache_solve_cq_kernel<DD><<<pset_grid(c, L.nb, 128), 128, 0, c->stream>>>(c->dev, L.dev, Crun.p, s));
+    CK(cudaGetLastError());
+    cache_apply(c, L); // the actual artificial observations
+    CK(cudaStreamSynchronize(c->stream));
+    L.cache_valid = true;
 }
 
 // dst record arrays [K][NREC][P] (per slot, resolved by the law parity of `store`): write ncomp components at offset
@@ -260,6 +350,15 @@ void rebuild_ppb_store(dmt_ctx *c) {
         c->dev.G[s][1] = c->d_G[s][1].p;
     }
     c->dev.NTb = nt;
+    {   // tile -> interval map of the PPb store (guiding cache kernels); a changed PPb store invalidates every cache
+        std::vector<int> kt(std::max(nt, 1), 0);
+        for (int k = 0; k < c->K; k++)
+            if (t0[k] >= 0)
+                for (int q = 0; q < (c->nsteps[k] + 3) / 4; q++) kt[t0[k] + q] = k;
+        c->d_k_of_ppbtile.alloc(kt.size());
+        CK(cudaMemcpy(c->d_k_of_ppbtile.p, kt.data(), sizeof(int) * kt.size(), cudaMemcpyHostToDevice));
+        invalidate_caches(c);
+    }
 }
 
 void fill_stats(dmt_ctx *c, Layout &L, double *host_out /* [2+3nb] */) {
@@ -399,6 +498,14 @@ int32_t dmt_create(const dmt_config *cfg, const int32_t *n_pts, const double *tt
         d.M = c->M; d.P = c->P; d.K = K; d.NT = c->NT; d.NTb = 0; d.m = c->m; d.two_sided = cfg->two_sided_laws ? 1 : 0;
         d.tile0 = c->d_tile0.p; d.step0 = c->d_step0.p; d.pt0 = c->d_pt0.p; d.nsteps = c->d_nsteps.p; d.ppb_tile0 = c->d_ppb_tile0.p;
         d.dt = c->d_dt.p; d.sqdt = c->d_sqdt.p; d.pset = c->d_pset.p;
+        {
+            std::vector<int> kt(c->NT, 0);
+            for (int k = 0; k < K; k++)
+                for (int t = c->tile0[k]; t < c->tile0[k + 1]; t++) kt[t] = k;
+            c->d_k_of_tile.alloc(c->NT);
+            CK(cudaMemcpy(c->d_k_of_tile.p, kt.data(), sizeof(int) * c->NT, cudaMemcpyHostToDevice));
+            d.k_of_tile = c->d_k_of_tile.p;
+        }
         d.X = c->d_X.p; d.W = c->d_W.p; d.X0 = c->d_X0.p; d.Xbuf = xb; d.Wbuf = wb; d.X0buf = x0b;
         d.parX = c->d_parX.p; d.parW = c->d_parW.p;
         for (int st = 0; st < 2; st++) d.parP[st] = c->d_parP[st].p;
@@ -446,6 +553,7 @@ int32_t dmt_get_stream(dmt_ctx *ctx, void **s) {
 int32_t dmt_set_params(dmt_ctx *ctx, int32_t side, int32_t store_mask, int32_t k0, int32_t k1, const double *theta) {
     return guarded(ctx, [&] {
         check_law_side(ctx, side); check_range(ctx, k0, k1);
+        if (side == 0) invalidate_caches(ctx); // the accepted laws change: cached guiding terms are stale
         REQUIRE(theta && (store_mask & 3), DMT_ERR_ARG, "null theta or empty store mask");
         for (int st = 0; st < 2; st++)
             if ((store_mask >> st) & 1)
@@ -456,6 +564,7 @@ int32_t dmt_set_params(dmt_ctx *ctx, int32_t side, int32_t store_mask, int32_t k
 int32_t dmt_set_aux(dmt_ctx *ctx, int32_t side, int32_t store, int32_t k0, int32_t k1, const double *B, const double *beta, const double *atil) {
     return guarded(ctx, [&] {
         check_law_side(ctx, side); check_range(ctx, k0, k1);
+        if (side == 0) invalidate_caches(ctx); // the accepted laws change: cached guiding terms are stale
         REQUIRE(store == 0 || store == 1, DMT_ERR_ARG, "store must be 0 (PP) or 1 (PPb)");
         REQUIRE(B && beta && atil, DMT_ERR_ARG, "null aux array");
         const int D = ctx->D, NH = ctx->NH, nk = k1 - k0 + 1;
@@ -479,6 +588,7 @@ int32_t dmt_set_aux(dmt_ctx *ctx, int32_t side, int32_t store, int32_t k0, int32
 int32_t dmt_set_aux_linearised(dmt_ctx *ctx, int32_t side, int32_t store, int32_t k0, int32_t k1, const double *xbar) {
     return guarded(ctx, [&] {
         check_law_side(ctx, side); check_range(ctx, k0, k1);
+        if (side == 0) invalidate_caches(ctx); // the accepted laws change: cached guiding terms are stale
         REQUIRE(store == 0 || store == 1, DMT_ERR_ARG, "store must be 0 (PP) or 1 (PPb)");
         REQUIRE(xbar, DMT_ERR_ARG, "null xbar");
         const size_t n = (size_t)(k1 - k0 + 1) * ctx->D * ctx->P;
@@ -500,6 +610,7 @@ int32_t dmt_set_aux_linearised(dmt_ctx *ctx, int32_t side, int32_t store, int32_
 int32_t dmt_set_obs(dmt_ctx *ctx, int32_t side, int32_t k0, int32_t k1, const double *L, const double *Sigma, const double *v) {
     return guarded(ctx, [&] {
         check_law_side(ctx, side); check_range(ctx, k0, k1);
+        if (side == 0) invalidate_caches(ctx); // the accepted laws change: cached guiding terms are stale
         REQUIRE(L && Sigma && v, DMT_ERR_ARG, "null observation array");
         const int m = ctx->m, D = ctx->D;
         double *r0 = ctx->d_obs[0].p, *r1 = ctx->d_obs[1].p;
@@ -561,6 +672,8 @@ int32_t dmt_set_blocks(dmt_ctx *ctx, int32_t layout, int32_t n_blocks, const int
         L.dev.ll = L.d_ll.p; L.dev.ok = L.d_ok.p; L.dev.last_acc = L.d_last_acc.p;
         L.dev.acc_hist = hl ? L.d_acc_hist.p : nullptr; L.dev.ll_hist = hl ? L.d_ll_hist.p : nullptr; L.dev.hist_len = (int)hl;
         L.set = true;
+        L.cache_enabled = false; L.cache_valid = false;
+        cache_set_private(L, false);
         rebuild_ppb_store(ctx);
     });
 }
@@ -643,7 +756,13 @@ int32_t dmt_recompute_guiding_term(dmt_ctx *ctx, int32_t layout, int32_t which) 
         Layout &L = layout_of(ctx, layout);
         REQUIRE(which >= 1 && which <= 3, DMT_ERR_ARG, "which must be DMT_P_ONLY, DMT_PO_ONLY or DMT_P_BOTH");
         if (which & 2) check_law_side(ctx, 1);
-        launch_bwd(ctx, L, which);
+        if (L.cache_enabled && (which & 1)) { // accepted laws through the guiding cache: build once, then F = F0 + Psi v
+            if (!L.cache_valid) cache_build(ctx, L);
+            else cache_apply(ctx, L);
+            if (which & 2) launch_bwd(ctx, L, DMT_PO_ONLY);
+        } else {
+            launch_bwd(ctx, L, which);
+        }
     });
 }
 
@@ -739,6 +858,7 @@ int32_t dmt_swap(dmt_ctx *ctx, int32_t layout, int32_t what, const uint8_t *chai
             swap_paths_kernel<<<chain_grid(ctx, L.nb, 128), 128, 0, ctx->stream>>>(ctx->dev, L.dev, what, dm);
         if (what & DMT_SWAP_PP) {
             check_law_side(ctx, 1);
+            invalidate_caches(ctx); // the accepted laws are now the former proposals (their guiding term is in the shared store)
             swap_laws_kernel<<<pset_grid(ctx, L.nb, 128), 128, 0, ctx->stream>>>(ctx->dev, L.dev, dm);
         }
         CK(cudaGetLastError());
@@ -837,8 +957,9 @@ int32_t dmt_accept_counts(dmt_ctx *ctx, int32_t layout, uint32_t it0, uint32_t i
 }
 
 // ---------------------------------------------------------------------------------------------------------------- guiding term
-static void xfer_guiding(dmt_ctx *ctx, int side, int store, int k, double *H, double *F, double *c, bool upload) {
+static void xfer_guiding(dmt_ctx *ctx, int side, int store, int k, double *H, double *F, double *c, bool upload, Layout *priv = nullptr) {
     check_law_side(ctx, side); check_range(ctx, k, k);
+    if (upload && side == 0) invalidate_caches(ctx);
     REQUIRE(store == 0 || store == 1, DMT_ERR_ARG, "store must be 0 (PP) or 1 (PPb)");
     REQUIRE(store == 0 || ctx->ppb_tile0[k] >= 0, DMT_ERR_STATE, "interval has no blocking law in any registered layout");
     REQUIRE(H && F && c, DMT_ERR_ARG, "null");
@@ -850,7 +971,9 @@ static void xfer_guiding(dmt_ctx *ctx, int side, int store, int k, double *H, do
         CK(cudaMemcpyAsync(dF.p, F, dF.n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(dc.p, c, dc.n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     }
-    xfer_guiding_kernel<<<pset_grid(ctx, 1, 128), 128, 0, ctx->stream>>>(ctx->dev, side, store, k, ctx->D, dH.p, dF.p, dc.p, upload ? 1 : 0);
+    double *Gpriv = (priv && priv->cache_valid && side == 0) ? priv->d_Gl[store].p : nullptr;
+    double *cpriv = Gpriv ? priv->d_c0l[store].p : nullptr;
+    xfer_guiding_kernel<<<pset_grid(ctx, 1, 128), 128, 0, ctx->stream>>>(ctx->dev, side, store, k, ctx->D, dH.p, dF.p, dc.p, upload ? 1 : 0, Gpriv, cpriv);
     CK(cudaGetLastError());
     if (!upload) {
         CK(cudaMemcpyAsync(H, dH.p, dH.n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -864,6 +987,21 @@ int32_t dmt_get_guiding_term(dmt_ctx *ctx, int32_t side, int32_t store, int32_t 
 }
 int32_t dmt_upload_guiding_term(dmt_ctx *ctx, int32_t side, int32_t store, int32_t k, const double *H, const double *F, const double *c) {
     return guarded(ctx, [&] { xfer_guiding(ctx, side, store, k, (double *)H, (double *)F, (double *)c, true); });
+}
+int32_t dmt_get_layout_guiding_term(dmt_ctx *ctx, int32_t layout, int32_t store, int32_t k, double *H, double *F, double *c) {
+    return guarded(ctx, [&] { xfer_guiding(ctx, 0, store, k, H, F, c, false, &layout_of(ctx, layout)); });
+}
+int32_t dmt_enable_guiding_cache(dmt_ctx *ctx, int32_t layout, int32_t enable) {
+    return guarded(ctx, [&] {
+        Layout &L = layout_of(ctx, layout);
+        L.cache_enabled = enable != 0;
+        L.cache_valid = false;
+        cache_set_private(L, false);
+        if (!enable) {
+            for (int st = 0; st < 2; st++) { L.d_Gl[st].release(); L.d_FP[st].release(); L.d_c0l[st].release(); }
+            L.d_cq.release();
+        }
+    });
 }
 
 // ---------------------------------------------------------------------------------------------------------------- test hooks

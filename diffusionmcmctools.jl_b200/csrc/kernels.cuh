@@ -51,6 +51,7 @@ struct DevCtx {
     const int *ppb_tile0; // [K] first tile in the PPb store, -1 if interval k never ends a non-terminal block
     const double *dt, *sqdt; // [NT*4] (padded like the tiles)
     const int *pset;      // [M]
+    const int *k_of_tile; // [NT] interval that owns tile t of the PP store
     double *X, *W, *X0;
     size_t Xbuf, Wbuf, X0buf; // buffer strides in doubles
     uint8_t *parX, *parW;     // [K][M]
@@ -80,6 +81,16 @@ struct LayoutDev {
     // layout-private guiding term of the ACCEPTED laws (dmt_enable_guiding_cache): null => the shared store cx.G / cx.c0
     double *Gl[2];     // [store] tiles like cx.G[slot][store]
     double *c0l[2];    // [store] [K][P]
+    // guiding cache: (F, c) of a block are exactly affine / quadratic in the block's artificial end-point observation v
+    double *FP[2];     // [store] [tiles][D + D*D][P][4]: F0 (v = 0) then Psi[i][m] = dF_i/dv_m
+    double *cq;        // [nb][1 + D + NH][P]: c = c0 + q.v + v'Qv/2 at the block start
+    const int *blk_of_k; // [K] block of this layout that contains interval k
+};
+
+struct BwdArgs {
+    int side_mask;
+    int use_override; // 1: every non-terminal block uses v[] as its artificial observation (cache build probes)
+    double v[6];
 };
 
 enum { OP_DRAW = 0, OP_RECOMPUTE = 1, OP_LOGLIK = 2, OP_INVSOLVE = 3, OP_INVSOLVE_LL = 4, OP_INIT = 5, OP_SWEEP = 6 };
@@ -582,7 +593,8 @@ __device__ __forceinline__ void obs_jump(int m, const double *op, size_t P, doub
 // its exact artificial observation, Sigma = eps I) is integrated in covariance form (P = H^-1, nu = P F), which is a
 // linear non-stiff ODE, and converted to (H,F) per grid point; c has a closed form there.
 template <class MD>
-__global__ void __launch_bounds__(BWD_TPB, DMT_BWD_MINB) bwd_kernel(const DevCtx cx, const LayoutDev ly, const int side_mask) {
+__global__ void __launch_bounds__(BWD_TPB, DMT_BWD_MINB) bwd_kernel(const DevCtx cx, const LayoutDev ly, const BwdArgs ba) {
+    const int side_mask = ba.side_mask;
     constexpr int D = MD::D, NH = D * (D + 1) / 2, NG = NH + D, NAUX = D * D + D + NH;
     const int ps = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y, side = blockIdx.z;
@@ -611,7 +623,8 @@ __global__ void __launch_bounds__(BWD_TPB, DMT_BWD_MINB) bwd_kernel(const DevCtx
         }
         const int nst = cx.nsteps[k], t0 = cx.tile0[k];
         const int gt0 = store ? cx.ppb_tile0[k] : t0;
-        double *Gp = cx.G[slot][store] + ((size_t)gt0 * NG * P + ps) * 4;
+        const bool priv = (side == 0) && (ly.Gl[store] != nullptr); // layout-private accepted-law store (guiding cache)
+        double *Gp = (priv ? ly.Gl[store] : cx.G[slot][store]) + ((size_t)gt0 * NG * P + ps) * 4;
         const size_t gstr = P * 4;
         const double *dtp = cx.dt + (size_t)t0 * 4;
 
@@ -683,7 +696,7 @@ __global__ void __launch_bounds__(BWD_TPB, DMT_BWD_MINB) bwd_kernel(const DevCtx
 #pragma unroll
                 for (int j = i; j < D; j++) Pm[sidx<D>(i, j)] = (i == j) ? cx.eps : 0.0;
 #pragma unroll
-            for (int i = 0; i < D; i++) nu[i] = cx.vart[slot][((size_t)k * D + i) * P + ps];
+            for (int i = 0; i < D; i++) nu[i] = ba.use_override ? ba.v[i] : cx.vart[slot][((size_t)k * D + i) * P + ps];
 #pragma unroll
             for (int i = 0; i < D; i++) trB += Bm[i * D + i];
         } else {
@@ -728,8 +741,133 @@ __global__ void __launch_bounds__(BWD_TPB, DMT_BWD_MINB) bwd_kernel(const DevCtx
             for (int i = 0; i < D; i++) nF = fma(nu[i], F[i], nF);
             cc = 0.5 * D * 1.8378770664093453 + 0.5 * logdet + trB * Tt + 0.5 * nF;
         }
-        cx.c0[slot][store][(size_t)k * P + ps] = cc;
+        (priv ? ly.c0l[store] : cx.c0[slot][store])[(size_t)k * P + ps] = cc;
     }
+}
+
+// =========================================================================================== guiding cache (K1 fast path)
+// In a smoothing sweep with blocking only the frozen end point v of each non-terminal block changes between two calls of
+// recompute_guiding_term!(be, Val(:P_only)) (src/biblock.jl:275-278 then src/block.jl:104-110).  H does not depend on v, and the
+// RK4-discretised F and c are EXACTLY affine resp. quadratic in v (the F equation is linear given the H stages, the jump
+// and the covariance-form start are affine in v).  So per layout we keep F0 = F(v=0), Psi = dF/dv and (c0, q, Q) of
+// c = c0 + q.v + v'Qv/2 — obtained by probing the unchanged bwd_kernel with v = 0, +-s e_m, s(e_m+e_n) — and a sweep's K1
+// becomes the streaming update F = F0 + Psi v (120 B per step instead of ~320 FP64 instructions per step).
+__device__ __forceinline__ bool cache_tile_of(const DevCtx &cx, const LayoutDev &ly, int store, int k, int &b) {
+    b = ly.blk_of_k[k];
+    const bool is_plast = (k == ly.i1[b]) && !ly.last[b]; // this interval's law comes from PPb in this layout
+    return store ? is_plast : !is_plast;
+}
+// after a probe run: mode 0: F0 := F ; mode 1: Psi[:, m] := (F - F0) * inv_scale.   grid (ceil(P/128), tiles of `store`)
+template <int D>
+__global__ void cache_extract_kernel(const DevCtx cx, const LayoutDev ly, int store, const int *k_of_t, int mode, int m, double inv_scale) {
+    constexpr int NH = D * (D + 1) / 2, NG = NH + D, NF = D + D * D;
+    const int ps = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y;
+    if (ps >= cx.P) return;
+    int b;
+    if (!cache_tile_of(cx, ly, store, k_of_t[t], b)) return;
+    const size_t P = cx.P;
+    const double *gp = ly.Gl[store] + (((size_t)t * NG + NH) * P + ps) * 4;
+    double *fp = ly.FP[store] + ((size_t)t * NF * P + ps) * 4;
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+        double f[4], f0[4];
+        ld256(gp + (size_t)i * P * 4, f);
+        if (mode == 0) {
+            st256(fp + (size_t)i * P * 4, f);
+        } else {
+            ld256(fp + (size_t)i * P * 4, f0);
+#pragma unroll
+            for (int s = 0; s < 4; s++) f[s] = (f[s] - f0[s]) * inv_scale;
+            st256(fp + (size_t)(D + i * D + m) * P * 4, f);
+        }
+    }
+}
+// the per-sweep K1 of a cached layout: F = F0 + Psi v for every tile of every non-terminal block
+template <int D>
+__global__ void cache_apply_kernel(const DevCtx cx, const LayoutDev ly, int store, const int *k_of_t) {
+    constexpr int NH = D * (D + 1) / 2, NG = NH + D, NF = D + D * D;
+    const int ps = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y;
+    if (ps >= cx.P) return;
+    int b;
+    if (!cache_tile_of(cx, ly, store, k_of_t[t], b) || ly.last[b]) return; // terminal block: no artificial observation
+    const size_t P = cx.P;
+    const int kend = ly.i1[b];
+    const int sv = cx.parP[1][(size_t)kend * P + ps];
+    double v[D];
+#pragma unroll
+    for (int mm = 0; mm < D; mm++) v[mm] = cx.vart[sv][((size_t)kend * D + mm) * P + ps];
+    double *gp = ly.Gl[store] + (((size_t)t * NG + NH) * P + ps) * 4;
+    const double *fp = ly.FP[store] + ((size_t)t * NF * P + ps) * 4;
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+        double f[4], p[4];
+        ld256(fp + (size_t)i * P * 4, f);
+#pragma unroll
+        for (int mm = 0; mm < D; mm++) {
+            ld256(fp + (size_t)(D + i * D + mm) * P * 4, p);
+#pragma unroll
+            for (int s = 0; s < 4; s++) f[s] = fma(p[s], v[mm], f[s]);
+        }
+        st256(gp + (size_t)i * P * 4, f);
+    }
+}
+// c at the block start of probe run `run` -> Crun[run][nb][P]
+__global__ void cache_collect_c_kernel(const DevCtx cx, const LayoutDev ly, int run, double *Crun) {
+    const int ps = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (ps >= cx.P) return;
+    Crun[((size_t)run * ly.nb + b) * cx.P + ps] = ly.c0l[0][(size_t)ly.i0[b] * cx.P + ps];
+}
+// (c0, q, Q) from the probes: run 0: v = 0; 1..D: +s e_m; D+1..2D: -s e_m; then s(e_m + e_n), m < n
+template <int D>
+__global__ void cache_solve_cq_kernel(const DevCtx cx, const LayoutDev ly, const double *Crun, double s) {
+    constexpr int NH = D * (D + 1) / 2, NC = 1 + D + NH;
+    const int ps = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (ps >= cx.P) return;
+    const size_t P = cx.P, str = (size_t)ly.nb * P, o = (size_t)b * P + ps;
+    const double c0 = Crun[o];
+    double q[D], Q[NH];
+#pragma unroll
+    for (int m = 0; m < D; m++) {
+        const double cp = Crun[(size_t)(1 + m) * str + o], cm = Crun[(size_t)(1 + D + m) * str + o];
+        q[m] = (cp - cm) / (2.0 * s);
+        Q[sidx<D>(m, m)] = (cp + cm - 2.0 * c0) / (s * s);
+    }
+    int run = 1 + 2 * D;
+#pragma unroll
+    for (int m = 0; m < D; m++)
+#pragma unroll
+        for (int n = m + 1; n < D; n++) {
+            const double cpair = Crun[(size_t)run * str + o];
+            Q[sidx<D>(m, n)] = (cpair - c0 - s * (q[m] + q[n])) / (s * s) - 0.5 * (Q[sidx<D>(m, m)] + Q[sidx<D>(n, n)]);
+            run++;
+        }
+    double *cq = ly.cq + (size_t)b * NC * P + ps;
+    cq[0] = c0;
+#pragma unroll
+    for (int m = 0; m < D; m++) cq[(size_t)(1 + m) * P] = q[m];
+#pragma unroll
+    for (int a = 0; a < NH; a++) cq[(size_t)(1 + D + a) * P] = Q[a];
+}
+template <int D> __global__ void cache_apply_c_kernel(const DevCtx cx, const LayoutDev ly) {
+    constexpr int NH = D * (D + 1) / 2, NC = 1 + D + NH;
+    const int ps = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (ps >= cx.P || ly.last[b]) return;
+    const size_t P = cx.P;
+    const int kend = ly.i1[b];
+    const int sv = cx.parP[1][(size_t)kend * P + ps];
+    double v[D];
+#pragma unroll
+    for (int m = 0; m < D; m++) v[m] = cx.vart[sv][((size_t)kend * D + m) * P + ps];
+    const double *cq = ly.cq + (size_t)b * NC * P + ps;
+    double c = cq[0];
+#pragma unroll
+    for (int m = 0; m < D; m++) {
+        double Qv = 0.0;
+#pragma unroll
+        for (int n = 0; n < D; n++) Qv = fma(cq[(size_t)(1 + D + sidx<D>(m, n)) * P], v[n], Qv);
+        c += v[m] * (cq[(size_t)(1 + m) * P] + 0.5 * Qv);
+    }
+    ly.c0l[0][(size_t)ly.i0[b] * P + ps] = c;
 }
 
 // auxiliary law := Jacobian linearisation of the target at xbar (last paragraph)
@@ -898,7 +1036,8 @@ __global__ void copy_acc_to_prop_kernel(const DevCtx cx, int D, int DW) {
 }
 
 // guiding term natural [n_k][d*d][P], [n_k][d][P], [n_k][P] <-> packed tiles of interval k.  dir 0: get, 1: upload
-__global__ void xfer_guiding_kernel(const DevCtx cx, int side, int store, int k, int D, double *Hn, double *Fn, double *cn, int dir) {
+__global__ void xfer_guiding_kernel(const DevCtx cx, int side, int store, int k, int D, double *Hn, double *Fn, double *cn, int dir,
+                                    double *G_priv, double *c0_priv) { // *_priv: a layout-private store (guiding cache) or null
     const int ps = blockIdx.x * blockDim.x + threadIdx.x;
     if (ps >= cx.P) return;
     const size_t P = cx.P;
@@ -906,7 +1045,7 @@ __global__ void xfer_guiding_kernel(const DevCtx cx, int side, int store, int k,
     const int slot = side ^ cx.parP[store][(size_t)k * P + ps];
     const int nst = cx.nsteps[k];
     const int gt0 = store ? cx.ppb_tile0[k] : cx.tile0[k];
-    double *Gp = cx.G[slot][store] + ((size_t)gt0 * NG * P + ps) * 4;
+    double *Gp = (G_priv ? G_priv : cx.G[slot][store]) + ((size_t)gt0 * NG * P + ps) * 4;
     for (int j = 0; j < nst; j++) {
         double *gp = Gp + (size_t)(j >> 2) * NG * P * 4 + (j & 3);
         for (int a = 0; a < D; a++) {
@@ -920,7 +1059,7 @@ __global__ void xfer_guiding_kernel(const DevCtx cx, int side, int store, int k,
             if (dir) gp[(size_t)(NH + a) * P * 4] = *fn; else *fn = gp[(size_t)(NH + a) * P * 4];
         }
     }
-    double *c0 = &cx.c0[slot][store][(size_t)k * P + ps];
+    double *c0 = &(c0_priv ? c0_priv : cx.c0[slot][store])[(size_t)k * P + ps];
     if (dir) *c0 = cn[ps];
     else {
         cn[ps] = *c0;

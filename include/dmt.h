@@ -166,6 +166,19 @@ int32_t dmt_get_last_accept(dmt_ctx *ctx, int32_t layout, uint8_t *acc);
 int32_t dmt_get_guiding_term(dmt_ctx *ctx, int32_t side, int32_t store, int32_t k, double *H, double *F, double *c);
 int32_t dmt_upload_guiding_term(dmt_ctx *ctx, int32_t side, int32_t store, int32_t k, const double *H, const double *F, const double *c);
 
+/* ---- guiding cache: the fast path of recompute_guiding_term!(be, Val(:P_only)) in smoothing-with-blocking sweeps ----- */
+/* Between two sweeps of the tutorial loop (docs/src/tutorials/block_collection/inference_with_blocking.md:52-58) only the
+ * artificial end-point observation of each non-terminal block changes (GP.set_obs!, src/biblock.jl:275-278).  With the cache
+ * enabled for a layout, dmt_recompute_guiding_term keeps a layout-private copy of the accepted laws' guiding term together
+ * with its exact affine (F) / quadratic (c) dependence on that observation; the first call after any change of the accepted
+ * laws rebuilds it (1 + 2d + d(d-1)/2 backward-filter passes), every later call is a single streaming pass F = F0 + Psi v.
+ * Results equal the uncached ones up to FP64 rounding.  Worth it only when the laws stay fixed for many sweeps (smoothing);
+ * leave it off when parameters change every iteration.  Costs (d + d^2) extra doubles per grid point and pset per layout.
+ * While enabled, the layout's guiding term is private to the layout (read it with dmt_get_layout_guiding_term). */
+int32_t dmt_enable_guiding_cache(dmt_ctx *ctx, int32_t layout, int32_t enable);
+/* accepted-side guiding term as ops on `layout` see it (the layout-private store when the cache is valid, else the shared one) */
+int32_t dmt_get_layout_guiding_term(dmt_ctx *ctx, int32_t layout, int32_t store, int32_t k, double *H, double *F, double *c);
+
 /* ---- test hooks: the device's counter-based random streams for given counters ------------------------------- */
 /* out[n_chains][n_tiles][4*dw]: the N(0,1) draws the pCN refresh (K3) uses for chains chain0.., tiles tile0.., iteration iter.
  * Replaces nothing in the reference (its Wnr/randn draws are not reproducible elsewhere); lets tests pin the generator. */

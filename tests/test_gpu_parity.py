@@ -224,6 +224,52 @@ def test_fused_sweep_pass_matches_the_three_separate_calls(name):
         ctx.close()
 
 
+@pytest.mark.parametrize("name", ["lorenz", "fhn", "prok"])
+def test_guiding_cache_matches_uncached_sweeps(name):
+    """dmt_enable_guiding_cache: recompute_guiding_term!(P only) as F = F0 + Psi v / c = c0 + q.v + v'Qv/2 must reproduce
+    the full backward filter sweep after sweep, across both staggered layouts, and survive an invalidation."""
+    K = 8
+    layouts = [([(0, 2), (3, 5), (6, 7)], 0.7), ([(0, 3), (4, 7)], 0.6)]
+    prob = small_problem(name, M=37, K=K, layouts=layouts, seed=21, nsteps=10)
+    a, b = make_ctx(prob, seed=5, n_layouts=3), make_ctx(prob, seed=5, n_layouts=3)
+    for ctx in (a, b):
+        ctx.set_blocks(2, [(0, K - 1)], 0.0)
+        ctx.recompute_guiding_term(2, _lib.P_ONLY)
+        assert ctx.init_paths(2, iter0=77, max_tries=50) == 0
+    b.enable_guiding_cache(0); b.enable_guiding_cache(1)
+    n_acc = 0
+    for it in range(6):
+        l = it % 2
+        if it == 4:   # change the accepted laws: caches must rebuild
+            th = prob.theta * (1 + 1e-3)
+            for ctx in (a, b):
+                ctx.set_params(th, side=0, stores=3)
+                ctx.set_aux_linearised(prob.xbar, side=0, store=0); ctx.set_aux_linearised(prob.xbar, side=0, store=1)
+        for ctx in (a, b):
+            ctx.set_artificial_obs(l)
+            ctx.recompute_guiding_term(l, _lib.P_ONLY)
+        for (i0, i1) in layouts[l][0]:
+            for k in range(i0, i1 + 1):
+                store = 1 if (k == i1 and i1 != K - 1) else 0
+                Ha, Fa, ca = a.get_layout_guiding_term(l, k, store)
+                Hb, Fb, cb = b.get_layout_guiding_term(l, k, store)
+                n = Ha.shape[0]
+                assert rel_err(Hb[:n - 1], Ha[:n - 1]) < 1e-12 and rel_err(Fb[:n - 1], Fa[:n - 1]) < 1e-10
+                if k == i0:
+                    assert np.abs(cb[0] - ca[0]).max() < 1e-9 * max(1.0, np.abs(ca[0]).max())
+        for ctx in (a, b):
+            ctx.find_W_loglikhd_draw(l, it)
+        assert np.array_equal(a.get_success(l), b.get_success(l))
+        assert rel_err(b.get_ll(l, 0), a.get_ll(l, 0)) < 1e-9 and rel_err(b.get_ll(l, 1), a.get_ll(l, 1)) < 1e-9
+        for ctx in (a, b):
+            ctx.accept_reject_path(l, it)
+        assert np.array_equal(a.get_last_accept(l), b.get_last_accept(l))
+        n_acc += a.get_last_accept(l).sum()
+        assert rel_err(b.get_X(0), a.get_X(0)) < 1e-9
+    assert n_acc > 0
+    a.close(); b.close()
+
+
 def test_rho_one_reproduces_accepted_path_bit_exactly():
     prob = small_problem("lorenz", M=64, K=3)
     prob.layouts = [([(0, 2)], 1.0)]
