@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--cpu-chains", type=int, default=None, help="chains in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--one-call", action="store_true", help="blocking sweep through dmt_blocking_sweep (same launches; per-kernel timing is then not available)")
     ap.add_argument("--no-cache", action="store_true", help="blocking sweep with the full backward filter every sweep (no guiding cache)")
     ap.add_argument("--separate", action="store_true", help="blocking sweep with the three separate passes instead of the fused one")
     return ap.parse_args()
@@ -193,16 +194,20 @@ def gpu_arm(a):
     fused = blocking and not a.separate  # find_W_for_X! + loglikhd! + draw_proposal_path! in one pass (dmt_find_W_loglikhd_draw)
     k1_each_step = (a.config == "c5")    # BASELINE C5: "each sweep = set_params -> K1 (P = M) -> K2" (backward-filter dominated)
     theta_dev_host = np.repeat(prob.theta[:, None], prob.P, axis=1).copy()
-    if fused:
+    onecall = fused and a.one_call  # dmt_blocking_sweep: set_obs! .. draw_proposal_path! in one call (same launches, one timing bracket)
+    if onecall:
+        names = ["sweep_fused", "accept", "stats"]
+    elif fused:
         names = ["set_obs", "bwd_filter", "sweep_fused", "accept", "stats"]
     elif k1_each_step:
         names = ["set_params_aux", "bwd_filter", "draw", "accept", "stats"]
     else:
         names = (["set_obs", "bwd_filter", "invsolve_ll"] if blocking else []) + ["draw", "accept", "stats"]
-    launches_per_step = len(names) + 1 + (1 if k1_each_step else 0)  # stats = reduce + finish kernels; c5: put_record + aux_linearise
+    # stats = reduce + finish kernels; c5: put_record + aux_linearise; one-call sweep: set_obs gather + the fused pass
+    launches_per_step = len(names) + 1 + (1 if k1_each_step else 0) + (3 if onecall else 0)  # + set_obs, 2 apply + 1 apply_c
     ev = {n: [] for n in names}
 
-    def sweep(it, timed):
+    def sweep(it, timed, E=None):
         l = it % nlay
         marks = []
 
@@ -210,7 +215,9 @@ def gpu_arm(a):
             if timed:
                 e = torch.cuda.Event(enable_timing=True); e.record(stream); marks.append(e)
         mark()
-        if blocking:
+        if onecall:
+            ctx.blocking_sweep(l, it); mark()   # set_obs!, recompute_guiding_term!(P only), find_W_for_X!, loglikhd!, draw_proposal_path!
+        elif blocking:
             ctx.set_artificial_obs(l); mark()
             ctx.recompute_guiding_term(l, _lib.P_ONLY); mark()
             if fused:
@@ -223,7 +230,7 @@ def gpu_arm(a):
             ctx.recompute_guiding_term(l, _lib.P_ONLY); mark()
         if not fused:
             ctx.draw_proposal_path(l, it); mark()
-        ctx.accept_reject_path(l, it); mark()
+        ctx.accept_reject_path(l, it, E); mark()   # E: host-drawn Exp(1) (the reference's rand(Exponential(1.0)), src/biblock.jl:122) or device Philox
         stats = ctx.allreduce_stats(l); mark()        # [sum ll, sum ll°, accept counts...] (NCCL allreduce when N > 1)
         if timed:
             for n, e0, e1 in zip(names, marks[:-1], marks[1:]):
@@ -292,28 +299,32 @@ def gpu_arm(a):
         roofline["sweep"] = {"algorithmic_bytes_per_unit": sweep_bytes // (prob.M * prob.steps_per_chain),
                              "achieved": sweep_bytes / (ms_total / a.steps * 1e-3) / 1e9, "frac": sweep_bytes / (ms_total / a.steps * 1e-3) / 1e9 / peak}
 
-    # ---- end to end through the C ABI with host buffers: H2D theta upload, D2H per-chain ll + accept flags every step
+    # ---- end to end through the C ABI with HOST buffers: what crosses the boundary every step of the reference loop is the
+    # accept step's Exp(1) draws (host RNG, as in the reference: H2D from pinned memory) and the per-(block, chain) ll and
+    # accept flags that the user's loop reads back (D2H); paths stay on the device (the tutorials read them every 400th step)
     e2e = None
     if not a.no_e2e:
-        theta_host = np.repeat(prob.theta[:, None], prob.P, axis=1).copy()
-        nb_max = max(len(r) for r, _ in prob.layouts)
+        nb_l = [len(r) for r, _ in prob.layouts]
+        rng = np.random.default_rng(7)
+        E_pinned = [torch.empty((nb, prob.M), dtype=torch.float64, pin_memory=True) for nb in nb_l]
+        for t in E_pinned:
+            t.copy_(torch.from_numpy(rng.exponential(size=tuple(t.shape))))
+        E_np = [t.numpy() for t in E_pinned]
         barrier()
         t0 = time.perf_counter()
         n_e2e = max(3, a.steps // 2)
         for it in range(a.warmup + a.steps, a.warmup + a.steps + n_e2e):
             l = it % nlay
-            ctx.set_params(theta_host, side=0, stores=3)              # H2D (pageable host -> device, inside the call)
-            sweep(it, False)
+            sweep(it, False, E_np[l])                                 # H2D of E inside dmt_accept_reject_path
             ll_host = ctx.get_ll(l, 0)                                # D2H
             acc_host = ctx.get_last_accept(l)                         # D2H
         barrier()
         dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        nb_l = [len(r) for r, _ in prob.layouts]
         e2e = {"value": units_per_step * n_e2e / float(dt.item()), "unit": "guided EM steps/s",
-               "h2d_bytes_per_step": int(theta_host.nbytes * 2), "d2h_bytes_per_step": int(np.mean(nb_l) * prob.M * 9 + 8 * (2 + np.mean(nb_l))),
-               "steps": n_e2e, "note": "dmt_set_params + sweep + dmt_get_ll + dmt_get_last_accept, host numpy buffers, wall clock"}
+               "h2d_bytes_per_step": int(np.mean(nb_l) * prob.M * 8), "d2h_bytes_per_step": int(np.mean(nb_l) * prob.M * 9 + 8 * (2 + np.mean(nb_l))),
+               "steps": n_e2e, "note": "sweep with host-drawn E (pinned) + dmt_get_ll + dmt_get_last_accept + stats, wall clock, max over ranks"}
 
     out = {
         "metric": "guided path updates/sec (chains x EM steps/s, FP64)", "value": value, "unit": "guided EM steps/s",

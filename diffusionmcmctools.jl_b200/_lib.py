@@ -65,6 +65,7 @@ SIGNATURES = {
     "dmt_find_W_and_loglikhd": (C.c_int32, [_vp, C.c_int32]),
     "dmt_draw_proposal_path": (C.c_int32, [_vp, C.c_int32, C.c_uint32, _dp]),
     "dmt_find_W_loglikhd_draw": (C.c_int32, [_vp, C.c_int32, C.c_uint32, _dp]),
+    "dmt_blocking_sweep": (C.c_int32, [_vp, C.c_int32, C.c_uint32]),
     "dmt_recompute_path": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "dmt_set_proposal_law": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32]),
     "dmt_accept_reject_path": (C.c_int32, [_vp, C.c_int32, C.c_uint32, _dp]),
@@ -301,6 +302,9 @@ class Ctx:
             Z = _f64(Z, (self.S, self.dw, self.M))
             zp = _p(Z)
         self._ck(self.lib.dmt_find_W_loglikhd_draw(self.h, layout, it, zp))
+
+    def blocking_sweep(self, layout, it):
+        self._ck(self.lib.dmt_blocking_sweep(self.h, layout, it))
 
     def recompute_path(self, layout, law_side=PROPOSAL, noise_side=ACCEPTED, skip=0):
         self._ck(self.lib.dmt_recompute_path(self.h, layout, law_side, noise_side, skip))

@@ -98,7 +98,7 @@ def noise(model, th, x, dW):
 def clamp(model, th, x):
     """keep simulated synthetic truth inside the model's domain (LV, Prokaryote)"""
     if model == LV:
-        return np.maximum(x, 1e-3)
+        return np.maximum(x, 0.05)
     if model == PROK:
         x = np.maximum(x, [[0.5], [1.5], [0.5], [0.5]])
         x[3] = np.minimum(x[3], th[8] - 0.5)
@@ -190,6 +190,8 @@ def make_problem(name, M, P=None, K=None, obs_dt=None, dt=None, seed=0, layouts=
         else:
             eta = big.normal(size=(m, P))
         v[k] = L @ x + Lc @ eta
+        if model in (LV, PROK):  # noisy observations of a positive state: keep them inside the law's domain, otherwise the guided
+            v[k] = clamp(model, th, v[k]) if m == d else v[k]   # proposal is pulled across the boundary and never succeeds
         xbar[k] = x
     if model == FHN:  # the upstream FitzHughNagumoAux linearises at the observed v (x2 does not enter the Jacobian)
         xbar[:, 0, :] = v[:, 0, :]

@@ -89,6 +89,7 @@ struct Layout {
     LayoutDev dev{};
     // guiding cache (dmt_enable_guiding_cache): layout-private accepted-law guiding term + its affine decomposition in v
     bool cache_enabled = false, cache_valid = false;
+    bool F_stale = false; // cache valid but F/c of the private store not materialised for the current artificial observations
     DevBuf<double> d_Gl[2], d_c0l[2], d_FP[2], d_cq;
     DevBuf<int> d_blk_of_k;
 };
@@ -186,7 +187,10 @@ template <class MD, int OP> void launch_fwd_model(dmt_ctx *c, Layout &L, const F
     fwd_kernel<MD, OP, TPB><<<chain_grid(c, L.nb, TPB), TPB, smem, c->stream>>>(c->dev, L.dev, fa);
 }
 
+void ensure_guiding(dmt_ctx *c, Layout &L);
+
 template <int OP> void launch_fwd(dmt_ctx *c, Layout &L, const FwdArgs &fa) {
+    ensure_guiding(c, L);
 #define DMT_CASE(MID)                                                                                              \
     case MID: launch_fwd_model<Model<MID>, OP>(c, L, fa); break;
     switch (c->cfg.model) {
@@ -234,10 +238,12 @@ void cache_set_private(Layout &L, bool on) {
 void invalidate_caches(dmt_ctx *c) {
     for (auto &L : c->layouts) {
         L.cache_valid = false;
+        L.F_stale = false;
         cache_set_private(L, false);
     }
 }
 void cache_apply(dmt_ctx *c, Layout &L) { // the per-sweep K1: F = F0 + Psi v ; c = c0 + q.v + v'Qv/2
+    L.F_stale = false;
     const dim3 g0((c->P + 127) / 128, c->NT), g1((c->P + 127) / 128, std::max(c->NTb, 1));
     DMT_D_SWITCH(c->D,
                  cache_apply_kernel<DD><<<g0, 128, 0, c->stream>>>(c->dev, L.dev, 0, c->d_k_of_tile.p);
@@ -293,6 +299,10 @@ void cache_build(dmt_ctx *c, Layout &L) {
     cache_apply(c, L); // the actual artificial observations
     CK(cudaStreamSynchronize(c->stream));
     L.cache_valid = true;
+}
+// dmt_blocking_sweep forms F on the fly and leaves the private store's F for older end points: materialise it on demand
+void ensure_guiding(dmt_ctx *c, Layout &L) {
+    if (L.cache_enabled && L.cache_valid && L.F_stale) cache_apply(c, L);
 }
 
 // dst record arrays [K][NREC][P] (per slot, resolved by the law parity of `store`): write ncomp components at offset
@@ -810,6 +820,21 @@ int32_t dmt_find_W_loglikhd_draw(dmt_ctx *ctx, int32_t layout, uint32_t iter, co
     });
 }
 
+int32_t dmt_blocking_sweep(dmt_ctx *ctx, int32_t layout, uint32_t iter) {
+    return guarded(ctx, [&] {
+        Layout &L = layout_of(ctx, layout);
+        set_artificial_obs_kernel<<<chain_grid(ctx, L.nb, 128), 128, 0, ctx->stream>>>(ctx->dev, L.dev, ctx->D); // GP.set_obs!(be)
+        CK(cudaGetLastError());
+        if (L.cache_enabled) {                       // recompute_guiding_term!(be, Val(:P_only)) through the guiding cache
+            if (!L.cache_valid) cache_build(ctx, L);
+            else cache_apply(ctx, L);
+        } else {
+            launch_bwd(ctx, L, DMT_P_ONLY);
+        }
+        launch_fwd<OP_SWEEP>(ctx, L, FwdArgs{iter, 0, 0, 0, nullptr}); // find_W_for_X!; loglikhd!; draw_proposal_path!
+    });
+}
+
 int32_t dmt_recompute_path(dmt_ctx *ctx, int32_t layout, int32_t law_side, int32_t noise_side, int32_t skip) {
     return guarded(ctx, [&] {
         check_law_side(ctx, law_side); check_side(ctx, noise_side);
@@ -971,6 +996,7 @@ static void xfer_guiding(dmt_ctx *ctx, int side, int store, int k, double *H, do
         CK(cudaMemcpyAsync(dF.p, F, dF.n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(dc.p, c, dc.n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     }
+    if (priv) ensure_guiding(ctx, *priv);
     double *Gpriv = (priv && priv->cache_valid && side == 0) ? priv->d_Gl[store].p : nullptr;
     double *cpriv = Gpriv ? priv->d_c0l[store].p : nullptr;
     xfer_guiding_kernel<<<pset_grid(ctx, 1, 128), 128, 0, ctx->stream>>>(ctx->dev, side, store, k, ctx->D, dH.p, dF.p, dc.p, upload ? 1 : 0, Gpriv, cpriv);

@@ -15,7 +15,7 @@ namespace dmt {
 template <int NG> struct GTile { // where the guiding term of interval k lives for this thread's pset / law side
     const double *base;          // tile 0, component 0, this pset
     const double *c0;            // c at the interval start, this pset
-    int store, slot;
+    int store, slot, gt0;        // gt0: first tile of the interval in its store
 };
 template <int NG>
 __device__ __forceinline__ GTile<NG> g_tile_of(const DevCtx &cx, const LayoutDev &ly, int k, int i1, bool last, int law_side, int ps) {
@@ -23,16 +23,21 @@ __device__ __forceinline__ GTile<NG> g_tile_of(const DevCtx &cx, const LayoutDev
     t.store = (k == i1 && !last) ? 1 : 0; // P_last comes from PPb (src/block.jl:68)
     t.slot = law_side ^ cx.parP[t.store][(size_t)k * cx.P + ps];
     const int gt0 = t.store ? cx.ppb_tile0[k] : cx.tile0[k];
+    t.gt0 = gt0;
     const bool priv = (law_side == 0) && (ly.Gl[t.store] != nullptr); // layout-private (cached) accepted-law guiding term
     t.base = (priv ? ly.Gl[t.store] : cx.G[t.slot][t.store]) + ((size_t)gt0 * NG * cx.P + ps) * 4;
     t.c0 = (priv ? ly.c0l[t.store] : cx.c0[t.slot][t.store]) + (size_t)k * cx.P + ps;
     return t;
 }
 
+// Register budget (profiles/r01_tuning.md): with <= 45k (chain, block) threads per GPU the kernel is latency bound, and having
+// EVERY CTA resident in one wave matters more than avoiding spills: d <= 3 models are capped at 168 registers
+// (6 CTAs of 64 threads per SM), the wider ones keep the full budget.
+template <class MD> constexpr int fwd_minb() { return DMT_FWD_MINB > 0 ? DMT_FWD_MINB : (MD::D <= 3 ? 6 : 1); }
 #ifdef DMT_FWD_MAXREG
 #define DMT_FWD_BOUNDS __maxnreg__(DMT_FWD_MAXREG)
 #else
-#define DMT_FWD_BOUNDS __launch_bounds__(TPB, DMT_FWD_MINB)
+#define DMT_FWD_BOUNDS __launch_bounds__(TPB, fwd_minb<MD>())
 #endif
 // One thread = one (chain, block).  grid = (ceil(M/TPB), n_blocks).  Replaces, per OP:
 //   OP_DRAW        draw_proposal_path!(bb)            src/biblock.jl:80-106   (pCN + guided EM + ll, fused; K3+K2+K4)

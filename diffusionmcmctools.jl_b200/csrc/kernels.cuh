@@ -25,13 +25,10 @@ namespace dmt {
 #define DMT_FWD_TPB 64
 #endif
 #ifndef DMT_FWD_MINB
-#define DMT_FWD_MINB 1 // min resident CTAs per SM promised to ptxas (caps registers)
-#endif
-#ifndef DMT_PF_DIST
-#define DMT_PF_DIST 2 // L2 prefetch distance in tiles (0 = off)
+#define DMT_FWD_MINB 0 // min resident CTAs per SM promised to ptxas (caps registers); 0 = per-model default (fwd_minb)
 #endif
 #ifndef DMT_EVICT_FIRST
-#define DMT_EVICT_FIRST 0 // 1: streamed sectors are marked L2::evict_first
+#define DMT_EVICT_FIRST 1 // 1: streamed sectors are marked L2::evict_first (spill lines and per-interval records stay in L2)
 #endif
 #ifndef DMT_BWD_MINB
 #define DMT_BWD_MINB 1
@@ -172,225 +169,7 @@ __device__ __forceinline__ void guided_terms(const typename MD::Par &par, const 
     }
 }
 
-// =========================================================================================== K2/K3/K4/K5 forward kernel
-// One thread = one (chain, block).  grid = (ceil(M/TPB), n_blocks).  Replaces, per OP:
-//   OP_DRAW        draw_proposal_path!(bb)            src/biblock.jl:80-106   (pCN + guided EM + ll, fused; K3+K2+K4)
-//   OP_RECOMPUTE   recompute_path!(b°, b.WW; skip)    src/block.jl:161-187    (K2+K4)
-//   OP_LOGLIK      loglikhd!(b)                       src/block.jl:140-152    (K4)
-//   OP_INVSOLVE    find_W_for_X!(b)                   src/block.jl:120-131    (K5)
-//   OP_INVSOLVE_LL both of the above in one pass over X
-//   OP_INIT        init_paths! / draw_proposal_path!(u::SamplingUnit)  src/sampling_unit.jl:83-87,118-120 (fresh noise, in place)
-// (v1: whole tile in registers, no shared memory.  Superseded by fwd_kernel in fwd_kernel.cuh, which stages the guiding
-//  term through a cp.async shared-memory pipeline; kept as the A/B reference: build with -DDMT_FWD_V1=1.)
-template <class MD, int OP>
-__global__ void __launch_bounds__(FWD_TPB, DMT_FWD_MINB) fwd_kernel_v1(const DevCtx cx, const LayoutDev ly, const FwdArgs fa) {
-    constexpr int D = MD::D, DW = MD::DW, NPAR = MD::NPAR, NH = D * (D + 1) / 2, NG = NH + D, NAUX = D * D + D + NH;
-    constexpr bool READS_X = (OP == OP_LOGLIK || OP == OP_INVSOLVE || OP == OP_INVSOLVE_LL);
-    constexpr bool WRITES_X = (OP == OP_DRAW || OP == OP_RECOMPUTE || OP == OP_INIT);
-    constexpr bool READS_W = (OP == OP_DRAW || OP == OP_RECOMPUTE);
-    constexpr bool WRITES_W = (OP == OP_DRAW || OP == OP_INIT || OP == OP_INVSOLVE || OP == OP_INVSOLVE_LL);
-    constexpr bool WANT_LL = (OP != OP_INVSOLVE);
-    constexpr bool RNG = (OP == OP_DRAW || OP == OP_INIT);
-
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = blockIdx.y;
-    if (c >= cx.M) return;
-    const size_t M = cx.M, P = cx.P;
-    if (OP == OP_INIT && ly.ok[(size_t)b * M + c]) return; // retry only the chains that failed so far
-    const int ps = cx.pset[c];
-    const int i0 = ly.i0[b], i1 = ly.i1[b];
-    const bool last = ly.last[b] != 0;
-
-    const int law_side = (OP == OP_RECOMPUTE || OP == OP_LOGLIK) ? fa.law_side : 0;
-    const int xin_side = law_side;                                 // start point / path that is read
-    const int xout_side = (OP == OP_DRAW) ? 1 : law_side;
-    const int win_side = (OP == OP_RECOMPUTE) ? fa.w_side : 0;
-    const int wout_side = (OP == OP_DRAW) ? 1 : 0;
-    const int ll_side = (OP == OP_DRAW) ? 1 : law_side;
-    const double rho = (OP == OP_DRAW) ? ly.rho[b] : 0.0;
-    const double crho = (OP == OP_DRAW) ? sqrt(1.0 - rho * rho) : 1.0;
-    const int skip = fa.skip;
-
-    double x[D];
-    {   // y1 = XX[1].x[1] of the block  (src/biblock.jl:96, src/block.jl:177)
-        const int sl = xin_side ^ cx.parX[(size_t)i0 * M + c];
-#pragma unroll
-        for (int i = 0; i < D; i++) x[i] = cx.X0[sl * cx.X0buf + ((size_t)i0 * D + i) * M + c];
-    }
-    double ll = 0.0;
-    bool ok = true;
-
-    for (int k = i0; k <= i1 && ok; ++k) {
-        const int store = (k == i1 && !last) ? 1 : 0; // P_last comes from PPb (src/block.jl:68)
-        const int slotL = law_side ^ cx.parP[store][(size_t)k * P + ps];
-        double th[NPAR];
-        {
-            const double *tp = cx.theta[slotL][store] + (size_t)k * NPAR * P + ps;
-#pragma unroll
-            for (int i = 0; i < NPAR; i++) th[i] = tp[(size_t)i * P];
-        }
-        const typename MD::Par par(th);
-        double Bm[D * D], beta[D], at[NH];
-        if (WANT_LL) {
-            const double *ap = cx.aux[slotL][store] + (size_t)k * NAUX * P + ps;
-#pragma unroll
-            for (int i = 0; i < D * D; i++) Bm[i] = ap[(size_t)i * P];
-#pragma unroll
-            for (int i = 0; i < D; i++) beta[i] = ap[(size_t)(D * D + i) * P];
-            if (!MD::CONSTDIFF) {
-#pragma unroll
-                for (int i = 0; i < NH; i++) at[i] = ap[(size_t)(D * D + D + i) * P];
-            }
-        }
-        const int nst = cx.nsteps[k];
-        const int t0 = cx.tile0[k];
-        const int gt0 = store ? cx.ppb_tile0[k] : t0;
-        const double *Gp = cx.G[slotL][store] + ((size_t)gt0 * NG * P + ps) * 4;
-        const size_t gstr = P * 4; // stride between components
-
-        if (WANT_LL && k == i0) { // loglikhd_obs(PP[1], y1) = -c - y'Hy/2 + F'y  (src/block.jl:178)
-            double g0[NG];
-#pragma unroll
-            for (int q = 0; q < NG; q++) g0[q] = Gp[(size_t)q * gstr];
-            double s = -cx.c0[slotL][store][(size_t)k * P + ps];
-#pragma unroll
-            for (int i = 0; i < D; i++) {
-                double hx = 0.0;
-#pragma unroll
-                for (int j = 0; j < D; j++) hx = fma(g0[sidx<D>(i, j)], x[j], hx);
-                s += x[i] * (g0[NH + i] - 0.5 * hx);
-            }
-            ll = s;
-        }
-
-        const uint8_t pw = cx.parW[(size_t)k * M + c], px = cx.parX[(size_t)k * M + c];
-        const double *Win = cx.W + (size_t)(win_side ^ pw) * cx.Wbuf + ((size_t)t0 * DW * M + c) * 4;
-        double *Wout = cx.W + (size_t)(wout_side ^ pw) * cx.Wbuf + ((size_t)t0 * DW * M + c) * 4;
-        const double *Xin = cx.X + (size_t)(xin_side ^ px) * cx.Xbuf + ((size_t)t0 * D * M + c) * 4;
-        double *Xout = cx.X + (size_t)(xout_side ^ px) * cx.Xbuf + ((size_t)t0 * D * M + c) * 4;
-        if (READS_X && k > i0) { // an existing path: interval k starts at ITS OWN XX[k].x[1]
-#pragma unroll
-            for (int i = 0; i < D; i++) x[i] = cx.X0[(size_t)(xin_side ^ px) * cx.X0buf + ((size_t)k * D + i) * M + c];
-        }
-        if (WRITES_X) { // XX°[k].x[1] = y1
-            double *x0p = cx.X0 + (size_t)(xout_side ^ px) * cx.X0buf + (size_t)k * D * M + c;
-#pragma unroll
-            for (int i = 0; i < D; i++) x0p[(size_t)i * M] = x[i];
-        }
-
-        const int ntl = (nst + 3) >> 2;
-        for (int q = 0; q < ntl; ++q) {
-            double g[NG][4], w[DW][4], xt[D][4], dt4[4], sq4[4];
-#pragma unroll
-            for (int i = 0; i < NG; i++) ld256(Gp + ((size_t)q * NG + i) * gstr, g[i]);
-            if (READS_W) {
-#pragma unroll
-                for (int j = 0; j < DW; j++) ld256(Win + ((size_t)q * DW + j) * M * 4, w[j]);
-            }
-            if (READS_X) {
-#pragma unroll
-                for (int i = 0; i < D; i++) ld256(Xin + ((size_t)q * D + i) * M * 4, xt[i]);
-            }
-            ld256u(cx.dt + (size_t)(t0 + q) * 4, dt4);
-            if (RNG) ld256u(cx.sqdt + (size_t)(t0 + q) * 4, sq4);
-            if (DMT_PF_DIST > 0 && q + DMT_PF_DIST < ntl) { // pull a later tile into L2 while this one is computed
-#pragma unroll
-                for (int i = 0; i < NG; i++) prefetch_l2(Gp + ((size_t)(q + DMT_PF_DIST) * NG + i) * gstr);
-                if (READS_W) {
-#pragma unroll
-                    for (int j = 0; j < DW; j++) prefetch_l2(Win + ((size_t)(q + DMT_PF_DIST) * DW + j) * M * 4);
-                }
-                if (READS_X) {
-#pragma unroll
-                    for (int i = 0; i < D; i++) prefetch_l2(Xin + ((size_t)(q + DMT_PF_DIST) * D + i) * M * 4);
-                }
-            }
-            if (RNG) { // K3: dW° = rho dW + sqrt(1-rho^2) sqrt(dt) xi   (A.2)
-                double z[4 * DW];
-                if (fa.Z) {
-#pragma unroll
-                    for (int s = 0; s < 4; s++)
-#pragma unroll
-                        for (int j = 0; j < DW; j++) {
-                            const int i = 4 * q + s;
-                            z[s * DW + j] = (i < nst) ? fa.Z[((size_t)(cx.step0[k] + i) * DW + j) * M + c] : 0.0;
-                        }
-                } else {
-                    tile_normals<DW>(cx.seed, cx.chain_offset + (uint32_t)c, (uint32_t)(t0 + q), fa.iter, z);
-                }
-#pragma unroll
-                for (int s = 0; s < 4; s++)
-#pragma unroll
-                    for (int j = 0; j < DW; j++) {
-                        if (OP == OP_DRAW) w[j][s] = rho * w[j][s] + crho * sq4[s] * z[s * DW + j];
-                        else w[j][s] = sq4[s] * z[s * DW + j];
-                    }
-            }
-#pragma unroll
-            for (int s = 0; s < 4; s++) {
-                const int i = 4 * q + s;
-                if (i < nst && ok) {
-                    double Hs[NH], F[D], gd[D], G = 0.0;
-#pragma unroll
-                    for (int a = 0; a < NH; a++) Hs[a] = g[a][s];
-#pragma unroll
-                    for (int a = 0; a < D; a++) F[a] = g[NH + a][s];
-                    const typename MD::Diff df(par, x);
-                    guided_terms<MD, WANT_LL>(par, df, Bm, beta, at, Hs, F, x, gd, G);
-                    if (WANT_LL && i < nst - skip) ll = fma(G, dt4[s], ll);
-                    double xn[D];
-                    if (WRITES_X) { // K2: x' = x + (b + a r) dt + sigma dW   (A.3)
-                        double dwv[DW], sw[D];
-#pragma unroll
-                        for (int j = 0; j < DW; j++) dwv[j] = w[j][s];
-                        df.sig_mul(dwv, sw);
-#pragma unroll
-                        for (int a = 0; a < D; a++) xn[a] = fma(gd[a], dt4[s], x[a]) + sw[a];
-                        bool fin = df.ok();
-#pragma unroll
-                        for (int a = 0; a < D; a++) fin = fin && isfinite(xn[a]);
-                        if (!(fin && MD::bound_ok(par, xn))) { ok = false; ll = -INFINITY; } // src/block.jl:181
-#pragma unroll
-                        for (int a = 0; a < D; a++) xt[a][s] = xn[a];
-                    } else {
-#pragma unroll
-                        for (int a = 0; a < D; a++) xn[a] = xt[a][s];
-                        if (OP == OP_INVSOLVE || OP == OP_INVSOLVE_LL) { // K5: dW = sigma^+ (x' - x - (b + a r) dt)   (A.5)
-                            double res[D], dwv[DW];
-#pragma unroll
-                            for (int a = 0; a < D; a++) res[a] = xn[a] - x[a] - gd[a] * dt4[s];
-                            df.inv_sig(res, dwv);
-#pragma unroll
-                            for (int j = 0; j < DW; j++) w[j][s] = dwv[j];
-                        }
-                    }
-#pragma unroll
-                    for (int a = 0; a < D; a++) x[a] = xn[a];
-                } else {
-                    if (WRITES_X) {
-#pragma unroll
-                        for (int a = 0; a < D; a++) xt[a][s] = 0.0;
-                    }
-                    if (WRITES_W && !RNG) {
-#pragma unroll
-                        for (int j = 0; j < DW; j++) w[j][s] = 0.0;
-                    }
-                }
-            }
-            if (WRITES_W) {
-#pragma unroll
-                for (int j = 0; j < DW; j++) st256(Wout + ((size_t)q * DW + j) * M * 4, w[j]);
-            }
-            if (WRITES_X) {
-#pragma unroll
-                for (int i = 0; i < D; i++) st256(Xout + ((size_t)q * D + i) * M * 4, xt[i]);
-            }
-            if (!ok) break;
-        }
-    }
-    if (WANT_LL) ly.ll[((size_t)ll_side * ly.nb + b) * M + c] = ll;
-    if (WRITES_X) ly.ok[(size_t)b * M + c] = ok ? 1 : 0;
-}
+// (the forward kernel K2/K3/K4/K5 lives in fwd_kernel.cuh)
 
 // =========================================================================================== K1 backward filter
 template <int D, bool DIAG>

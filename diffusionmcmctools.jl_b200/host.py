@@ -265,6 +265,18 @@ def find_W_for_X(be):
     be.ctx.find_W_for_X(be.layout)
 
 
+def enable_guiding_cache(be, enable=True):
+    """Not in the reference: keep the v-independent part of the guiding term between sweeps (include/dmt.h).
+    Use it for smoothing with blocking, where only the blocks' frozen end points change between recompute_guiding_term! calls."""
+    be.ctx.enable_guiding_cache(be.layout, enable)
+
+
+def blocking_sweep(be, mcmciter):
+    """GP.set_obs!(be); recompute_guiding_term!(be, Val(:P_only)); find_W_for_X!(be); loglikhd!(be); draw_proposal_path!(be)
+    (docs/src/tutorials/block_collection/inference_with_blocking.md:52-57) as one library call / three kernel launches."""
+    be.ctx.blocking_sweep(be.layout, mcmciter)
+
+
 # ---- parameters (src/block_ensemble.jl:226-255 -> src/biblock.jl:334-371) -------------------------------------------
 def is_critical_update(be, pnames):
     raise NotImplementedError("the reference's is_critical_update reads fields no ParamNames struct has (src/biblock.jl:315-317, "

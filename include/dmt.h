@@ -131,6 +131,12 @@ int32_t dmt_draw_proposal_path(dmt_ctx *ctx, int32_t layout, uint32_t iter, cons
  * (docs/src/tutorials/block_collection/inference_with_blocking.md:55-57) — in ONE pass over the path: the accepted noise
  * recovered by K5 feeds the pCN refresh in registers.  Same results as the three calls up to FP64 rounding. (K5+K4+K3+K2+K4) */
 int32_t dmt_find_W_loglikhd_draw(dmt_ctx *ctx, int32_t layout, uint32_t iter, const double *Z);
+/* The whole body of the blocking sweep before the accept step, in the tutorial's order
+ * (docs/src/tutorials/block_collection/inference_with_blocking.md:52-57):
+ *   GP.set_obs!(be); recompute_guiding_term!(be, Val(:P_only)); find_W_for_X!(be); loglikhd!(be); draw_proposal_path!(be)
+ * as three launches: the end-point gather, K1 (through the guiding cache when enabled) and ONE fused forward pass over the
+ * path.  Same results as the five calls up to FP64 rounding. */
+int32_t dmt_blocking_sweep(dmt_ctx *ctx, int32_t layout, uint32_t iter);
 /* recompute_path!(b°, b.WW; skip) as used by set_proposal_law! (src/biblock.jl:343 -> src/block.jl:161-187):
  * law and X of `law_side`, noise of `noise_side`; sets ll[law_side].                                    (K2+K4) */
 int32_t dmt_recompute_path(dmt_ctx *ctx, int32_t layout, int32_t law_side, int32_t noise_side, int32_t skip);

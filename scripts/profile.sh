@@ -6,7 +6,8 @@ set -u
 TAG=${1:-r01}; shift || true
 OUT=gpurun_out
 mkdir -p $OUT
-CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e $*"
+# warm-up 2: the first sweep on each of the two layouts builds its guiding cache (10 probe passes of bwd_kernel); steady state after
+CMD="python bench.py --steps 2 --warmup 2 --no-cpu-baseline --no-e2e $*"
 echo "== plain: $CMD"
 $CMD > $OUT/plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -20 $OUT/plain_$TAG.log; exit 1; }
 tail -1 $OUT/plain_$TAG.log | cut -c1-400
@@ -15,6 +16,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 echo "rc=$?"; tail -3 $OUT/ncu_launch_$TAG.log | cut -c1-300
 echo "== full capture of the sweep kernels (draw, invsolve_ll, bwd)"
 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-    -k 'regex:fwd_kernel|bwd_kernel' -s 4 -c 4 -o $OUT/prof_$TAG -f $CMD > $OUT/ncu_full_$TAG.log 2>&1
+    -k 'regex:fwd_kernel|bwd_kernel|cache_apply_kernel' -s ${NCU_SKIP:-28} -c ${NCU_COUNT:-6} -o $OUT/prof_$TAG -f $CMD > $OUT/ncu_full_$TAG.log 2>&1
 echo "rc=$?"; tail -3 $OUT/ncu_full_$TAG.log | cut -c1-300
 ls -la $OUT

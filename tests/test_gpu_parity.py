@@ -231,20 +231,23 @@ def test_guiding_cache_matches_uncached_sweeps(name):
     K = 8
     layouts = [([(0, 2), (3, 5), (6, 7)], 0.7), ([(0, 3), (4, 7)], 0.6)]
     prob = small_problem(name, M=37, K=K, layouts=layouts, seed=21, nsteps=10)
-    a, b = make_ctx(prob, seed=5, n_layouts=3), make_ctx(prob, seed=5, n_layouts=3)
-    for ctx in (a, b):
+    a, b, s = (make_ctx(prob, seed=5, n_layouts=3) for _ in range(3))
+    for ctx in (a, b, s):
         ctx.set_blocks(2, [(0, K - 1)], 0.0)
         ctx.recompute_guiding_term(2, _lib.P_ONLY)
         assert ctx.init_paths(2, iter0=77, max_tries=50) == 0
-    b.enable_guiding_cache(0); b.enable_guiding_cache(1)
+    for ctx in (b, s):
+        ctx.enable_guiding_cache(0); ctx.enable_guiding_cache(1)
     n_acc = 0
     for it in range(6):
         l = it % 2
         if it == 4:   # change the accepted laws: caches must rebuild
             th = prob.theta * (1 + 1e-3)
-            for ctx in (a, b):
+            for ctx in (a, b, s):
                 ctx.set_params(th, side=0, stores=3)
                 ctx.set_aux_linearised(prob.xbar, side=0, store=0); ctx.set_aux_linearised(prob.xbar, side=0, store=1)
+        # s: the whole sweep body as ONE call (K1 folded into the forward pass once the cache is valid)
+        s.blocking_sweep(l, it)
         for ctx in (a, b):
             ctx.set_artificial_obs(l)
             ctx.recompute_guiding_term(l, _lib.P_ONLY)
@@ -259,15 +262,23 @@ def test_guiding_cache_matches_uncached_sweeps(name):
                     assert np.abs(cb[0] - ca[0]).max() < 1e-9 * max(1.0, np.abs(ca[0]).max())
         for ctx in (a, b):
             ctx.find_W_loglikhd_draw(l, it)
-        assert np.array_equal(a.get_success(l), b.get_success(l))
-        assert rel_err(b.get_ll(l, 0), a.get_ll(l, 0)) < 1e-9 and rel_err(b.get_ll(l, 1), a.get_ll(l, 1)) < 1e-9
-        for ctx in (a, b):
+        for o in (b, s):
+            assert np.array_equal(a.get_success(l), o.get_success(l))
+            assert rel_err(o.get_ll(l, 0), a.get_ll(l, 0)) < 1e-9 and rel_err(o.get_ll(l, 1), a.get_ll(l, 1)) < 1e-9
+        for ctx in (a, b, s):
             ctx.accept_reject_path(l, it)
-        assert np.array_equal(a.get_last_accept(l), b.get_last_accept(l))
         n_acc += a.get_last_accept(l).sum()
-        assert rel_err(b.get_X(0), a.get_X(0)) < 1e-9
+        for o in (b, s):
+            assert np.array_equal(a.get_last_accept(l), o.get_last_accept(l))
+            assert rel_err(o.get_X(0), a.get_X(0)) < 1e-9 and rel_err(o.get_W(0), a.get_W(0)) < 1e-9
+        if it == 3:   # the one-call sweep left F un-materialised: any other op on the layout must see the current guiding term
+            Hs, Fs, cs = s.get_layout_guiding_term(l, layouts[l][0][0][0], 0)
+            Ha, Fa, ca = a.get_layout_guiding_term(l, layouts[l][0][0][0], 0)
+            assert rel_err(Fs[:-1], Fa[:-1]) < 1e-10 and np.abs(cs[0] - ca[0]).max() < 1e-9 * max(1.0, np.abs(ca[0]).max())
+            s.loglikhd(l, 0, 0); a.loglikhd(l, 0, 0); b.loglikhd(l, 0, 0)
+            assert rel_err(s.get_ll(l, 0), a.get_ll(l, 0)) < 1e-9
     assert n_acc > 0
-    a.close(); b.close()
+    a.close(); b.close(); s.close()
 
 
 def test_rho_one_reproduces_accepted_path_bit_exactly():
