@@ -201,8 +201,20 @@ template <int OP> void launch_fwd(dmt_ctx *c, Layout &L, const FwdArgs &fa) {
     CK(cudaGetLastError());
 }
 
+template <class MD> void launch_bwd_model(dmt_ctx *c, Layout &L, const BwdArgs &ba) {
+    const int nz = c->cfg.two_sided_laws ? 2 : 1;
+    bool all_terminal = true;
+    for (int b = 0; b < L.nb; b++) all_terminal = all_terminal && L.last[b];
+    if (MD::ATIL_DIAG && MD::D >= 5 && all_terminal && !getenv("DMT_NO_COOP_K1")) {
+        // wide state, no exact-observation interval: D lanes per parameter set (kernels.cuh, bwd_coop_kernel)
+        constexpr int per_cta = 4 * (32 / MD::D);
+        bwd_coop_kernel<MD><<<dim3((c->P + per_cta - 1) / per_cta, L.nb, nz), 128, 0, c->stream>>>(c->dev, L.dev, ba);
+    } else {
+        bwd_kernel<MD><<<pset_grid(c, L.nb, BWD_TPB, nz), BWD_TPB, 0, c->stream>>>(c->dev, L.dev, ba);
+    }
+}
+
 void launch_bwd(dmt_ctx *c, Layout &L, int side_mask, const double *v_override = nullptr) {
-    dim3 grid = pset_grid(c, L.nb, BWD_TPB, c->cfg.two_sided_laws ? 2 : 1);
     BwdArgs ba{};
     ba.side_mask = side_mask;
     if (v_override) {
@@ -210,7 +222,7 @@ void launch_bwd(dmt_ctx *c, Layout &L, int side_mask, const double *v_override =
         for (int i = 0; i < c->D; i++) ba.v[i] = v_override[i];
     }
 #define DMT_CASE(MID)                                                                                              \
-    case MID: bwd_kernel<Model<MID>><<<grid, BWD_TPB, 0, c->stream>>>(c->dev, L.dev, ba); break;
+    case MID: launch_bwd_model<Model<MID>>(c, L, ba); break;
     switch (c->cfg.model) {
         DMT_FOR_MODELS(DMT_CASE)
         default: throw DmtError(DMT_ERR_UNSUPPORTED, "model not compiled into this build of libdmt");

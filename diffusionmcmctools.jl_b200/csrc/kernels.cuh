@@ -524,6 +524,166 @@ __global__ void __launch_bounds__(BWD_TPB, DMT_BWD_MINB) bwd_kernel(const DevCtx
     }
 }
 
+// =========================================================================================== K1, row-cooperative variant
+// For wide states and few (pset, block) pairs (BASELINE C5: Jansen–Rit d = 6, one terminal block) one thread per pset is the
+// wrong mapping: a 28-component Riccati system per thread spills heavily and only P threads exist.  Here D consecutive lanes
+// form a group that owns ONE pset: lane r keeps row r of the symmetric H and F_r in registers; one gather of H through
+// warp shuffles per RK4 stage feeds both products of  dH = -(HC + (HC)'),  C = B - a H / 2  (a diagonal):
+//     (HC)_{rj} = sum_k H_rk C_kj          and, by symmetry of H,          (HC)_{jr} = sum_k H_kj C_kr
+// so no transpose exchange is needed.  32/D psets per warp, 32x more threads, same arithmetic per component as bwd_kernel
+// (results agree to FP64 rounding).  Terminal blocks of diagonal-a models only (what C5 needs); others use bwd_kernel.
+template <class MD>
+__global__ void __launch_bounds__(128) bwd_coop_kernel(const DevCtx cx, const LayoutDev ly, const BwdArgs ba) {
+    constexpr int D = MD::D, NH = D * (D + 1) / 2, NG = NH + D, NAUX = D * D + D + NH, GPW = 32 / D;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int g = lane / D, r = lane % D;
+    const int base = g * D;
+    const int ps_raw = (blockIdx.x * (blockDim.x >> 5) + wid) * GPW + g;
+    const int b = blockIdx.y, side = blockIdx.z;
+    if (!((ba.side_mask >> side) & 1)) return;
+    const bool active = (g < GPW) && (ps_raw < cx.P);
+    const int ps = min(ps_raw, cx.P - 1); // idle lanes shadow a valid pset (they take part in the shuffles, never store)
+    const size_t P = cx.P;
+    const int i0 = ly.i0[b], i1 = ly.i1[b];
+    double Hrow[D], Fr = 0.0, cc = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; j++) Hrow[j] = 0.0;
+
+    for (int k = i1; k >= i0; --k) {
+        const int slot = side ^ cx.parP[0][(size_t)k * P + ps];
+        double Bm[D * D], Bcol[D], beta[D], ad[D];
+        {
+            const double *ap = cx.aux[slot][0] + (size_t)k * NAUX * P + ps;
+#pragma unroll
+            for (int i = 0; i < D * D; i++) Bm[i] = ap[(size_t)i * P];
+#pragma unroll
+            for (int i = 0; i < D; i++) {
+                Bcol[i] = ap[(size_t)(i * D + r) * P]; // column r of B: lane-specific VALUES, static register indices
+                beta[i] = ap[(size_t)(D * D + i) * P];
+                ad[i] = ap[(size_t)(D * D + D + sidx<D>(i, i)) * P];
+            }
+        }
+        const int nst = cx.nsteps[k], t0 = cx.tile0[k];
+        const bool priv = (side == 0) && (ly.Gl[0] != nullptr);
+        double *Gp = (priv ? ly.Gl[0] : cx.G[slot][0]) + ((size_t)t0 * NG * P + ps) * 4;
+        const size_t gstr = P * 4;
+        const double *dtp = cx.dt + (size_t)t0 * 4;
+
+        {   // jump at the observation: H += L'S^-1 L, F += L'S^-1 v, c += (m log 2pi + log det S + v'S^-1 v)/2; lane r does row r
+            const int m = cx.m;
+            const double *op = cx.obs[slot] + (size_t)k * (m * D + m * m + m) * P + ps;
+            double Sg[D][D], Lc[D][D], Lcol[D], v[D], Ycol[D], y[D];
+#pragma unroll
+            for (int a = 0; a < D; a++) {
+                Lcol[a] = (a < m) ? op[(size_t)(a * D + r) * P] : 0.0;
+#pragma unroll
+                for (int bq = 0; bq < D; bq++) Sg[a][bq] = (a < m && bq < m) ? op[(size_t)(m * D + a * m + bq) * P] : (a == bq ? 1.0 : 0.0);
+                v[a] = (a < m) ? op[(size_t)(m * D + m * m + a) * P] : 0.0;
+            }
+            double ld = 0.0;
+#pragma unroll
+            for (int j = 0; j < D; j++) {
+                double s = Sg[j][j];
+#pragma unroll
+                for (int q = 0; q < j; q++) s -= Lc[j][q] * Lc[j][q];
+                const double l = sqrt(s);
+                Lc[j][j] = l;
+                if (j < m) ld += log(l);
+#pragma unroll
+                for (int i = j + 1; i < D; i++) {
+                    double t = Sg[i][j];
+#pragma unroll
+                    for (int q = 0; q < j; q++) t -= Lc[i][q] * Lc[j][q];
+                    Lc[i][j] = t / l;
+                }
+            }
+            double yy = 0.0;
+#pragma unroll
+            for (int a = 0; a < D; a++) { // forward substitution on column r of L and on v
+                const double il = 1.0 / Lc[a][a];
+                double s = Lcol[a], sv = v[a];
+#pragma unroll
+                for (int q = 0; q < a; q++) { s -= Lc[a][q] * Ycol[q]; sv -= Lc[a][q] * y[q]; }
+                Ycol[a] = s * il;
+                y[a] = sv * il;
+                yy = fma(y[a], y[a], yy);
+            }
+#pragma unroll
+            for (int j = 0; j < D; j++) {
+                double s = 0.0;
+#pragma unroll
+                for (int a = 0; a < D; a++) s = fma(Ycol[a], __shfl_sync(FULL, Ycol[a], base + j), s);
+                Hrow[j] += s;
+            }
+#pragma unroll
+            for (int a = 0; a < D; a++) Fr = fma(Ycol[a], y[a], Fr);
+            cc += 0.5 * (m * 1.8378770664093453 + 2.0 * ld + yy);
+        }
+
+        auto rhs = [&](const double *Hr, double F_r, double *dHr, double &dFr, double &dc) {
+            double Mx[D], My[D], Fall[D], tr = 0.0;
+#pragma unroll
+            for (int j = 0; j < D; j++) { Mx[j] = 0.0; My[j] = 0.0; Fall[j] = __shfl_sync(FULL, F_r, base + j); }
+#pragma unroll
+            for (int q = 0; q < D; q++) {
+                const double ckr = fma(-0.5 * ad[q], Hr[q], Bcol[q]); // C_qr = B_qr - a_q H_qr / 2, H_qr = H_rq (own row)
+#pragma unroll
+                for (int j = 0; j < D; j++) {
+                    const double hqj = __shfl_sync(FULL, Hr[j], base + q);       // H_qj from the lane that owns row q
+                    const double cqj = fma(-0.5 * ad[q], hqj, Bm[q * D + j]);    // C_qj
+                    Mx[j] = fma(Hr[q], cqj, Mx[j]);                              // (HC)_{rj}
+                    My[j] = fma(hqj, ckr, My[j]);                                // (HC)_{jr} = sum_q H_jq C_qr, H_jq = H_qj
+                    if (j == q) tr = fma(ad[q], hqj, tr);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < D; j++) dHr[j] = -(Mx[j] + My[j]);
+            double s = 0.0, bF = 0.0, FaF = 0.0;
+#pragma unroll
+            for (int q = 0; q < D; q++) {
+                s = fma(Hr[q], beta[q], s);
+                s = fma(-fma(-ad[q], Hr[q], Bcol[q]), Fall[q], s); // - (B - aH)_{qr} F_q
+                bF = fma(beta[q], Fall[q], bF);
+                FaF = fma(ad[q] * Fall[q], Fall[q], FaF);
+            }
+            dFr = s;
+            dc = bF + 0.5 * FaF - 0.5 * tr;
+        };
+
+        for (int j = nst - 1; j >= 0; --j) { // classical RK4 from t[j+1] back to t[j], row r of H, F_r, c (replicated)
+            const double h = dtp[j];
+            double kH[D], kF, kc, aH[D], aF, ac, Hs[D], Fs;
+            rhs(Hrow, Fr, kH, kF, kc);
+#pragma unroll
+            for (int i = 0; i < D; i++) { Hs[i] = fma(-0.5 * h, kH[i], Hrow[i]); aH[i] = kH[i]; }
+            Fs = fma(-0.5 * h, kF, Fr); aF = kF; ac = kc;
+            rhs(Hs, Fs, kH, kF, kc);
+#pragma unroll
+            for (int i = 0; i < D; i++) { Hs[i] = fma(-0.5 * h, kH[i], Hrow[i]); aH[i] = fma(2.0, kH[i], aH[i]); }
+            Fs = fma(-0.5 * h, kF, Fr); aF = fma(2.0, kF, aF); ac = fma(2.0, kc, ac);
+            rhs(Hs, Fs, kH, kF, kc);
+#pragma unroll
+            for (int i = 0; i < D; i++) { Hs[i] = fma(-h, kH[i], Hrow[i]); aH[i] = fma(2.0, kH[i], aH[i]); }
+            Fs = fma(-h, kF, Fr); aF = fma(2.0, kF, aF); ac = fma(2.0, kc, ac);
+            rhs(Hs, Fs, kH, kF, kc);
+            const double h6 = h / 6.0;
+#pragma unroll
+            for (int i = 0; i < D; i++) Hrow[i] = fma(-h6, aH[i] + kH[i], Hrow[i]);
+            Fr = fma(-h6, aF + kF, Fr);
+            cc = fma(-h6, ac + kc, cc);
+            if (active) {
+                double *gp = Gp + (size_t)(j >> 2) * NG * gstr + (j & 3);
+#pragma unroll
+                for (int jj = 0; jj < D; jj++)
+                    if (jj >= r) gp[(size_t)(r * D - r * (r - 1) / 2 + (jj - r)) * gstr] = Hrow[jj]; // packed upper (r, jj)
+                gp[(size_t)(NH + r) * gstr] = Fr;
+            }
+        }
+        if (active && r == 0) (priv ? ly.c0l[0] : cx.c0[slot][0])[(size_t)k * P + ps] = cc;
+    }
+}
+
 // =========================================================================================== guiding cache (K1 fast path)
 // In a smoothing sweep with blocking only the frozen end point v of each non-terminal block changes between two calls of
 // recompute_guiding_term!(be, Val(:P_only)) (src/biblock.jl:275-278 then src/block.jl:104-110).  H does not depend on v, and the
