@@ -148,6 +148,8 @@ struct dmt_ctx {
     DevBuf<uint8_t> d_mask;
     void *nccl_comm = nullptr;
     int n_ranks = 1;
+    bool tma_ok = false;     // P == M with the identity pset map: the TMA fast path of fwd_kernel is usable
+    bool parP_mixed = false; // a masked swap_PP! made the law parity chain-dependent
 
     double *scratch(size_t n) {
         if (d_scratch.n < n) d_scratch.alloc(n, false);
@@ -175,16 +177,25 @@ void check_range(dmt_ctx *c, int k0, int k1) { REQUIRE(0 <= k0 && k0 <= k1 && k1
 dim3 chain_grid(dmt_ctx *c, int ny, int tpb) { return dim3((c->M + tpb - 1) / tpb, ny, 1); }
 dim3 pset_grid(dmt_ctx *c, int ny, int tpb, int nz = 1) { return dim3((c->P + tpb - 1) / tpb, ny, nz); }
 
-template <class MD, int OP> void launch_fwd_model(dmt_ctx *c, Layout &L, const FwdArgs &fa) {
-    constexpr int TPB = (MD::D >= 6) ? 32 : FWD_TPB; // wide guiding terms: smaller CTAs keep the smem ring under 64 KB
-    constexpr size_t smem = fwd_smem_bytes<MD, TPB>();
+template <class MD, int OP, bool TMA> void launch_fwd_variant(dmt_ctx *c, Layout &L, const FwdArgs &fa) {
+    constexpr int TPB = (MD::D >= 6) ? 32 : FWD_TPB; // wide guiding terms: smaller CTAs
+    constexpr size_t smem = fwd_smem_bytes<MD, TPB, TMA>();
     static bool attr_done[64] = {};
     const int dev = c->cfg.device & 63;
     if (!attr_done[dev]) {
-        CK(cudaFuncSetAttribute(fwd_kernel<MD, OP, TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(fwd_kernel<MD, OP, TPB, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done[dev] = true;
     }
-    fwd_kernel<MD, OP, TPB><<<chain_grid(c, L.nb, TPB), TPB, smem, c->stream>>>(c->dev, L.dev, fa);
+    fwd_kernel<MD, OP, TPB, TMA><<<chain_grid(c, L.nb, TPB), TPB, smem, c->stream>>>(c->dev, L.dev, fa);
+}
+template <class MD, int OP> void launch_fwd_model(dmt_ctx *c, Layout &L, const FwdArgs &fa) {
+#ifdef DMT_WITH_TMA
+    // TMA path (opt-in build, -DDMT_WITH_TMA, and DMT_TMA=1 at run time): every chain owns its pset in chain order and the law
+    // parity is uniform, so a warp's H,F chunk is contiguous.  Measured SLOWER than the LDG.256 path inside the real kernel
+    // (3.83 vs 3.29 ms, profiles/r01_tuning.md) although faster on the bare memory pattern — kept for the next round's work.
+    if (c->tma_ok && !c->parP_mixed) { launch_fwd_variant<MD, OP, true>(c, L, fa); return; }
+#endif
+    launch_fwd_variant<MD, OP, false>(c, L, fa);
 }
 
 void ensure_guiding(dmt_ctx *c, Layout &L);
@@ -486,6 +497,11 @@ int32_t dmt_create(const dmt_config *cfg, const int32_t *n_pts, const double *tt
             pset[i] = pset_of_chain ? pset_of_chain[i] : (c->P == c->M ? i : 0);
             REQUIRE(pset[i] >= 0 && pset[i] < c->P, DMT_ERR_ARG, "pset_of_chain entry out of range");
             REQUIRE(pset_of_chain || c->P == c->M || c->P == 1, DMT_ERR_ARG, "pset_of_chain required when 1 < P < M");
+        }
+        {
+            bool ident = (c->P == c->M);
+            for (int i = 0; i < c->M && ident; i++) ident = (pset[i] == i);
+            c->tma_ok = ident && getenv("DMT_TMA") != nullptr;
         }
         c->d_tile0.alloc(K + 1); c->d_step0.alloc(K + 1); c->d_pt0.alloc(K + 1); c->d_nsteps.alloc(K); c->d_ppb_tile0.alloc(K);
         c->d_pset.alloc(c->M); c->d_dt.alloc(dt.size()); c->d_sqdt.alloc(sq.size());
@@ -896,6 +912,7 @@ int32_t dmt_swap(dmt_ctx *ctx, int32_t layout, int32_t what, const uint8_t *chai
         if (what & DMT_SWAP_PP) {
             check_law_side(ctx, 1);
             invalidate_caches(ctx); // the accepted laws are now the former proposals (their guiding term is in the shared store)
+            if (chain_mask) ctx->parP_mixed = true;
             swap_laws_kernel<<<pset_grid(ctx, L.nb, 128), 128, 0, ctx->stream>>>(ctx->dev, L.dev, dm);
         }
         CK(cudaGetLastError());

@@ -12,6 +12,30 @@
 
 namespace dmt {
 
+// ---- TMA bulk copy + mbarrier (sm_90+): the warp-contiguous 1 KiB chunk of one component of one tile, global -> shared
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *b, int cnt) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(cnt)); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(smem_u32(b)),
+                 "r"(parity) : "memory");
+}
+#ifndef DMT_HALF_TILE
+#define DMT_HALF_TILE 0 // measured: 3.61 vs 3.32 ms for the fused C3 pass (profiles/r01_tuning.md) => off
+#endif
+// 16-byte half of a lane's sector through L1: the first half-load brings the whole 32-byte sector into L1, the second one
+// (issued two steps later) hits there, so L2 still sees the sector once while only half of it is live in registers.
+__device__ __forceinline__ void ld128c(const double *p, double *v) {
+    asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(p));
+}
+constexpr int FWD_RING = 2; // tiles of H,F in flight per warp on the TMA path
+
 template <int NG> struct GTile { // where the guiding term of interval k lives for this thread's pset / law side
     const double *base;          // tile 0, component 0, this pset
     const double *c0;            // c at the interval start, this pset
@@ -49,7 +73,13 @@ template <class MD> constexpr int fwd_minb() { return DMT_FWD_MINB > 0 ? DMT_FWD
 //   OP_SWEEP       find_W_for_X!(b); loglikhd!(b); draw_proposal_path!(bb) of the blocking sweep
 //                  (docs/src/tutorials/block_collection/inference_with_blocking.md:55-57) in ONE pass over the tiles: the
 //                  accepted noise recovered by K5 feeds the pCN refresh in registers (168 instead of 264 B per step).
-template <class MD, int OP, int TPB>
+//
+// TMA = true is the fast path for the common case (one pset per chain in chain order, uniform law parity): the widest stream,
+// H and F, does not go through registers at load time — per warp, lane 0 copies the NEXT tile's warp-contiguous chunks
+// (NG x 1 KiB) global -> shared with cp.async.bulk while the warp works on the current tile (2-stage ring, one mbarrier per
+// stage, no block barrier).  Measured on the memory pattern alone (profiles/r01_stream_pattern.txt): 6.3 TB/s instead of
+// 5.4 TB/s at C3's 41k threads.  All lanes of a warp stay in the loops on this path (a failed chain idles, it does not exit).
+template <class MD, int OP, int TPB, bool TMA>
 __global__ void DMT_FWD_BOUNDS fwd_kernel(const DevCtx cx, const LayoutDev ly, const FwdArgs fa) {
     constexpr int D = MD::D, DW = MD::DW, NPAR = MD::NPAR, NH = D * (D + 1) / 2, NG = NH + D, NAUX = D * D + D + NH;
     constexpr bool SWEEP = (OP == OP_SWEEP);
@@ -61,11 +91,17 @@ __global__ void DMT_FWD_BOUNDS fwd_kernel(const DevCtx cx, const LayoutDev ly, c
     constexpr bool WANT_LL = (OP != OP_INVSOLVE);
     constexpr bool RNG = (OP == OP_DRAW || OP == OP_INIT || SWEEP);
 
-    const int c = blockIdx.x * TPB + threadIdx.x;
+    const int c_raw = blockIdx.x * TPB + threadIdx.x;
     const int b = blockIdx.y;
-    if (c >= cx.M) return;
+    if (!TMA && c_raw >= cx.M) return;
+    if (TMA && (c_raw & ~31) >= cx.M) return;          // the whole warp lies beyond the ensemble (uniform exit)
+    const int c = TMA ? min(c_raw, cx.M - 1) : c_raw;  // TMA: lanes without a chain shadow the last one and never store
     const size_t M = cx.M, P = cx.P;
-    if (OP == OP_INIT && ly.ok[(size_t)b * M + c]) return; // retry only the chains that failed so far
+    bool live = c_raw < cx.M;
+    if (OP == OP_INIT && ly.ok[(size_t)b * M + c]) { // retry only the chains that failed so far
+        if (!TMA) return;
+        live = false;
+    }
     const int ps = cx.pset[c];
     const int i0 = ly.i0[b], i1 = ly.i1[b];
     const bool last = ly.last[b] != 0;
@@ -94,7 +130,46 @@ __global__ void DMT_FWD_BOUNDS fwd_kernel(const DevCtx cx, const LayoutDev ly, c
     double ll = 0.0, llo = 0.0;
     bool ok = true;
 
-    for (int k = i0; k <= i1 && (ok || SWEEP); ++k) {
+    // ---- TMA ring state (fast path only)
+    extern __shared__ __align__(128) unsigned char fwd_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double *ring = reinterpret_cast<double *>(fwd_smem) + (size_t)wid * FWD_RING * NG * 128;          // [stage][component][lane][4]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(fwd_smem + (size_t)(TPB / 32) * FWD_RING * NG * 1024) + wid * FWD_RING;
+    int kp = i0, qp = 0, ntl_p = 0, n_prod = 0, n_cons = 0; // producer cursor (interval, tile), tiles produced / consumed
+    const double *gp_p = nullptr;
+    uint32_t chunk_bytes = 0;
+    if (TMA) {
+        chunk_bytes = 32u * (uint32_t)min(32, cx.M - (c_raw & ~31));
+        if (lane == 0)
+            for (int s = 0; s < FWD_RING; s++) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncwarp();
+        gp_p = g_tile_of<NG>(cx, ly, kp, i1, last, law_side, ps).base;
+        ntl_p = (cx.nsteps[kp] + 3) >> 2;
+    }
+    auto produce = [&]() { // every lane advances the cursor; lane 0 (always a real chain) issues the copies of its warp's chunk
+        if (kp > i1) return;
+        if (lane == 0) {
+            uint64_t *bar = &bars[n_prod % FWD_RING];
+            mbar_expect_tx(bar, NG * chunk_bytes);
+            double *dst = ring + (size_t)(n_prod % FWD_RING) * NG * 128;
+#pragma unroll
+            for (int a = 0; a < NG; a++) bulk_g2s(dst + a * 128, gp_p + ((size_t)qp * NG + a) * gstr, chunk_bytes, bar);
+        }
+        n_prod++;
+        if (++qp == ntl_p) {
+            qp = 0;
+            if (++kp <= i1) {
+                gp_p = g_tile_of<NG>(cx, ly, kp, i1, last, law_side, ps).base;
+                ntl_p = (cx.nsteps[kp] + 3) >> 2;
+            }
+        }
+    };
+    if (TMA) {
+        for (int s = 0; s < FWD_RING - 1; s++) produce();
+    }
+
+    for (int k = i0; k <= i1 && (ok || SWEEP || TMA); ++k) {
         const GTile<NG> gt = g_tile_of<NG>(cx, ly, k, i1, last, law_side, ps);
         const int store = gt.store, slotL = gt.slot;
         const double *Gp = gt.base;
@@ -129,7 +204,7 @@ __global__ void DMT_FWD_BOUNDS fwd_kernel(const DevCtx cx, const LayoutDev ly, c
 #pragma unroll
             for (int i = 0; i < D; i++) x[i] = cx.X0[(size_t)(xin_side ^ px) * cx.X0buf + ((size_t)k * D + i) * M + c];
         }
-        if (WRITES_X || SWEEP) { // XX°[k].x[1] = y1
+        if ((WRITES_X || SWEEP) && live) { // XX°[k].x[1] = y1
             double *x0p = cx.X0 + (size_t)(xout_side ^ px) * cx.X0buf + (size_t)k * D * M + c;
 #pragma unroll
             for (int i = 0; i < D; i++) x0p[(size_t)i * M] = SWEEP ? xo[i] : x[i];
@@ -144,11 +219,21 @@ __global__ void DMT_FWD_BOUNDS fwd_kernel(const DevCtx cx, const LayoutDev ly, c
 #pragma unroll
                 for (int j = 0; j < DW; j++) ld256(Win + ((size_t)q * DW + j) * M * 4, w[j]);
             }
+            if (TMA) produce(); // keep the copy engine FWD_RING-1 tiles ahead (the stage it refills was drained last iteration)
+            constexpr bool HALF = (DMT_HALF_TILE != 0) && !TMA; // inputs in two 16-byte halves (second half right before step 2)
+            if (!TMA) {
 #pragma unroll
-            for (int a = 0; a < NG; a++) ld256(Gp + ((size_t)q * NG + a) * gstr, g[a]);
+                for (int a = 0; a < NG; a++) {
+                    if (HALF) ld128c(Gp + ((size_t)q * NG + a) * gstr, g[a]);
+                    else ld256(Gp + ((size_t)q * NG + a) * gstr, g[a]);
+                }
+            }
             if (READS_X) {
 #pragma unroll
-                for (int i = 0; i < D; i++) ld256(Xin + ((size_t)q * D + i) * M * 4, xt[i]);
+                for (int i = 0; i < D; i++) {
+                    if (HALF) ld128c(Xin + ((size_t)q * D + i) * M * 4, xt[i]);
+                    else ld256(Xin + ((size_t)q * D + i) * M * 4, xt[i]);
+                }
             }
             ld256u(cx.dt + (size_t)(t0 + q) * 4, dt4);
             if (RNG) ld256u(cx.sqdt + (size_t)(t0 + q) * 4, sq4);
@@ -178,11 +263,24 @@ __global__ void DMT_FWD_BOUNDS fwd_kernel(const DevCtx cx, const LayoutDev ly, c
                             if (OP == OP_DRAW) w[j][s] = rho * w[j][s] + crho * sq4[s] * z[s * DW + j];
                             else w[j][s] = sq4[s] * z[s * DW + j];
                         }
+                    if (live) {
 #pragma unroll
-                    for (int j = 0; j < DW; j++) st256(Wout + ((size_t)q * DW + j) * M * 4, w[j]); // final: stream out now
+                        for (int j = 0; j < DW; j++) st256(Wout + ((size_t)q * DW + j) * M * 4, w[j]); // final: stream out now
+                    }
                 }
             }
 
+            if (TMA) { // this tile's H,F have landed in shared memory: each lane takes its own sectors
+                mbar_wait(&bars[n_cons % FWD_RING], (uint32_t)(n_cons / FWD_RING) & 1u);
+                const double *sg = ring + (size_t)(n_cons % FWD_RING) * NG * 128 + lane * 4;
+#pragma unroll
+                for (int a = 0; a < NG; a++) {
+                    const double2 u = *reinterpret_cast<const double2 *>(sg + a * 128), v2 = *reinterpret_cast<const double2 *>(sg + a * 128 + 2);
+                    g[a][0] = u.x; g[a][1] = u.y; g[a][2] = v2.x; g[a][3] = v2.y;
+                }
+                n_cons++;
+                __syncwarp(); // all lanes have read: the stage may be refilled by the next produce()
+            }
             if (WANT_LL && k == i0 && q == 0) { // loglikhd_obs(PP[1], y1) = -c - y'Hy/2 + F'y  (src/block.jl:178)
                 double s0 = -*gt.c0;
 #pragma unroll
@@ -198,6 +296,14 @@ __global__ void DMT_FWD_BOUNDS fwd_kernel(const DevCtx cx, const LayoutDev ly, c
 #pragma unroll
             for (int s = 0; s < 4; s++) {
                 const int i = 4 * q + s;
+                if (HALF && s == 2) { // second halves of the input sectors: L1 hits
+#pragma unroll
+                    for (int a = 0; a < NG; a++) ld128c(Gp + ((size_t)q * NG + a) * gstr + 2, g[a] + 2);
+                    if (READS_X) {
+#pragma unroll
+                        for (int a = 0; a < D; a++) ld128c(Xin + ((size_t)q * D + a) * M * 4 + 2, xt[a] + 2);
+                    }
+                }
                 if (i < nst && (ok || SWEEP)) {
                     double Hs[NH], F[D], gd[D], G = 0.0;
 #pragma unroll
@@ -280,28 +386,30 @@ __global__ void DMT_FWD_BOUNDS fwd_kernel(const DevCtx cx, const LayoutDev ly, c
                     }
                 }
             }
-            if (WRITES_W && (!RNG || SWEEP)) {
+            if (WRITES_W && (!RNG || SWEEP) && live) {
 #pragma unroll
                 for (int j = 0; j < DW; j++) st256(Wout + ((size_t)q * DW + j) * M * 4, w[j]);
             }
-            if (SWEEP) {
+            if (SWEEP && live) {
 #pragma unroll
                 for (int j = 0; j < DW; j++) st256(Wprop + ((size_t)q * DW + j) * M * 4, wo[j]);
 #pragma unroll
                 for (int i = 0; i < D; i++) st256(Xout + ((size_t)q * D + i) * M * 4, xot[i]);
             }
-            if (WRITES_X) {
+            if (WRITES_X && live) {
 #pragma unroll
                 for (int i = 0; i < D; i++) st256(Xout + ((size_t)q * D + i) * M * 4, xt[i]);
             }
-            if (!ok && !SWEEP) break;
+            if (!ok && !SWEEP && !TMA) break;
         }
     }
-    if (WANT_LL) ly.ll[((size_t)ll_side * ly.nb + b) * M + c] = ll;
-    if (SWEEP) ly.ll[((size_t)ly.nb + b) * M + c] = llo;
-    if (WRITES_X || SWEEP) ly.ok[(size_t)b * M + c] = ok ? 1 : 0;
+    if (WANT_LL && live) ly.ll[((size_t)ll_side * ly.nb + b) * M + c] = ll;
+    if (SWEEP && live) ly.ll[((size_t)ly.nb + b) * M + c] = llo;
+    if ((WRITES_X || SWEEP) && live) ly.ok[(size_t)b * M + c] = ok ? 1 : 0;
 }
 
-template <class MD, int TPB> constexpr size_t fwd_smem_bytes() { return 0; }
+template <class MD, int TPB, bool TMA> constexpr size_t fwd_smem_bytes() {
+    return TMA ? (size_t)(TPB / 32) * FWD_RING * (MD::D * (MD::D + 1) / 2 + MD::D) * 1024 + (size_t)(TPB / 32) * FWD_RING * 8 : 0;
+}
 
 } // namespace dmt

@@ -95,6 +95,68 @@ __global__ void k_seq_cp(const double *G, const double *Win, double *Wout, doubl
     cp_wait<0>();
 }
 
+// ---- TMA variant: the warp's H,F (and W) chunks are contiguous (32 lanes x 32 B = 1 KiB per component): one elected lane
+// copies them global -> shared with cp.async.bulk (full-line L2 access, no registers), S tiles ahead, per-warp mbarriers.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *b, int cnt) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(cnt)); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(smem_u32(b)),
+                 "r"(parity) : "memory");
+}
+template <int S, int WPB, bool W_TMA>
+__global__ void __launch_bounds__(WPB * 32) k_seq_tma(const double *G, const double *Win, double *Wout, double *Xout, int M, int len) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    constexpr int NC = W_TMA ? NG + DW : NG;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double *ring = reinterpret_cast<double *>(smraw) + (size_t)wid * S * NC * 128; // [stage][comp][lane][4]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smraw + (size_t)WPB * S * NC * 1024) + wid * S;
+    const int c0 = (blockIdx.x * WPB + wid) * 32, c = c0 + lane, b = blockIdx.y;
+    if (c0 >= M) return;
+    if (lane == 0) for (int s = 0; s < S; s++) mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    auto issue = [&](size_t t, int st) {
+        if (lane == 0) {
+            mbar_expect_tx(&bars[st], NC * 1024);
+            for (int a = 0; a < NG; a++) bulk_g2s(ring + ((size_t)st * NC + a) * 128, G + ((t * NG + a) * M + c0) * 4, 1024, &bars[st]);
+            if (W_TMA) for (int j = 0; j < DW; j++) bulk_g2s(ring + ((size_t)st * NC + NG + j) * 128, Win + ((t * DW + j) * M + c0) * 4, 1024, &bars[st]);
+        }
+    };
+    for (int p = 0; p < S - 1 && p < len; p++) issue((size_t)b * len + p, p);
+    double carry = 0;
+    for (int q = 0; q < len; q++) {
+        const size_t t = (size_t)b * len + q;
+        if (q + S - 1 < len) issue(t + S - 1, (q + S - 1) % S); // that stage was drained in iteration q-1 (syncwarp below)
+        double w[DW][4];
+        if (!W_TMA) for (int j = 0; j < DW; j++) ld256(Win + ((t * DW + j) * M + c) * 4, w[j]);
+        mbar_wait(&bars[q % S], (q / S) & 1);
+        const double *sg = ring + (size_t)(q % S) * NC * 128 + lane * 4;
+        double acc[4] = {carry, carry, carry, carry};
+        for (int a = 0; a < NG; a++) {
+            const double2 u = *reinterpret_cast<const double2 *>(sg + a * 128), v = *reinterpret_cast<const double2 *>(sg + a * 128 + 2);
+            acc[0] += u.x; acc[1] += u.y; acc[2] += v.x; acc[3] += v.y;
+        }
+        if (W_TMA) for (int j = 0; j < DW; j++) {
+            const double2 u = *reinterpret_cast<const double2 *>(sg + (NG + j) * 128), v = *reinterpret_cast<const double2 *>(sg + (NG + j) * 128 + 2);
+            w[j][0] = u.x; w[j][1] = u.y; w[j][2] = v.x; w[j][3] = v.y;
+        }
+        __syncwarp(); // every lane has read its sectors of this stage: it may be refilled
+        for (int j = 0; j < DW; j++) {
+            for (int i = 0; i < 4; i++) w[j][i] += acc[i];
+            st256(Wout + ((t * DW + j) * M + c) * 4, w[j]);
+            st256(Xout + ((t * D + j) * M + c) * 4, w[j]);
+        }
+        carry = acc[3] * 1e-30;
+    }
+}
+
 template <class F> float timeit(F f, int reps = 5) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     f(); CK(cudaDeviceSynchronize());
@@ -123,6 +185,15 @@ int main(int argc, char **argv) {
         snprintf(nm, 96, "seq cp.async S=2  blocks=%3d", nb);
         CK(cudaFuncSetAttribute(k_seq_cp<2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 12 * 2 * 64 * 16));
         rep(nm, timeit([&] { k_seq_cp<2, 64><<<dim3((M + 63) / 64, nb), 64, 2 * 12 * 2 * 64 * 16>>>(G, Wi, Wo, Xo, M, len); }));
+#define RUN_TMA(S_, W_)                                                                                                   \
+    {                                                                                                                    \
+        constexpr int NCc = (W_) ? NG + DW : NG;                                                                         \
+        const int smem = 2 * (S_) * NCc * 1024 + 2 * (S_) * 8;                                                           \
+        CK(cudaFuncSetAttribute(k_seq_tma<S_, 2, W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));               \
+        snprintf(nm, 96, "seq TMA ring S=%d %s blocks=%3d", S_, (W_) ? "G+W" : "G  ", nb);                                \
+        rep(nm, timeit([&] { k_seq_tma<S_, 2, W_><<<dim3((M + 63) / 64, nb), 64, smem>>>(G, Wi, Wo, Xo, M, len); }));     \
+    }
+        RUN_TMA(2, false) RUN_TMA(3, false) RUN_TMA(4, false) RUN_TMA(3, true) RUN_TMA(4, true)
         snprintf(nm, 96, "seq cp.async S=4  blocks=%3d", nb);
         CK(cudaFuncSetAttribute(k_seq_cp<4, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 12 * 2 * 64 * 16));
         rep(nm, timeit([&] { k_seq_cp<4, 64><<<dim3((M + 63) / 64, nb), 64, 4 * 12 * 2 * 64 * 16>>>(G, Wi, Wo, Xo, M, len); }));
