@@ -270,16 +270,11 @@ __global__ void DMT_FWD_BOUNDS fwd_kernel(const DevCtx cx, const LayoutDev ly, c
                 }
             }
 
-            if (TMA) { // this tile's H,F have landed in shared memory: each lane takes its own sectors
+            const double *sg = nullptr; // TMA: this lane's sectors of the current tile in the shared-memory ring
+            if (TMA) {                  // the tile's H,F have landed; the step loop reads them in place (no register copy)
                 mbar_wait(&bars[n_cons % FWD_RING], (uint32_t)(n_cons / FWD_RING) & 1u);
-                const double *sg = ring + (size_t)(n_cons % FWD_RING) * NG * 128 + lane * 4;
-#pragma unroll
-                for (int a = 0; a < NG; a++) {
-                    const double2 u = *reinterpret_cast<const double2 *>(sg + a * 128), v2 = *reinterpret_cast<const double2 *>(sg + a * 128 + 2);
-                    g[a][0] = u.x; g[a][1] = u.y; g[a][2] = v2.x; g[a][3] = v2.y;
-                }
+                sg = ring + (size_t)(n_cons % FWD_RING) * NG * 128 + lane * 4;
                 n_cons++;
-                __syncwarp(); // all lanes have read: the stage may be refilled by the next produce()
             }
             if (WANT_LL && k == i0 && q == 0) { // loglikhd_obs(PP[1], y1) = -c - y'Hy/2 + F'y  (src/block.jl:178)
                 double s0 = -*gt.c0;
@@ -287,8 +282,8 @@ __global__ void DMT_FWD_BOUNDS fwd_kernel(const DevCtx cx, const LayoutDev ly, c
                 for (int i = 0; i < D; i++) {
                     double hx = 0.0;
 #pragma unroll
-                    for (int j = 0; j < D; j++) hx = fma(g[sidx<D>(i, j)][0], x[j], hx);
-                    s0 += x[i] * (g[NH + i][0] - 0.5 * hx);
+                    for (int j = 0; j < D; j++) hx = fma(TMA ? sg[sidx<D>(i, j) * 128] : g[sidx<D>(i, j)][0], x[j], hx);
+                    s0 += x[i] * ((TMA ? sg[(NH + i) * 128] : g[NH + i][0]) - 0.5 * hx);
                 }
                 ll = s0;
                 llo = s0; // same law, same start point
@@ -307,9 +302,9 @@ __global__ void DMT_FWD_BOUNDS fwd_kernel(const DevCtx cx, const LayoutDev ly, c
                 if (i < nst && (ok || SWEEP)) {
                     double Hs[NH], F[D], gd[D], G = 0.0;
 #pragma unroll
-                    for (int a = 0; a < NH; a++) Hs[a] = g[a][s];
+                    for (int a = 0; a < NH; a++) Hs[a] = TMA ? sg[a * 128 + s] : g[a][s];
 #pragma unroll
-                    for (int a = 0; a < D; a++) F[a] = g[NH + a][s];
+                    for (int a = 0; a < D; a++) F[a] = TMA ? sg[(NH + a) * 128 + s] : g[NH + a][s];
                     const typename MD::Diff df(par, x);
 #if defined(DMT_EXP_NOEM) // (experiment only: time the kernel without the drift / guiding arithmetic)
 #pragma unroll
@@ -400,6 +395,7 @@ __global__ void DMT_FWD_BOUNDS fwd_kernel(const DevCtx cx, const LayoutDev ly, c
 #pragma unroll
                 for (int i = 0; i < D; i++) st256(Xout + ((size_t)q * D + i) * M * 4, xt[i]);
             }
+            if (TMA) __syncwarp(); // every lane is done with this stage: the next produce() may refill it
             if (!ok && !SWEEP && !TMA) break;
         }
     }
