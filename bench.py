@@ -289,6 +289,14 @@ def gpu_arm(a):
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "algorithmic_bytes_per_unit": bpu, "units_per_launch": prob.M * prob.steps_per_chain, "launch_ms": kern_ms[kname]}
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel, from the committed `ncu --set full` capture
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        ent = tr.get(roofline["kernel"])
+        if ent and ent.get("units_per_launch") == roofline["units_per_launch"]:
+            roofline["traffic"] = ent["dram_bytes_per_launch"]
+            roofline["traffic_source"] = ent["source"]
+    except Exception:
+        pass
     if blocking:  # the whole sweep also moves the K1 write and the K5+K4 pass (reported separately)
         d, dw = prob.d, prob.dw
         nh = d * (d + 1) // 2

@@ -298,3 +298,28 @@ def set_proposal_law(be, theta_o, pnames, critical_change, skip=0):
         be.ctx.set_aux_linearised(se.xbar, side=_lib.PROPOSAL, store=_lib.STORE_PP)
         be.ctx.set_aux_linearised(se.xbar_blocking, side=_lib.PROPOSAL, store=_lib.STORE_PPB)
     be.ctx.set_proposal_law(be.layout, critical_change, skip)
+
+
+# ---- checkpoint / resume (not in the reference, which keeps its state in Julia objects) -------------
+def save_state(se, path, layouts=()):
+    """Everything needed to continue a run bit-exactly: accepted and proposal X and W (resolved through the parity bits), the
+    accepted parameters, and per layout the ll fields.  The counter-based generator needs no state beyond (seed, iteration)."""
+    ctx = se.ctx
+    d = dict(X0=ctx.get_X(0), X1=ctx.get_X(1), W0=ctx.get_W(0), W1=ctx.get_W(1), theta=se.theta, theta_o=se.theta_o,
+             n_pts=ctx.n_pts, tt=ctx.tt, chain_lo=se.chain_lo, chain_hi=se.chain_hi)
+    for be in layouts:
+        d["ll0_%d" % be.layout] = ctx.get_ll(be.layout, 0)
+        d["ll1_%d" % be.layout] = ctx.get_ll(be.layout, 1)
+    np.savez_compressed(path, **d)
+
+
+def load_state(se, path, layouts=()):
+    """Restore a state written by save_state into an ensemble built with the same recordings, grids, seed and layouts."""
+    z = np.load(path)
+    ctx = se.ctx
+    if not (np.array_equal(z["n_pts"], ctx.n_pts) and np.array_equal(z["tt"], ctx.tt) and int(z["chain_lo"]) == se.chain_lo and int(z["chain_hi"]) == se.chain_hi):
+        raise ValueError("checkpoint belongs to a different ensemble (grid or chain slice differ)")
+    ctx.set_X(z["X0"], 0); ctx.set_X(z["X1"], 1); ctx.set_W(z["W0"], 0); ctx.set_W(z["W1"], 1)
+    for be in layouts:
+        ctx.set_ll(be.layout, z["ll0_%d" % be.layout], 0)
+        ctx.set_ll(be.layout, z["ll1_%d" % be.layout], 1)

@@ -158,6 +158,14 @@ GP.recompute_guiding_term!(be::DBE, ::Val{:P_only}) = _rgt(be, 1)
 GP.recompute_guiding_term!(be::DBE, ::Val{:P°_only}) = _rgt(be, 2)
 find_W_for_X!(be::DBE) = check(be.se.ctx, ccall((:dmt_find_W_for_X, libdmt), Int32, (Ptr{Cvoid}, Int32), be.se.ctx, be.layout))
 
+# ---- the blocking step of docs/src/tutorials/block_collection/inference_with_blocking.md as one call:
+# set_obs!; recompute_guiding_term!(Val(:P_only)); find_W_for_X!; loglikhd!; draw_proposal_path!
+blocking_sweep!(be::DBE, mcmciter::Integer) =
+    check(be.se.ctx, ccall((:dmt_blocking_sweep, libdmt), Int32, (Ptr{Cvoid}, Int32, UInt32), be.se.ctx, be.layout, mcmciter - 1))
+# while θ, the auxiliary laws and the real observations stay fixed, K1 after set_obs! is F = F⁰ + Ψv (exact); see include/dmt.h
+enable_guiding_cache!(be::DBE, on::Bool=true) =
+    check(be.se.ctx, ccall((:dmt_enable_guiding_cache, libdmt), Int32, (Ptr{Cvoid}, Int32, Int32), be.se.ctx, be.layout, on))
+
 # ---- parameters (src/block_ensemble.jl:242-255 -> src/biblock.jl:334-371).  The name translation of
 # src/param_names_collections.jl stays here on the host: `pnames` is its result for the target law,
 # a vector of (index into θ°) => (index into the model's parameter vector) pairs.

@@ -125,3 +125,35 @@ def test_inference_tutorial_parameter_update(orc, olib):
         assert np.allclose(se.theta[2], gamma)
         assert rel_err(se.ctx.get_X(0), ora.X(0)) < 1e-9 and rel_err(se.ctx.get_ll(be.layout, 0), ora.ll(0, 0)) < 1e-9
     se.ctx.close()
+
+
+def test_checkpoint_resume_is_bit_exact(tmp_path):
+    """save_state / load_state: a resumed run continues exactly like the uninterrupted one"""
+    K = 8
+    layouts = [([(0, 2), (3, 5), (6, 7)], 0.8), ([(0, 3), (4, 7)], 0.7)]
+    prob = configs.make_problem("lorenz", 40, K=K, dt=0.01, seed=9, layouts=layouts)
+
+    def fresh():
+        se = H.SamplingEnsemble(prob.model, recordings_of(prob), (prob.n_pts, prob.tt), seed=5, two_sided_laws=False)
+        se.init_paths()
+        return se, [H.BlockEnsemble(se, r, rho, 0) for r, rho in layouts]
+
+    def sweeps(bes, its):
+        for i in its:
+            for be in bes:
+                H.blocking_sweep(be, i)
+                H.accept_reject_proposal_path(be, i)
+
+    se, bes = fresh()
+    sweeps(bes, range(3))
+    ck = str(tmp_path / "state.npz")
+    H.save_state(se, ck, bes)
+    sweeps(bes, range(3, 6))
+    Xa, Wa, lla = se.ctx.get_X(0), se.ctx.get_W(0), [se.ctx.get_ll(be.layout, 0) for be in bes]
+    se.ctx.close()
+    se2, bes2 = fresh()
+    H.load_state(se2, ck, bes2)
+    sweeps(bes2, range(3, 6))
+    assert np.array_equal(se2.ctx.get_X(0), Xa) and np.array_equal(se2.ctx.get_W(0), Wa)
+    assert all(np.array_equal(se2.ctx.get_ll(be.layout, 0), l) for be, l in zip(bes2, lla))
+    se2.ctx.close()
