@@ -9,6 +9,9 @@
 // recursion starts so the stores overlap the arithmetic.
 #pragma once
 #include "kernels.cuh"
+#ifdef DMT_EXP_CLK
+#include <cstdio>
+#endif
 
 namespace dmt {
 
@@ -129,6 +132,13 @@ __global__ void DMT_FWD_BOUNDS fwd_kernel(const DevCtx cx, const LayoutDev ly, c
     }
     double ll = 0.0, llo = 0.0;
     bool ok = true;
+#ifdef DMT_EXP_CLK // (experiment only: per-thread cycle breakdown of a tile: issue+RNG | wait+step 0 | steps 1-3 | stores)
+    long long clk_acc[4] = {0, 0, 0, 0}, ck0 = 0, ck1 = 0, ck2 = 0, ck3 = 0;
+    int clk_n = 0;
+#define DMT_CLK(v) v = clock64()
+#else
+#define DMT_CLK(v)
+#endif
 
     // ---- TMA ring state (fast path only)
     extern __shared__ __align__(128) unsigned char fwd_smem[];
@@ -214,6 +224,7 @@ __global__ void DMT_FWD_BOUNDS fwd_kernel(const DevCtx cx, const LayoutDev ly, c
         for (int q = 0; q < ntl; ++q) {
             double g[NG][4], w[DW][4], xt[D][4], dt4[4], sq4[4];
             double wo[SWEEP ? DW : 1][4], xot[SWEEP ? D : 1][4], z[RNG ? 4 * DW : 1];
+            DMT_CLK(ck0);
             // ---- every sector of the tile, once, straight into registers
             if (READS_W) {
 #pragma unroll
@@ -270,6 +281,7 @@ __global__ void DMT_FWD_BOUNDS fwd_kernel(const DevCtx cx, const LayoutDev ly, c
                 }
             }
 
+            DMT_CLK(ck1);
             const double *sg = nullptr; // TMA: this lane's sectors of the current tile in the shared-memory ring
             if (TMA) {                  // the tile's H,F have landed; the step loop reads them in place (no register copy)
                 mbar_wait(&bars[n_cons % FWD_RING], (uint32_t)(n_cons / FWD_RING) & 1u);
@@ -291,6 +303,7 @@ __global__ void DMT_FWD_BOUNDS fwd_kernel(const DevCtx cx, const LayoutDev ly, c
 #pragma unroll
             for (int s = 0; s < 4; s++) {
                 const int i = 4 * q + s;
+                if (s == 1) { DMT_CLK(ck2); }
                 if (HALF && s == 2) { // second halves of the input sectors: L1 hits
 #pragma unroll
                     for (int a = 0; a < NG; a++) ld128c(Gp + ((size_t)q * NG + a) * gstr + 2, g[a] + 2);
@@ -381,6 +394,7 @@ __global__ void DMT_FWD_BOUNDS fwd_kernel(const DevCtx cx, const LayoutDev ly, c
                     }
                 }
             }
+            DMT_CLK(ck3);
             if (WRITES_W && (!RNG || SWEEP) && live) {
 #pragma unroll
                 for (int j = 0; j < DW; j++) st256(Wout + ((size_t)q * DW + j) * M * 4, w[j]);
@@ -395,10 +409,18 @@ __global__ void DMT_FWD_BOUNDS fwd_kernel(const DevCtx cx, const LayoutDev ly, c
 #pragma unroll
                 for (int i = 0; i < D; i++) st256(Xout + ((size_t)q * D + i) * M * 4, xt[i]);
             }
+#ifdef DMT_EXP_CLK
+            { long long ck4 = clock64(); clk_acc[0] += ck1 - ck0; clk_acc[1] += ck2 - ck1; clk_acc[2] += ck3 - ck2; clk_acc[3] += ck4 - ck3; clk_n++; }
+#endif
             if (TMA) __syncwarp(); // every lane is done with this stage: the next produce() may refill it
             if (!ok && !SWEEP && !TMA) break;
         }
     }
+#ifdef DMT_EXP_CLK
+    if (SWEEP && (c % 1024) == 37 && (b == 2 || b == 7) && fa.iter == 9)
+        printf("CLK c=%d b=%d tiles=%d  issue+rng %lld  wait+step0 %lld  steps1-3 %lld  stores %lld (cycles per tile)\n", c, b, clk_n, clk_acc[0] / clk_n,
+               clk_acc[1] / clk_n, clk_acc[2] / clk_n, clk_acc[3] / clk_n);
+#endif
     if (WANT_LL && live) ly.ll[((size_t)ll_side * ly.nb + b) * M + c] = ll;
     if (SWEEP && live) ly.ll[((size_t)ly.nb + b) * M + c] = llo;
     if ((WRITES_X || SWEEP) && live) ly.ok[(size_t)b * M + c] = ok ? 1 : 0;
