@@ -2,7 +2,9 @@
 
 The directory name carries a dot, so import it through the shim at the repo root:  `import dmt_b200`.
 """
-from . import _lib, configs, host  # noqa: F401
+from . import _lib, configs, host, param_names, hetero  # noqa: F401
+from .hetero import HeterogeneousBlockEnsemble, HeterogeneousEnsemble  # noqa: F401
+from .param_names import ParamNamesAllObs, ParamNamesBlock, ParamNamesRecording, ParamNamesUnit  # noqa: F401
 from ._lib import Ctx, DmtError  # noqa: F401
 from .host import (BlockEnsemble, SamplingEnsemble, accept_reject_proposal_path, accpt_rate, draw_proposal_path,  # noqa: F401
                    fetch_ll, fetch_ll_o, find_W_for_X, ll_of_accepted, loglikhd, loglikhd_o, recompute_guiding_term, save_ll,

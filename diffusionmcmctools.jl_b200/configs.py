@@ -222,6 +222,10 @@ def named_config(cfg, M=None, seed=0, chain_offset=0, P=None):
         return make_problem("fhn", M or 1, P, seed=seed, rho=0.96, chain_offset=chain_offset)
     if cfg == "c2":
         return make_problem("lv", M or 1024, P, seed=seed, rho=0.9, chain_offset=chain_offset)
+    if cfg == "c3" and P is not None and P != (M or 4096):
+        # shared data / shared guiding term (SURVEY §8d "report both P=1 and P=M"): blocking freezes a per-recording artificial
+        # observation, so the P < M variant is the single terminal block 1:200 with the same pCN rho
+        return make_problem("lorenz", M or 4096, P, seed=seed, rho=0.9, chain_offset=chain_offset)
     if cfg == "c3":
         return make_problem("lorenz", M or 4096, P, seed=seed, layouts=blocking_layouts(200, 20, 0.9), chain_offset=chain_offset)
     if cfg == "c4":

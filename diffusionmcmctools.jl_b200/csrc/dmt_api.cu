@@ -177,16 +177,52 @@ void check_range(dmt_ctx *c, int k0, int k1) { REQUIRE(0 <= k0 && k0 <= k1 && k1
 dim3 chain_grid(dmt_ctx *c, int ny, int tpb) { return dim3((c->M + tpb - 1) / tpb, ny, 1); }
 dim3 pset_grid(dmt_ctx *c, int ny, int tpb, int nz = 1) { return dim3((c->P + tpb - 1) / tpb, ny, nz); }
 
-template <class MD, int OP, bool TMA> void launch_fwd_variant(dmt_ctx *c, Layout &L, const FwdArgs &fa) {
+template <class MD, int OP, bool TMA, int G> void launch_fwd_lanes(dmt_ctx *c, Layout &L, const FwdArgs &fa, int *wave_threads) {
     constexpr int TPB = (MD::D >= 6) ? 32 : FWD_TPB; // wide guiding terms: smaller CTAs
     constexpr size_t smem = fwd_smem_bytes<MD, TPB, TMA>();
     static bool attr_done[64] = {};
+    static int wave[64] = {};
     const int dev = c->cfg.device & 63;
     if (!attr_done[dev]) {
-        CK(cudaFuncSetAttribute(fwd_kernel<MD, OP, TPB, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(fwd_kernel<MD, OP, TPB, TMA, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0, sms = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fwd_kernel<MD, OP, TPB, TMA, G>, TPB, smem));
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->cfg.device));
+        wave[dev] = per_sm * sms * TPB; // threads resident at once
         attr_done[dev] = true;
     }
-    fwd_kernel<MD, OP, TPB, TMA><<<chain_grid(c, L.nb, TPB), TPB, smem, c->stream>>>(c->dev, L.dev, fa);
+    if (wave_threads) { *wave_threads = wave[dev]; return; } // query only
+    const dim3 grid((unsigned)(((size_t)c->M * G + TPB - 1) / TPB), L.nb, 1);
+    fwd_kernel<MD, OP, TPB, TMA, G><<<grid, TPB, smem, c->stream>>>(c->dev, L.dev, fa);
+}
+// Lanes per (chain, block): 1 when the ensemble fills the GPU by itself; 2, 4 or 8 when M x blocks x lanes still fits one wave
+// of the cooperative instantiation (the generator is split over the lanes, fwd_kernel.cuh).  DMT_FWD_LANES overrides.
+template <class MD, int OP, bool TMA> void launch_fwd_variant(dmt_ctx *c, Layout &L, const FwdArgs &fa) {
+    constexpr bool COOP_OK = !TMA && (OP == OP_DRAW || OP == OP_INIT || OP == OP_SWEEP);
+    int lanes = 1;
+    if (COOP_OK) {
+        static int forced = -1;
+        if (forced < 0) { const char *e = getenv("DMT_FWD_LANES"); forced = e ? atoi(e) : 0; }
+        const size_t units = (size_t)c->M * L.nb;
+        int w = 0;
+        if (forced) lanes = forced;
+        else {
+            launch_fwd_lanes<MD, OP, false, 8>(c, L, fa, &w);
+            if (units * 8 <= (size_t)w) lanes = 8;
+            else {
+                launch_fwd_lanes<MD, OP, false, 4>(c, L, fa, &w);
+                if (units * 4 <= (size_t)w) lanes = 4;
+                else {
+                    launch_fwd_lanes<MD, OP, false, 2>(c, L, fa, &w);
+                    if (units * 2 <= (size_t)w) lanes = 2;
+                }
+            }
+        }
+    }
+    if (COOP_OK && lanes == 8) launch_fwd_lanes<MD, OP, false, COOP_OK ? 8 : 1>(c, L, fa, nullptr);
+    else if (COOP_OK && lanes == 4) launch_fwd_lanes<MD, OP, false, COOP_OK ? 4 : 1>(c, L, fa, nullptr);
+    else if (COOP_OK && lanes == 2) launch_fwd_lanes<MD, OP, false, COOP_OK ? 2 : 1>(c, L, fa, nullptr);
+    else launch_fwd_lanes<MD, OP, TMA, 1>(c, L, fa, nullptr);
 }
 template <class MD, int OP> void launch_fwd_model(dmt_ctx *c, Layout &L, const FwdArgs &fa) {
 #ifdef DMT_WITH_TMA

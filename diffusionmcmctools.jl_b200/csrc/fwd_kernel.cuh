@@ -60,11 +60,12 @@ __device__ __forceinline__ GTile<NG> g_tile_of(const DevCtx &cx, const LayoutDev
 // Register budget (profiles/r01_tuning.md): with <= 45k (chain, block) threads per GPU the kernel is latency bound, and having
 // EVERY CTA resident in one wave matters more than avoiding spills: d <= 3 models are capped at 168 registers
 // (6 CTAs of 64 threads per SM), the wider ones keep the full budget.
-template <class MD> constexpr int fwd_minb() { return DMT_FWD_MINB > 0 ? DMT_FWD_MINB : (MD::D <= 3 ? 6 : 1); }
+// The cooperative instantiations (G > 1) only run when the GPU is far from full: no cap, no spills.
+template <class MD, int G = 1> constexpr int fwd_minb() { return G > 1 ? 1 : (DMT_FWD_MINB > 0 ? DMT_FWD_MINB : (MD::D <= 3 ? 6 : 1)); }
 #ifdef DMT_FWD_MAXREG
 #define DMT_FWD_BOUNDS __maxnreg__(DMT_FWD_MAXREG)
 #else
-#define DMT_FWD_BOUNDS __launch_bounds__(TPB, fwd_minb<MD>())
+#define DMT_FWD_BOUNDS __launch_bounds__(TPB, fwd_minb<MD, G>())
 #endif
 // One thread = one (chain, block).  grid = (ceil(M/TPB), n_blocks).  Replaces, per OP:
 //   OP_DRAW        draw_proposal_path!(bb)            src/biblock.jl:80-106   (pCN + guided EM + ll, fused; K3+K2+K4)
@@ -82,7 +83,13 @@ template <class MD> constexpr int fwd_minb() { return DMT_FWD_MINB > 0 ? DMT_FWD
 // (NG x 1 KiB) global -> shared with cp.async.bulk while the warp works on the current tile (2-stage ring, one mbarrier per
 // stage, no block barrier).  Measured on the memory pattern alone (profiles/r01_stream_pattern.txt): 6.3 TB/s instead of
 // 5.4 TB/s at C3's 41k threads.  All lanes of a warp stay in the loops on this path (a failed chain idles, it does not exit).
-template <class MD, int OP, int TPB, bool TMA>
+//
+// G > 1 (ensembles too small to fill the GPU: thread count x G still fits one wave): G adjacent lanes share one
+// (chain, block).  The normals of a tile — 2 DW independent Philox + Box-Muller calls, most of the tile's instructions — are
+// split over the G lanes and all-gathered with shuffles; everything else is computed redundantly by the G lanes from the same
+// loads (one sector request per group, no extra traffic) and lane 0 of the group stores.  The random stream and every
+// result are bit-identical to G = 1.
+template <class MD, int OP, int TPB, bool TMA, int G = 1>
 __global__ void DMT_FWD_BOUNDS fwd_kernel(const DevCtx cx, const LayoutDev ly, const FwdArgs fa) {
     constexpr int D = MD::D, DW = MD::DW, NPAR = MD::NPAR, NH = D * (D + 1) / 2, NG = NH + D, NAUX = D * D + D + NH;
     constexpr bool SWEEP = (OP == OP_SWEEP);
@@ -94,15 +101,18 @@ __global__ void DMT_FWD_BOUNDS fwd_kernel(const DevCtx cx, const LayoutDev ly, c
     constexpr bool WANT_LL = (OP != OP_INVSOLVE);
     constexpr bool RNG = (OP == OP_DRAW || OP == OP_INIT || SWEEP);
 
-    const int c_raw = blockIdx.x * TPB + threadIdx.x;
+    static_assert(G == 1 || (!TMA && (G == 2 || G == 4 || G == 8)), "lanes per chain");
+    constexpr bool UNI = TMA || (G > 1);               // warp-uniform control flow: lanes idle instead of leaving
+    const int t_raw = blockIdx.x * TPB + threadIdx.x;
+    const int c_raw = t_raw / G, sub = t_raw % G;
     const int b = blockIdx.y;
-    if (!TMA && c_raw >= cx.M) return;
-    if (TMA && (c_raw & ~31) >= cx.M) return;          // the whole warp lies beyond the ensemble (uniform exit)
-    const int c = TMA ? min(c_raw, cx.M - 1) : c_raw;  // TMA: lanes without a chain shadow the last one and never store
+    if (!UNI && c_raw >= cx.M) return;
+    if (UNI && ((t_raw & ~31) / G) >= cx.M) return;    // the whole warp lies beyond the ensemble (uniform exit)
+    const int c = UNI ? min(c_raw, cx.M - 1) : c_raw;  // lanes without a chain shadow the last one and never store
     const size_t M = cx.M, P = cx.P;
-    bool live = c_raw < cx.M;
+    bool live = c_raw < cx.M && sub == 0;
     if (OP == OP_INIT && ly.ok[(size_t)b * M + c]) { // retry only the chains that failed so far
-        if (!TMA) return;
+        if (!UNI) return;
         live = false;
     }
     const int ps = cx.pset[c];
@@ -179,7 +189,7 @@ __global__ void DMT_FWD_BOUNDS fwd_kernel(const DevCtx cx, const LayoutDev ly, c
         for (int s = 0; s < FWD_RING - 1; s++) produce();
     }
 
-    for (int k = i0; k <= i1 && (ok || SWEEP || TMA); ++k) {
+    for (int k = i0; k <= i1 && (ok || SWEEP || UNI); ++k) {
         const GTile<NG> gt = g_tile_of<NG>(cx, ly, k, i1, last, law_side, ps);
         const int store = gt.store, slotL = gt.slot;
         const double *Gp = gt.base;
@@ -263,7 +273,8 @@ __global__ void DMT_FWD_BOUNDS fwd_kernel(const DevCtx cx, const LayoutDev ly, c
 #pragma unroll
                     for (int s = 0; s < 4 * DW; s++) z[s] = 0.5;
 #else
-                    tile_normals<DW>(cx.seed, cx.chain_offset + (uint32_t)c, (uint32_t)(t0 + q), fa.iter, z);
+                    if (G > 1) tile_normals_coop<DW, G>(cx.seed, cx.chain_offset + (uint32_t)c, (uint32_t)(t0 + q), fa.iter, sub, z);
+                    else tile_normals<DW>(cx.seed, cx.chain_offset + (uint32_t)c, (uint32_t)(t0 + q), fa.iter, z);
 #endif
                 }
                 if (!SWEEP) { // K3: dW° = rho dW + sqrt(1-rho^2) sqrt(dt) xi   (A.2)
@@ -413,7 +424,7 @@ __global__ void DMT_FWD_BOUNDS fwd_kernel(const DevCtx cx, const LayoutDev ly, c
             { long long ck4 = clock64(); clk_acc[0] += ck1 - ck0; clk_acc[1] += ck2 - ck1; clk_acc[2] += ck3 - ck2; clk_acc[3] += ck4 - ck3; clk_n++; }
 #endif
             if (TMA) __syncwarp(); // every lane is done with this stage: the next produce() may refill it
-            if (!ok && !SWEEP && !TMA) break;
+            if (!ok && !SWEEP && !UNI) break;
         }
     }
 #ifdef DMT_EXP_CLK

@@ -66,6 +66,26 @@ __device__ __forceinline__ void tile_normals(uint64_t seed, uint32_t chain, uint
     }
 }
 
+// the same 4*DW normals, produced by G adjacent lanes together: lane `sub` of the group evaluates calls sub, sub+G, ... and the
+// group all-gathers the pairs with shuffles (every lane of the warp must call this)
+template <int DW, int G>
+__device__ __forceinline__ void tile_normals_coop(uint64_t seed, uint32_t chain, uint32_t gtile, uint32_t iter, int sub, double *z) {
+    constexpr int NC = 2 * DW, PER = (NC + G - 1) / G;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    double zl[2 * PER];
+#pragma unroll
+    for (int p = 0; p < PER; p++) {
+        const int call = min(sub + p * G, NC - 1); // (a lane past the end repeats the last call; its result is not gathered)
+        u32x4 c = {chain, gtile, iter, (STREAM_PCN << 8) | (uint32_t)call};
+        box_muller(philox4x32_10(c, k0, k1), zl[2 * p], zl[2 * p + 1]);
+    }
+#pragma unroll
+    for (int call = 0; call < NC; call++) {
+        z[2 * call] = __shfl_sync(0xffffffffu, zl[2 * (call / G)], call % G, G);
+        z[2 * call + 1] = __shfl_sync(0xffffffffu, zl[2 * (call / G) + 1], call % G, G);
+    }
+}
+
 __device__ __forceinline__ double accept_exponential(uint64_t seed, uint32_t chain, uint32_t block, uint32_t iter, uint32_t layout) {
     u32x4 c = {chain, block, iter, (STREAM_ACC << 8) | layout};
     u32x4 o = philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));

@@ -14,6 +14,7 @@ host (BASELINE.json north_star): `set_proposal_law` takes the already-translated
 import numpy as np
 
 from . import _lib
+from .param_names import ParamNamesAllObs
 
 P_only, Po_only = "P_only", "P°_only"  # Val(:P_only), Val(:P°_only)  (src/DiffusionMCMCTools.jl:9-10)
 
@@ -34,7 +35,7 @@ class SamplingEnsemble:
     contiguous chain slice of `rank` (chains are independent: src/block_ensemble.jl:63-67)."""
 
     def __init__(self, model, recordings, tts, *, aux_laws_blocking=None, artificial_noise=1e-11, device=0, seed=0, two_sided_laws=True,
-                 max_layouts=8, rank=0, world=1, pset_of_chain=None):
+                 max_layouts=8, rank=0, world=1, pset_of_chain=None, chain_offset_base=0):
         n_pts, tt = tts
         x0 = np.asarray(recordings["x0"], dtype=np.float64)
         M_tot = x0.shape[1]
@@ -57,9 +58,10 @@ class SamplingEnsemble:
             self.theta = self.theta[:, plo:phi].copy()
         self.theta_o = self.theta.copy()
         self.xbar = None
+        self.obs_param_hook = None            # (per-recording {interval: ((i_theta, i_obs), ...)}, θ°) -> (L, Sigma, v) of the proposal side
         L, Sigma = recordings["L"], recordings["Sigma"]
         self.ctx = _lib.Ctx(model, n_pts, tt, hi - lo, phi - plo, obs_dim=np.asarray(L).shape[-2] if np.asarray(L).ndim == 2 else np.asarray(L).shape[1],
-                            device=device, two_sided_laws=two_sided_laws, n_layouts=max_layouts, chain_offset=lo, seed=seed,
+                            device=device, two_sided_laws=two_sided_laws, n_layouts=max_layouts, chain_offset=chain_offset_base + lo, seed=seed,
                             artificial_noise=artificial_noise, pset_of_chain=pset_of_chain)
         self.two_sided = two_sided_laws
         self._next_layout = 0
@@ -279,18 +281,41 @@ def blocking_sweep(be, mcmciter):
 
 # ---- parameters (src/block_ensemble.jl:226-255 -> src/biblock.jl:334-371) -------------------------------------------
 def is_critical_update(be, pnames):
-    raise NotImplementedError("the reference's is_critical_update reads fields no ParamNames struct has (src/biblock.jl:315-317, "
-                              "SURVEY Appendix C.2); pass critical_change explicitly, as every tutorial does")
+    """GP.is_critical_update(be, pnames).  The reference's version reads fields no ParamNames struct has
+    (src/biblock.jl:315-317), so for the bare pair list there is nothing to ask; a ParamNamesAllObs tree
+    answers what the docstring there describes (param_names.ParamNamesAllObs.is_critical)."""
+    if isinstance(pnames, ParamNamesAllObs):
+        return pnames.is_critical()
+    raise NotImplementedError("pass critical_change explicitly (as every tutorial does) or a ParamNamesAllObs")
 
 
-def set_proposal_law(be, theta_o, pnames, critical_change, skip=0):
+def set_proposal_law(be, theta_o, pnames, critical_change=None, skip=0):
     """set_proposal_law!(be, θ°, pnames, critical_change; skip)  src/block_ensemble.jl:242-255.
-    pnames: already-translated pairs (index into θ°, index into the model's parameter vector); theta_o: [len] or [len, P]."""
+    pnames: a ParamNamesAllObs (src/param_names_collections.jl:268-288; each recording may map different entries of θ° to its
+    law — mixed effects), or already-translated pairs (index into θ°, index into the model's parameter vector) applied to
+    every recording.  theta_o: [len] or [len, P]."""
     se = be.se
     th = se.theta.copy()                      # equalize_law_params!: everything not updated is shared with the accepted law
     theta_o = np.asarray(theta_o, dtype=np.float64)
-    for i_src, j_dst in pnames:
-        th[j_dst, :] = theta_o[i_src]
+    if isinstance(pnames, ParamNamesAllObs):
+        if critical_change is None:
+            critical_change = pnames.is_critical()
+        if th.shape[1] != se.chain_hi - se.chain_lo:
+            raise ValueError("per-recording parameter names need one parameter set per recording (P == M)")
+        for r, m in enumerate(pnames.flat_updates(se.model)[se.chain_lo:se.chain_hi]):
+            for j_dst, i_src in m.items():
+                th[j_dst, r] = theta_o[i_src]
+        ou = pnames.obs_updates()[se.chain_lo:se.chain_hi]
+        if any(ou):
+            if se.obs_param_hook is None:
+                raise NotImplementedError("θ° updates observation parameters: set se.obs_param_hook(updates, theta_o) -> (L, Sigma, v)")
+            Lm, Sg, vv = se.obs_param_hook(ou, theta_o)
+            be.ctx.set_obs(Lm, Sg, vv, side=_lib.PROPOSAL)
+    else:
+        if critical_change is None:
+            raise ValueError("critical_change must be given with a bare pair list")
+        for i_src, j_dst in pnames:
+            th[j_dst, :] = theta_o[i_src]
     se.theta_o = th
     be.ctx.equalize_laws(3)                   # GP.equalize_obs_params! / equalize_law_params!  (src/biblock.jl:384-443)
     be.ctx.set_params(th, side=_lib.PROPOSAL, stores=3)

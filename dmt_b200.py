@@ -21,4 +21,6 @@ PKG_DIR = _DIR
 
 
 def __getattr__(name):
+    if name.startswith("__"):  # not a package: `import dmt_b200.x` must not load a second copy of a submodule
+        raise AttributeError(name)
     return getattr(pkg, name)
