@@ -82,6 +82,7 @@ SIGNATURES = {
     "dmt_get_guiding_term": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _dp]),
     "dmt_upload_guiding_term": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _dp]),
     "dmt_enable_guiding_cache": (C.c_int32, [_vp, C.c_int32, C.c_int32]),
+    "dmt_set_fwd_lanes": (C.c_int32, [_vp, C.c_int32]),
     "dmt_get_layout_guiding_term": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _dp]),
     "dmt_debug_normals": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, _dp]),
     "dmt_debug_exponentials": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, _dp]),
@@ -128,6 +129,9 @@ def _p(a):
     return a.ctypes.data_as(_dp)
 
 
+DEFAULT_FWD_LANES = 0  # applied to every new Ctx (the test-suite runs the GPU tests once per setting)
+
+
 class Ctx:
     """One device-resident SamplingEnsemble (M chains on one GPU).  Thin wrapper of the C ABI; arrays are numpy, with
     the chain / pset index LAST (fastest), as include/dmt.h documents."""
@@ -159,6 +163,8 @@ class Ctx:
         rc = self.lib.dmt_create(C.byref(cfg), self.n_pts.ctypes.data_as(_ip), _p(self.tt), pp, C.byref(self.h))
         if rc:
             raise DmtError(rc, (self.lib.dmt_last_error(None) or b"").decode())
+        if DEFAULT_FWD_LANES:
+            self.set_fwd_lanes(DEFAULT_FWD_LANES)
 
     # -- plumbing
     def _ck(self, rc):
@@ -380,6 +386,10 @@ class Ctx:
         n, d = int(self.n_pts[k]), self.d
         H = _f64(H, (n, d, d, self.P)); F = _f64(F, (n, d, self.P)); c = _f64(c, (n, self.P))
         self._ck(self.lib.dmt_upload_guiding_term(self.h, side, store, k, _p(H), _p(F), _p(c)))
+
+    def set_fwd_lanes(self, lanes):
+        """lanes per (chain, block) in the forward kernel: 0 = automatic, or 1 / 2 / 4 / 8 (results are identical)"""
+        self._ck(self.lib.dmt_set_fwd_lanes(self.h, int(lanes)))
 
     # -- guiding cache
     def enable_guiding_cache(self, layout, enable=True):

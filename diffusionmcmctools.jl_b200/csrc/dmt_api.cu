@@ -148,6 +148,7 @@ struct dmt_ctx {
     DevBuf<uint8_t> d_mask;
     void *nccl_comm = nullptr;
     int n_ranks = 1;
+    int fwd_lanes = 0;       // dmt_set_fwd_lanes: 0 = automatic
     bool tma_ok = false;     // P == M with the identity pset map: the TMA fast path of fwd_kernel is usable
     bool parP_mixed = false; // a masked swap_PP! made the law parity chain-dependent
 
@@ -201,8 +202,9 @@ template <class MD, int OP, bool TMA> void launch_fwd_variant(dmt_ctx *c, Layout
     constexpr bool COOP_OK = !TMA && (OP == OP_DRAW || OP == OP_INIT || OP == OP_SWEEP);
     int lanes = 1;
     if (COOP_OK) {
-        static int forced = -1;
-        if (forced < 0) { const char *e = getenv("DMT_FWD_LANES"); forced = e ? atoi(e) : 0; }
+        static int env_forced = -1;
+        if (env_forced < 0) { const char *e = getenv("DMT_FWD_LANES"); env_forced = e ? atoi(e) : 0; }
+        const int forced = c->fwd_lanes ? c->fwd_lanes : env_forced;
         const size_t units = (size_t)c->M * L.nb;
         int w = 0;
         if (forced) lanes = forced;
@@ -1081,6 +1083,12 @@ int32_t dmt_upload_guiding_term(dmt_ctx *ctx, int32_t side, int32_t store, int32
 }
 int32_t dmt_get_layout_guiding_term(dmt_ctx *ctx, int32_t layout, int32_t store, int32_t k, double *H, double *F, double *c) {
     return guarded(ctx, [&] { xfer_guiding(ctx, 0, store, k, H, F, c, false, &layout_of(ctx, layout)); });
+}
+int32_t dmt_set_fwd_lanes(dmt_ctx *ctx, int32_t lanes) {
+    return guarded(ctx, [&] {
+        if (lanes != 0 && lanes != 1 && lanes != 2 && lanes != 4 && lanes != 8) throw DmtError(DMT_ERR_ARG, "lanes must be 0 (auto), 1, 2, 4 or 8");
+        ctx->fwd_lanes = lanes;
+    });
 }
 int32_t dmt_enable_guiding_cache(dmt_ctx *ctx, int32_t layout, int32_t enable) {
     return guarded(ctx, [&] {

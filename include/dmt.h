@@ -185,6 +185,13 @@ int32_t dmt_enable_guiding_cache(dmt_ctx *ctx, int32_t layout, int32_t enable);
 /* accepted-side guiding term as ops on `layout` see it (the layout-private store when the cache is valid, else the shared one) */
 int32_t dmt_get_layout_guiding_term(dmt_ctx *ctx, int32_t layout, int32_t store, int32_t k, double *H, double *F, double *c);
 
+/* ---- tuning: lanes per (chain, block) in the forward kernel (K2-K5) ------------------------------------------------
+ * 0 (default) = automatic: 1 lane when chains x blocks fill the GPU, else the largest of 2/4/8 for which all threads are still
+ * resident at once — the lanes split the tile's Philox/Box-Muller calls and compute everything else redundantly, so results
+ * and random streams are bit-identical for every setting.  1, 2, 4, 8 force a value.  No counterpart in the reference (its
+ * per-recording loop, src/block_ensemble.jl:50, is serial). */
+int32_t dmt_set_fwd_lanes(dmt_ctx *ctx, int32_t lanes);
+
 /* ---- test hooks: the device's counter-based random streams for given counters ------------------------------- */
 /* out[n_chains][n_tiles][4*dw]: the N(0,1) draws the pCN refresh (K3) uses for chains chain0.., tiles tile0.., iteration iter.
  * Replaces nothing in the reference (its Wnr/randn draws are not reproducible elsewhere); lets tests pin the generator. */

@@ -391,3 +391,40 @@ def test_failure_is_per_chain_not_an_error(orc, olib):
     ll = ctx.get_ll(0, 0)
     assert np.isneginf(ll[0, ::4]).all() and np.isfinite(ll[0, 1::4]).all()
     ctx.close()
+
+
+@pytest.mark.parametrize("name", ["lorenz", "fhn", "prok", "jr"])
+def test_lanes_per_chain_do_not_change_any_result(name):
+    """dmt_set_fwd_lanes: 2 / 4 / 8 lanes per (chain, block) split the generator calls of a tile and all-gather the normals;
+    paths, noise, log-likelihoods and accept decisions must be bit-identical to the one-lane kernel (M = 41: ragged last warp)"""
+    K = 6
+    single = name == "jr"
+    layouts = [([(0, K - 1)], 0.7)] if single else [([(0, 1), (2, 3), (4, 5)], 0.7), ([(0, K - 1)], 0.0)]
+    prob = small_problem(name, M=41, K=K, layouts=layouts, seed=5, nsteps=10)
+    out = []
+    for lanes in (1, 2, 4, 8):
+        ctx = make_ctx(prob, seed=77, ll_hist_len=4)
+        ctx.set_fwd_lanes(lanes)
+        init = 0 if single else 1
+        ctx.recompute_guiding_term(init, _lib.P_ONLY)
+        assert ctx.init_paths(init, iter0=900, max_tries=50) == 0            # OP_INIT
+        if single:
+            ctx.loglikhd(0, 0, 0)
+        for it in range(3):
+            if single:
+                ctx.draw_proposal_path(0, it)                                # OP_DRAW
+            else:
+                ctx.blocking_sweep(0, it)                                    # OP_SWEEP
+            ctx.accept_reject_path(0, it)
+        out.append((ctx.get_X(0), ctx.get_W(0), ctx.get_X(1), ctx.get_W(1), ctx.get_ll(0, 0), ctx.get_ll(0, 1),
+                    ctx.get_accept_history(0, 0, 2)))
+        ctx.close()
+    for o in out[1:]:
+        for a, b in zip(out[0], o):
+            assert np.array_equal(a, b, equal_nan=True)
+    with pytest.raises(dmt_b200.DmtError):
+        c = make_ctx(prob, seed=1)
+        try:
+            c.set_fwd_lanes(3)
+        finally:
+            c.close()
