@@ -208,7 +208,8 @@ template <class MD, int OP, bool TMA> void launch_fwd_variant(dmt_ctx *c, Layout
         const size_t units = (size_t)c->M * L.nb;
         int w = 0;
         if (forced) lanes = forced;
-        else {
+        else if (MD::DW >= 2) { // with one Wiener coordinate the generator is a small part of the tile: redundant lanes only cost issue slots
+                                 // (Jansen-Rit draw, 8192 chains: 87 ms with 1 lane, 121 ms with 4)
             launch_fwd_lanes<MD, OP, false, 8>(c, L, fa, &w);
             if (units * 8 <= (size_t)w) lanes = 8;
             else {

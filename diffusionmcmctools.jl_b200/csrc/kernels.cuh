@@ -549,6 +549,12 @@ __global__ void __launch_bounds__(128) bwd_coop_kernel(const DevCtx cx, const La
     double Hrow[D], Fr = 0.0, cc = 0.0;
 #pragma unroll
     for (int j = 0; j < D; j++) Hrow[j] = 0.0;
+    // exchange buffer of the RHS: every lane publishes its row of H and its F, then reads the whole (H, F) of its parameter
+    // set back (broadcast reads, conflict-free across the groups of a warp).  Two buffers alternate, so one __syncwarp per
+    // evaluation is enough.  (Replaces D^2 + D double shuffles per evaluation: the kernel was bound by the shuffle pipe.)
+    constexpr int GSZ = D * D + D;
+    __shared__ __align__(16) double xch[4][2][(32 / D + 1) * GSZ];
+    int xbuf = 0;
 
     for (int k = i1; k >= i0; --k) {
         const int slot = side ^ cx.parP[0][(size_t)k * P + ps];
@@ -623,14 +629,20 @@ __global__ void __launch_bounds__(128) bwd_coop_kernel(const DevCtx cx, const La
 
         auto rhs = [&](const double *Hr, double F_r, double *dHr, double &dFr, double &dc) {
             double Mx[D], My[D], Fall[D], tr = 0.0;
+            double *blk = &xch[wid][xbuf][g * GSZ];
+            xbuf ^= 1;
 #pragma unroll
-            for (int j = 0; j < D; j++) { Mx[j] = 0.0; My[j] = 0.0; Fall[j] = __shfl_sync(FULL, F_r, base + j); }
+            for (int j = 0; j < D; j++) blk[r * D + j] = Hr[j];
+            blk[D * D + r] = F_r;
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < D; j++) { Mx[j] = 0.0; My[j] = 0.0; Fall[j] = blk[D * D + j]; }
 #pragma unroll
             for (int q = 0; q < D; q++) {
                 const double ckr = fma(-0.5 * ad[q], Hr[q], Bcol[q]); // C_qr = B_qr - a_q H_qr / 2, H_qr = H_rq (own row)
 #pragma unroll
                 for (int j = 0; j < D; j++) {
-                    const double hqj = __shfl_sync(FULL, Hr[j], base + q);       // H_qj from the lane that owns row q
+                    const double hqj = blk[q * D + j];                           // H_qj, published by the lane that owns row q
                     const double cqj = fma(-0.5 * ad[q], hqj, Bm[q * D + j]);    // C_qj
                     Mx[j] = fma(Hr[q], cqj, Mx[j]);                              // (HC)_{rj}
                     My[j] = fma(hqj, ckr, My[j]);                                // (HC)_{jr} = sum_q H_jq C_qr, H_jq = H_qj
@@ -651,6 +663,7 @@ __global__ void __launch_bounds__(128) bwd_coop_kernel(const DevCtx cx, const La
             dc = bF + 0.5 * FaF - 0.5 * tr;
         };
 
+        double tb[D + 1][4] = {}; // this lane's components of the current 4-step tile: (r, r..D-1) of H and F_r -> 256-bit stores
         for (int j = nst - 1; j >= 0; --j) { // classical RK4 from t[j+1] back to t[j], row r of H, F_r, c (replicated)
             const double h = dtp[j];
             double kH[D], kF, kc, aH[D], aF, ac, Hs[D], Fs;
@@ -672,12 +685,20 @@ __global__ void __launch_bounds__(128) bwd_coop_kernel(const DevCtx cx, const La
             for (int i = 0; i < D; i++) Hrow[i] = fma(-h6, aH[i] + kH[i], Hrow[i]);
             Fr = fma(-h6, aF + kF, Fr);
             cc = fma(-h6, ac + kc, cc);
-            if (active) {
-                double *gp = Gp + (size_t)(j >> 2) * NG * gstr + (j & 3);
+#pragma unroll
+            for (int sl = 0; sl < 4; sl++) {
+                if ((j & 3) == sl) {
+#pragma unroll
+                    for (int jj = 0; jj < D; jj++) tb[jj][sl] = Hrow[jj];
+                    tb[D][sl] = Fr;
+                }
+            }
+            if ((j & 3) == 0 && active) { // the tile is complete (slots past the interval end hold don't-care values)
+                double *gp = Gp + (size_t)(j >> 2) * NG * gstr;
 #pragma unroll
                 for (int jj = 0; jj < D; jj++)
-                    if (jj >= r) gp[(size_t)(r * D - r * (r - 1) / 2 + (jj - r)) * gstr] = Hrow[jj]; // packed upper (r, jj)
-                gp[(size_t)(NH + r) * gstr] = Fr;
+                    if (jj >= r) st256(gp + (size_t)(r * D - r * (r - 1) / 2 + (jj - r)) * gstr, tb[jj]); // packed upper (r, jj)
+                st256(gp + (size_t)(NH + r) * gstr, tb[D]);
             }
         }
         if (active && r == 0) (priv ? ly.c0l[0] : cx.c0[slot][0])[(size_t)k * P + ps] = cc;
