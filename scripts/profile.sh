@@ -16,6 +16,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 echo "rc=$?"; tail -3 $OUT/ncu_launch_$TAG.log | cut -c1-300
 echo "== full capture of the sweep kernels (draw, invsolve_ll, bwd)"
 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-    -k 'regex:fwd_kernel|bwd_kernel|cache_apply_kernel' -s ${NCU_SKIP:-28} -c ${NCU_COUNT:-6} -o $OUT/prof_$TAG -f $CMD > $OUT/ncu_full_$TAG.log 2>&1
+    -k 'regex:fwd_kernel|bwd_kernel|bwd_coop_kernel|cache_apply_kernel' -s ${NCU_SKIP:-28} -c ${NCU_COUNT:-6} -o $OUT/prof_$TAG -f $CMD > $OUT/ncu_full_$TAG.log 2>&1
 echo "rc=$?"; tail -3 $OUT/ncu_full_$TAG.log | cut -c1-300
 ls -la $OUT

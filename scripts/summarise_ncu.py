@@ -55,5 +55,25 @@ if os.path.exists(rep):
             i = hdr.index(w)
             lines.append("| %s | %s | " % (w, units[i]) + " | ".join(r[i][:14] for r in rows[2:]) + " |")
     lines.append("")
+    # dram traffic per launch of the forward kernels -> profiles/traffic.json (bench.py fills roofline.traffic from it)
+    import json
+    import re
+    MODELS = {0: "FitzHughNagumo", 1: "LotkaVolterra", 2: "Lorenz", 3: "Prokaryote", 4: "JansenRit", 5: "OU2"}
+    OPS = {0: "OP_DRAW", 1: "OP_RECOMPUTE", 2: "OP_LOGLIK", 3: "OP_INVSOLVE", 4: "OP_INVSOLVE_LL", 5: "OP_INIT", 6: "OP_SWEEP"}
+    tpath = os.path.join(out_dir, "traffic.json")
+    traffic = json.load(open(tpath)) if os.path.exists(tpath) else {}
+    ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    acc = collections.OrderedDict()
+    for r in rows[2:]:
+        mm = re.search(r"fwd_kernel<(?:dmt::)?Model<(\d+)>, *(\d+)", r[ki])
+        if mm:
+            key = "fwd_kernel<%s, %s>" % (MODELS[int(mm.group(1))], OPS[int(mm.group(2))])
+            acc.setdefault(key, []).append(float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]])
+    units_per_launch = int(os.environ.get("UNITS_PER_LAUNCH", "81920000"))
+    for key, v in acc.items():
+        traffic[key] = {"dram_bytes_per_launch": int(sum(v) / len(v)), "units_per_launch": units_per_launch,
+                        "source": "profiles/%s_summary.md (ncu --set full, mean of %d launches)" % (tag, len(v))}
+    json.dump(traffic, open(tpath, "w"), indent=1)
 open(os.path.join(out_dir, "%s_summary.md" % tag), "w").write("\n".join(lines))
 print("\n".join(lines))
