@@ -18,4 +18,7 @@ echo "== full capture of the sweep kernels (draw, invsolve_ll, bwd)"
 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
     -k 'regex:fwd_kernel|bwd_kernel|bwd_coop_kernel|cache_apply_kernel' -s ${NCU_SKIP:-28} -c ${NCU_COUNT:-6} -o $OUT/prof_$TAG -f $CMD > $OUT/ncu_full_$TAG.log 2>&1
 echo "rc=$?"; tail -3 $OUT/ncu_full_$TAG.log | cut -c1-300
+# gpurun copies back at most 64 MiB: keep the exported pages, drop the report unless KEEP_REP=1
+ncu -i $OUT/prof_$TAG.ncu-rep --page raw --csv > $OUT/prof_${TAG}_raw.csv 2>/dev/null
+[ "${KEEP_REP:-0}" = 1 ] || rm -f $OUT/prof_$TAG.ncu-rep
 ls -la $OUT

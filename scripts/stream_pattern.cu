@@ -59,6 +59,67 @@ __global__ void k_seq(const double *G, const double *Win, double *Wout, double *
         carry = acc[3] * 1e-30;
     }
 }
+// ---- the two candidates WITH a dependent arithmetic chain of `work` DFMAs per step (stands for the Euler-Maruyama recursion):
+// (a) the shipped pattern: whole 4-step tile loaded, 4 x work, tile stored;
+// (b) layout [step][component][chain] (8 bytes per lane, LDG.64/STG.64) with a rolling register pipeline PF steps deep, so
+//     loads stay in flight during the recursion.  Same bytes, same work, same thread count.
+__device__ __forceinline__ double ld64(const double *p) { double v; asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v; }
+__device__ __forceinline__ void st64(double *p, double v) { asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+__global__ void __launch_bounds__(64, 6) k_tile_work(const double *G, const double *Win, double *Wout, double *Xout, int M, int len, int work) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (c >= M) return;
+    double carry = 0;
+    for (int q = 0; q < len; q++) {
+        const size_t t = (size_t)b * len + q;
+        double g[NG][4], w[DW][4];
+        for (int a = 0; a < NG; a++) ld256(G + ((t * NG + a) * M + c) * 4, g[a]);
+        for (int j = 0; j < DW; j++) ld256(Win + ((t * DW + j) * M + c) * 4, w[j]);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            double acc = carry;
+            for (int a = 0; a < NG; a++) acc += g[a][i];
+            for (int k = 0; k < work; k++) acc = fma(acc, 0.999999, 1e-9);
+            for (int j = 0; j < DW; j++) w[j][i] += acc;
+            carry = acc * 1e-30;
+        }
+        for (int j = 0; j < DW; j++) {
+            st256(Wout + ((t * DW + j) * M + c) * 4, w[j]);
+            st256(Xout + ((t * D + j) * M + c) * 4, w[j]);
+        }
+    }
+}
+template <int PF>
+__global__ void __launch_bounds__(64, 6) k_step_work(const double *G, const double *Win, double *Wout, double *Xout, int M, int len, int work) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (c >= M) return;
+    const size_t s0 = (size_t)b * len;
+    double g[PF][NG], w[PF][DW], carry = 0;
+#pragma unroll
+    for (int p = 0; p < PF; p++) {
+        for (int a = 0; a < NG; a++) g[p][a] = ld64(G + ((s0 + p) * NG + a) * M + c);
+        for (int j = 0; j < DW; j++) w[p][j] = ld64(Win + ((s0 + p) * DW + j) * M + c);
+    }
+    for (int s = 0; s < len; s += PF) {
+#pragma unroll
+        for (int p = 0; p < PF; p++) {
+            const size_t t = s0 + s + p;
+            double acc = carry;
+            for (int a = 0; a < NG; a++) acc += g[p][a];
+            double wv[DW];
+            for (int j = 0; j < DW; j++) wv[j] = w[p][j];
+            if (s + p + PF < len) { // slot p is free again: request step s + p + PF
+                for (int a = 0; a < NG; a++) g[p][a] = ld64(G + ((t + PF) * NG + a) * M + c);
+                for (int j = 0; j < DW; j++) w[p][j] = ld64(Win + ((t + PF) * DW + j) * M + c);
+            }
+            for (int k = 0; k < work; k++) acc = fma(acc, 0.999999, 1e-9);
+            for (int j = 0; j < DW; j++) {
+                st64(Wout + (t * DW + j) * M + c, wv[j] + acc);
+                st64(Xout + (t * D + j) * M + c, wv[j] + acc);
+            }
+            carry = acc * 1e-30;
+        }
+    }
+}
 // sequential, everything read through an S-stage cp.async ring in shared memory
 template <int S, int TPB>
 __global__ void k_seq_cp(const double *G, const double *Win, double *Wout, double *Xout, int M, int len) {
@@ -176,6 +237,18 @@ int main(int argc, char **argv) {
     auto rep = [&](const char *n, float ms) { printf("%-44s %8.3f ms  %7.1f GB/s\n", n, ms, gb / ms * 1e3); };
     rep("copy (cudaMemcpy D2D, same bytes r+w)", timeit([&] { cudaMemcpyAsync(G, G + nG / 2, (size_t)(gb * 1e9 / 2), cudaMemcpyDeviceToDevice); }));
     rep("par: thread per (chain,tile), TPB 128", timeit([&] { k_par<<<dim3((M + 127) / 128, NT), 128>>>(G, Wi, Wo, Xo, M, NT); }));
+    if (argc > 2) { // second argument: only the tile-vs-rolling comparison
+        for (int nb : {10, 20}) for (int work : {0, 64, 128, 256, 512}) {
+            const int len = NT / nb; char nm[96];
+            snprintf(nm, 96, "tile   LDG.256      blocks=%2d work=%3d/step", nb, work);
+            rep(nm, timeit([&] { k_tile_work<<<dim3((M + 63) / 64, nb), 64>>>(G, Wi, Wo, Xo, M, len, work); }));
+            snprintf(nm, 96, "rolling LDG.64 PF=4 blocks=%2d work=%3d/step", nb, work);
+            rep(nm, timeit([&] { k_step_work<4><<<dim3((M + 63) / 64, nb), 64>>>(G, Wi, Wo, Xo, M, len * 4, work); }));
+            snprintf(nm, 96, "rolling LDG.64 PF=8 blocks=%2d work=%3d/step", nb, work);
+            rep(nm, timeit([&] { k_step_work<8><<<dim3((M + 63) / 64, nb), 64>>>(G, Wi, Wo, Xo, M, len * 4, work); }));
+        }
+        return 0;
+    }
     for (int nb : {10, 20, 50, 100, 500}) {
         const int len = NT / nb; char nm[96];
         snprintf(nm, 96, "seq LDG.256 PF0   blocks=%3d (threads %d)", nb, M * nb);

@@ -35,8 +35,12 @@ if os.path.exists(lpath):
     lines.append("")
 
 rep = os.path.join(g, "prof_%s.ncu-rep" % tag)
-if os.path.exists(rep):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rawcsv = os.path.join(g, "prof_%s_raw.csv" % tag)
+if os.path.exists(rep) or os.path.exists(rawcsv):
+    if os.path.exists(rawcsv):
+        raw = open(rawcsv).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
@@ -69,9 +73,15 @@ if os.path.exists(rep):
         mm = re.search(r"fwd_kernel<(?:dmt::)?Model<(\d+)>, *(\d+)", r[ki])
         if mm:
             key = "fwd_kernel<%s, %s>" % (MODELS[int(mm.group(1))], OPS[int(mm.group(2))])
-            acc.setdefault(key, []).append(float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]])
+            try:
+                acc.setdefault(key, []).append(float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]])
+            except ValueError:
+                pass
     units_per_launch = int(os.environ.get("UNITS_PER_LAUNCH", "81920000"))
     for key, v in acc.items():
+        v = [x for x in v if x == x]
+        if not v:
+            continue
         traffic[key] = {"dram_bytes_per_launch": int(sum(v) / len(v)), "units_per_launch": units_per_launch,
                         "source": "profiles/%s_summary.md (ncu --set full, mean of %d launches)" % (tag, len(v))}
     json.dump(traffic, open(tpath, "w"), indent=1)
