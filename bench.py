@@ -185,10 +185,19 @@ def gpu_arm(a):
     elif not a.no_cache:  # smoothing: the laws stay fixed, only the blocks' frozen end points move => K1 through the guiding cache
         for l in range(nlay):
             ctx.enable_guiding_cache(l)
-    if world > 1:  # native NCCL communicator inside libdmt for the small stats allreduce
+    allreduce_kind = "none"
+    if world > 1 and not os.environ.get("DMT_NO_P2P"):
+        # the small stats all-reduce as the library's own one-shot kernel over NVLink peer memory (dmt_p2p_init)
+        mine = torch.from_numpy(ctx.p2p_export().copy()).to(dev)
+        allh = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        ctx.p2p_init(world, rank, np.stack([h.cpu().numpy() for h in allh]))
+        allreduce_kind = "p2p kernel (NVLink peer memory)"
+    elif world > 1:  # native NCCL communicator inside libdmt
         uid = torch.from_numpy(ctx.nccl_unique_id() if rank == 0 else np.zeros(128, np.uint8)).to(dev)
         dist.broadcast(uid, 0)
         ctx.comm_init(world, rank, uid.cpu().numpy())
+        allreduce_kind = "ncclAllReduce"
     stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
 
     fused = blocking and not a.separate  # find_W_for_X! + loglikhd! + draw_proposal_path! in one pass (dmt_find_W_loglikhd_draw)
@@ -345,7 +354,7 @@ def gpu_arm(a):
                    "config_id": a.config, "chains_per_gpu": prob.M, "steps_per_chain": prob.steps_per_chain,
                    "l2": "inputs (paths %.1f GB + guiding term %.1f GB per GPU) are far larger than the 126 MB L2"
                          % (2 * 8 * ctx.S * (prob.d + prob.dw) * prob.M / 1e9, 8 * ctx.S * (prob.d * (prob.d + 1) // 2 + prob.d) * prob.P / 1e9),
-                   "step": "one blocking sweep over one layout" if blocking else "draw + accept"},
+                   "step": "one blocking sweep over one layout" if blocking else "draw + accept", "stats_allreduce": allreduce_kind},
         "roofline": roofline, "kernel_ms": kern_ms, "kernel_ms_by_layout": kern_ms_by_layout, "gpu_launches": launches_per_step * a.steps, "clocks": clocks,
         "last_stats": {"sum_ll": float(last[0]), "sum_ll_prop": float(last[1]), "accept_frac": float(np.sum(last[2:]) / (len(last[2:]) * prob.M * world))},
     }

@@ -89,6 +89,8 @@ SIGNATURES = {
     "dmt_nccl_unique_id": (C.c_int32, [_bp]),
     "dmt_comm_init": (C.c_int32, [_vp, C.c_int32, C.c_int32, _bp]),
     "dmt_allreduce_stats": (C.c_int32, [_vp, C.c_int32, _dp]),
+    "dmt_p2p_export": (C.c_int32, [_vp, _bp]),
+    "dmt_p2p_init": (C.c_int32, [_vp, C.c_int32, C.c_int32, _bp]),
 }
 
 _lib = None
@@ -426,6 +428,16 @@ class Ctx:
         uid = np.ascontiguousarray(uid, dtype=np.uint8)
         assert uid.size == 128
         self._ck(self.lib.dmt_comm_init(self.h, n_ranks, rank, uid.ctypes.data_as(_bp)))
+
+    def p2p_export(self):
+        h = np.zeros(64, dtype=np.uint8)
+        self._ck(self.lib.dmt_p2p_export(self.h, h.ctypes.data_as(_bp)))
+        return h
+
+    def p2p_init(self, n_ranks, rank, handles):
+        handles = np.ascontiguousarray(handles, dtype=np.uint8)
+        assert handles.shape == (n_ranks, 64)
+        self._ck(self.lib.dmt_p2p_init(self.h, n_ranks, rank, handles.ctypes.data_as(_bp)))
 
     def allreduce_stats(self, layout):
         out = np.empty(2 + self.layout_nb[layout])

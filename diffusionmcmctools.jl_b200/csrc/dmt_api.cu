@@ -147,6 +147,10 @@ struct dmt_ctx {
     DevBuf<double> d_scratch, d_partial, d_stats;
     DevBuf<uint8_t> d_mask;
     void *nccl_comm = nullptr;
+    // peer-memory all-reduce (dmt_p2p_export / dmt_p2p_init)
+    P2PBuf *p2p_local = nullptr;
+    P2PArgs p2p{};
+    bool p2p_ready = false;
     int n_ranks = 1;
     int fwd_lanes = 0;       // dmt_set_fwd_lanes: 0 = automatic
     bool tma_ok = false;     // P == M with the identity pset map: the TMA fast path of fwd_kernel is usable
@@ -613,6 +617,10 @@ int32_t dmt_destroy(dmt_ctx *ctx) {
     if (!ctx) return DMT_OK;
     cudaSetDevice(ctx->cfg.device);
     if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->nccl_comm);
+    if (ctx->p2p_ready)
+        for (int r = 0; r < ctx->p2p.world; r++)
+            if (r != ctx->p2p.rank && ctx->p2p.peer[r]) cudaIpcCloseMemHandle(ctx->p2p.peer[r]);
+    if (ctx->p2p_local) cudaFree(ctx->p2p_local);
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
     delete ctx;
     return DMT_OK;
@@ -1159,11 +1167,57 @@ int32_t dmt_comm_init(dmt_ctx *ctx, int32_t n_ranks, int32_t rank, const uint8_t
         ctx->n_ranks = n_ranks;
     });
 }
+int32_t dmt_p2p_export(dmt_ctx *ctx, uint8_t *handle64) {
+    return guarded(ctx, [&] {
+        REQUIRE(handle64, DMT_ERR_ARG, "null");
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        if (!ctx->p2p_local) {
+            CK(cudaMalloc(&ctx->p2p_local, sizeof(P2PBuf)));
+            CK(cudaMemset(ctx->p2p_local, 0, sizeof(P2PBuf)));
+            CK(cudaDeviceSynchronize());
+        }
+        cudaIpcMemHandle_t h;
+        CK(cudaIpcGetMemHandle(&h, ctx->p2p_local));
+        memcpy(handle64, &h, 64);
+    });
+}
+int32_t dmt_p2p_init(dmt_ctx *ctx, int32_t n_ranks, int32_t rank, const uint8_t *handles) {
+    return guarded(ctx, [&] {
+        REQUIRE(handles && n_ranks >= 1 && n_ranks <= P2P_MAX_RANKS && rank >= 0 && rank < n_ranks, DMT_ERR_ARG, "bad peer arguments");
+        REQUIRE(ctx->p2p_local, DMT_ERR_STATE, "dmt_p2p_export first");
+        ctx->p2p = P2PArgs{};
+        for (int r = 0; r < n_ranks; r++) {
+            if (r == rank) { ctx->p2p.peer[r] = ctx->p2p_local; continue; }
+            cudaIpcMemHandle_t h;
+            memcpy(&h, handles + (size_t)r * 64, 64);
+            void *p = nullptr;
+            CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            ctx->p2p.peer[r] = (P2PBuf *)p;
+        }
+        ctx->p2p.rank = rank;
+        ctx->p2p.world = n_ranks;
+        ctx->p2p.seq = 0;
+        ctx->n_ranks = n_ranks;
+        ctx->p2p_ready = true;
+    });
+}
 int32_t dmt_allreduce_stats(dmt_ctx *ctx, int32_t layout, double *out) {
     return guarded(ctx, [&] {
         Layout &L = layout_of(ctx, layout);
         REQUIRE(out, DMT_ERR_ARG, "null");
         fill_stats(ctx, L, nullptr);
+        if (ctx->p2p_ready && 2 + L.nb <= P2P_MAX_VALS) { // own one-shot all-reduce over NVLink peer memory (kernels.cuh)
+            ctx->p2p.seq++;
+            ctx->p2p.nval = 2 + L.nb;
+            p2p_allreduce_kernel<<<1, P2P_MAX_VALS, 0, ctx->stream>>>(ctx->p2p, ctx->d_stats.p);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(out, ctx->d_stats.p, sizeof(double) * (2 + L.nb), cudaMemcpyDeviceToHost, ctx->stream));
+            int err = 0;
+            CK(cudaMemcpyAsync(&err, &ctx->p2p_local->error, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (err) throw DmtError(DMT_ERR_NCCL, "peer all-reduce timed out: a rank did not arrive within 20 s");
+            return;
+        }
         if (ctx->nccl_comm) // ONE small allreduce: [sum ll, sum ll°, accept counts per block]  
             NCK(g_nccl.AllReduce(ctx->d_stats.p, ctx->d_stats.p, (size_t)(2 + L.nb), 8 /* ncclDouble */, 0 /* ncclSum */, ctx->nccl_comm, ctx->stream));
         CK(cudaMemcpyAsync(out, ctx->d_stats.p, sizeof(double) * (2 + L.nb), cudaMemcpyDeviceToHost, ctx->stream));

@@ -1101,4 +1101,50 @@ __global__ void accept_counts_kernel(const uint8_t *acc_hist, int nb, int M, uin
     if ((threadIdx.x & 31) == 0 && n) atomicAdd(&counts[b], n);
 }
 
+
+// ------------------------------------------------------------------------------------------- C1 over NVLink peer memory
+// One-shot all-reduce of the few statistics doubles ([sum ll, sum ll°, accept counts per block]) written as ONE
+// single-CTA kernel over peer-mapped memory instead of a NCCL call: every rank stores its values into slot `rank` of every
+// peer's exchange buffer, publishes a sequence number with a system-scope release, waits for all peers' sequence numbers with
+// acquire loads, and sums the slots IN RANK ORDER (bitwise reproducible for a given world size, identical on every rank).
+// Two data parities alternate: a rank can be at most one reduction ahead of any other.
+constexpr int P2P_MAX_RANKS = 16, P2P_MAX_VALS = 256;
+struct P2PBuf {
+    double data[2][P2P_MAX_RANKS][P2P_MAX_VALS];
+    unsigned long long flag[P2P_MAX_RANKS];
+    int error;
+};
+struct P2PArgs {
+    P2PBuf *peer[P2P_MAX_RANKS]; // peer[r]: rank r's buffer as mapped into this process (peer[rank] = the local one)
+    int rank, world, nval;
+    unsigned long long seq;      // 1, 2, 3, ... the same on every rank
+};
+__global__ void __launch_bounds__(P2P_MAX_VALS) p2p_allreduce_kernel(const P2PArgs a, double *vals) {
+    const int t = threadIdx.x, par = (int)(a.seq & 1ull);
+    if (t < a.nval) {
+        const double v = vals[t];
+        for (int r = 0; r < a.world; r++) a.peer[r]->data[par][a.rank][t] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (t < a.world) {
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&a.peer[t]->flag[a.rank]), "l"(a.seq) : "memory");
+        const unsigned long long *mine = &a.peer[a.rank]->flag[t];
+        unsigned long long seen = 0, t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+            if (seen >= a.seq) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 20000000000ull) { a.peer[a.rank]->error = 1; break; } // 20 s: a peer never arrived
+        } while (true);
+    }
+    __syncthreads();
+    if (t < a.nval) {
+        double s = 0.0;
+        for (int r = 0; r < a.world; r++) s += *(volatile const double *)&a.peer[a.rank]->data[par][r][t];
+        vals[t] = s;
+    }
+}
+
 } // namespace dmt

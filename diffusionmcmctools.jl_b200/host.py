@@ -105,6 +105,19 @@ class SamplingEnsemble:
         self.ctx.comm_init(self.world, self.rank, uid)
         self._has_comm = True
 
+    def p2p_init(self):
+        """map every rank's exchange buffer (CUDA IPC) so that the stats all-reduce is the library's own one-shot kernel over
+        NVLink peer memory instead of a NCCL call; the 64-byte handles travel through the default torch.distributed group"""
+        import torch
+        import torch.distributed as dist
+        mine = torch.from_numpy(self.ctx.p2p_export().copy())
+        if dist.get_backend() == "nccl":
+            mine = mine.cuda()
+        allh = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(allh, mine)
+        self.ctx.p2p_init(self.world, self.rank, np.stack([h.cpu().numpy() for h in allh]))
+        self._has_comm = True
+
     def num_recordings(self):  # OBS.num_recordings(se)  src/sampling_ensemble.jl:46
         return self.M_total
 

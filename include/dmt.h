@@ -203,6 +203,13 @@ int32_t dmt_debug_exponentials(dmt_ctx *ctx, uint32_t chain0, uint32_t iter, uin
 /* NCCL is dlopen'ed at first use.  unique_id: the 128-byte ncclUniqueId from dmt_nccl_unique_id on rank 0. */
 int32_t dmt_nccl_unique_id(uint8_t *id128);
 int32_t dmt_comm_init(dmt_ctx *ctx, int32_t n_ranks, int32_t rank, const uint8_t *id128);
+/* Peer-memory variant of the same exchange (preferred on one NVLink/NVSwitch node): every rank exports a 64-byte CUDA IPC
+ * handle of its exchange buffer, the host all-gathers the handles by any means, dmt_p2p_init maps the peers.  After that
+ * dmt_allreduce_stats is ONE single-CTA kernel that stores this rank's values into every peer's buffer, publishes / awaits a
+ * sequence number with system-scope release / acquire, and sums the slots in rank order (bitwise reproducible, identical on
+ * all ranks) — no NCCL call on the path.  One process per GPU (IPC handles cannot be opened by the exporting process). */
+int32_t dmt_p2p_export(dmt_ctx *ctx, uint8_t *handle64);
+int32_t dmt_p2p_init(dmt_ctx *ctx, int32_t n_ranks, int32_t rank, const uint8_t *handles /* [n_ranks][64] */);
 /* out[0]=sum ll, out[1]=sum ll°, out[2..2+n_blocks)=accept counts of the last accept step, summed over ranks */
 int32_t dmt_allreduce_stats(dmt_ctx *ctx, int32_t layout, double *out /* [2+n_blocks] */);
 

@@ -62,6 +62,18 @@ def main():
         ref = torch.empty((prob.n_pts.sum(), prob.d, M), dtype=torch.float64, device="cuda")
     dist.broadcast(ref, 0)
     ok &= bool(np.array_equal(X, ref.cpu().numpy()[:, :, lo:hi]))
+    # the same run with the library's own peer-memory all-reduce instead of NCCL: same sums (to rounding: NCCL's order is its own),
+    # bit-identical on every rank
+    se2 = H.SamplingEnsemble(prob.model, rec, (prob.n_pts, prob.tt), device=local, seed=77, two_sided_laws=False, rank=rank, world=world)
+    se2.p2p_init()
+    X2, out2 = run(se2)
+    ok &= bool(np.array_equal(X2, X))
+    for (ll, llo, _), (ll2, llo2, _) in zip(out, out2):
+        ok &= abs(ll - ll2) <= 1e-12 * abs(ll) and abs(llo - llo2) <= 1e-12 * abs(llo)
+    mine = torch.tensor([o[0] for o in out2] + [o[1] for o in out2], dtype=torch.float64, device="cuda")
+    every = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(every, mine)
+    ok &= all(bool(torch.equal(every[0], e)) for e in every)
     flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
