@@ -89,6 +89,8 @@ SIGNATURES = {
     "dmt_nccl_unique_id": (C.c_int32, [_bp]),
     "dmt_comm_init": (C.c_int32, [_vp, C.c_int32, C.c_int32, _bp]),
     "dmt_allreduce_stats": (C.c_int32, [_vp, C.c_int32, _dp]),
+    "dmt_set_accepted": (C.c_int32, [_vp, C.c_int32, C.c_uint32, _bp]),
+    "dmt_set_ll_history": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_uint32, _dp]),
     "dmt_p2p_export": (C.c_int32, [_vp, _bp]),
     "dmt_p2p_init": (C.c_int32, [_vp, C.c_int32, C.c_int32, _bp]),
 }
@@ -367,6 +369,14 @@ class Ctx:
         a = np.empty((it1 - it0 + 1, self.layout_nb[layout], self.M), dtype=np.uint8)
         self._ck(self.lib.dmt_get_accept_history(self.h, layout, it0, it1, a.ctypes.data_as(_bp)))
         return a.astype(bool)
+
+    def set_accepted(self, layout, it, acc):
+        a = np.ascontiguousarray(np.broadcast_to(np.asarray(acc), (self.layout_nb[layout], self.M)), dtype=np.uint8)
+        self._ck(self.lib.dmt_set_accepted(self.h, layout, it, a.ctypes.data_as(_bp)))
+
+    def set_ll_history(self, layout, side, it, ll):
+        a = _f64(np.broadcast_to(np.asarray(ll, dtype=np.float64), (self.layout_nb[layout], self.M)), (self.layout_nb[layout], self.M))
+        self._ck(self.lib.dmt_set_ll_history(self.h, layout, side, it, _p(a)))
 
     def get_ll_history(self, layout, side, it0, it1):
         a = np.empty((it1 - it0 + 1, self.layout_nb[layout], self.M))

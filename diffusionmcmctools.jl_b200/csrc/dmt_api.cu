@@ -1044,6 +1044,25 @@ int32_t dmt_get_ll_history(dmt_ctx *ctx, int32_t layout, int32_t side, uint32_t 
         CK(cudaStreamSynchronize(ctx->stream));
     });
 }
+int32_t dmt_set_accepted(dmt_ctx *ctx, int32_t layout, uint32_t iter, const uint8_t *acc) {
+    return guarded(ctx, [&] {
+        Layout &L = layout_of(ctx, layout);
+        REQUIRE(acc && iter < (uint32_t)L.dev.hist_len, DMT_ERR_ARG, "bad history index");
+        const size_t per = (size_t)L.nb * ctx->M;
+        CK(cudaMemcpyAsync(L.d_acc_hist.p + iter * per, acc, per, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    });
+}
+int32_t dmt_set_ll_history(dmt_ctx *ctx, int32_t layout, int32_t side, uint32_t iter, const double *ll) {
+    return guarded(ctx, [&] {
+        Layout &L = layout_of(ctx, layout);
+        check_side(ctx, side);
+        REQUIRE(ll && iter < (uint32_t)L.dev.hist_len, DMT_ERR_ARG, "bad history index");
+        const size_t per = (size_t)L.nb * ctx->M;
+        CK(cudaMemcpyAsync(L.d_ll_hist.p + ((size_t)iter * 2 + side) * per, ll, per * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    });
+}
 int32_t dmt_accept_counts(dmt_ctx *ctx, int32_t layout, uint32_t it0, uint32_t it1, int64_t *counts) {
     return guarded(ctx, [&] {
         Layout &L = layout_of(ctx, layout);

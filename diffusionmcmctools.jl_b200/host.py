@@ -252,6 +252,22 @@ def save_ll(be, mcmciter):
     be.ctx.save_ll(be.layout, mcmciter)
 
 
+def set_ll(be, i, v, side=0):
+    """set_ll!(b, i, v): ll_history[i] = v  (src/block.jl:82-86); v broadcasts over [n_blocks, M]"""
+    be.ctx.set_ll_history(be.layout, side, i, v)
+
+
+def set_accepted(be, i, v):
+    """set_accepted!(bb, i, v): accpt_history[i] = v  (src/biblock.jl:130-135); v broadcasts over [n_blocks, M]"""
+    be.ctx.set_accepted(be.layout, i, v)
+
+
+def recompute_path(be, skip=0, law_side=_lib.PROPOSAL, noise_side=_lib.ACCEPTED):
+    """recompute_path!(b°, b.WW; skip) for every block of every recording (src/block.jl:161-187): the path under the proposal
+    law driven by the accepted noise, with its log-likelihood"""
+    be.ctx.recompute_path(be.layout, law_side, noise_side, skip)
+
+
 def ll_of_accepted(be, i):
     """[recording][block] log-likelihood of the path accepted at iteration i  (src/biblock.jl:222-224)"""
     acc = be.ctx.get_accept_history(be.layout, i, i)[0]

@@ -160,6 +160,9 @@ int32_t dmt_set_ll(dmt_ctx *ctx, int32_t layout, int32_t side, const double *ll)
 int32_t dmt_get_success(dmt_ctx *ctx, int32_t layout, uint8_t *ok /* [n_blocks][M], last forward op */);
 /* accpt_history / ll_history (src/biblock.jl:47, src/block.jl:58) for iterations it0..it1 inclusive */
 int32_t dmt_get_accept_history(dmt_ctx *ctx, int32_t layout, uint32_t it0, uint32_t it1, uint8_t *acc /* [it][n_blocks][M] */);
+/* set_accepted!(bb, i, v)  src/biblock.jl:130-135 and set_ll!(b, i, v)  src/block.jl:82-86: overwrite one history entry */
+int32_t dmt_set_accepted(dmt_ctx *ctx, int32_t layout, uint32_t iter, const uint8_t *acc /* [n_blocks][M] */);
+int32_t dmt_set_ll_history(dmt_ctx *ctx, int32_t layout, int32_t side, uint32_t iter, const double *ll /* [n_blocks][M] */);
 int32_t dmt_get_ll_history(dmt_ctx *ctx, int32_t layout, int32_t side, uint32_t it0, uint32_t it1, double *ll /* [it][n_blocks][M] */);
 /* accpt_rate numerators (src/biblock.jl:232): LOCAL accept counts per block over it0..it1 */
 int32_t dmt_accept_counts(dmt_ctx *ctx, int32_t layout, uint32_t it0, uint32_t it1, int64_t *counts /* [n_blocks] */);

@@ -166,6 +166,15 @@ blocking_sweep!(be::DBE, mcmciter::Integer) =
 enable_guiding_cache!(be::DBE, on::Bool=true) =
     check(be.se.ctx, ccall((:dmt_enable_guiding_cache, libdmt), Int32, (Ptr{Cvoid}, Int32, Int32), be.se.ctx, be.layout, on))
 
+# lanes per (chain, block) in the forward kernel: 0 = automatic (results never depend on it)
+set_fwd_lanes!(se::DeviceEnsemble, lanes::Integer) =
+    check(se.ctx, ccall((:dmt_set_fwd_lanes, libdmt), Int32, (Ptr{Cvoid}, Int32), se.ctx, lanes))
+# multi-GPU, one process per GPU: export the 64-byte handle, all-gather it (MPI.Allgather, Distributed, ...), map the peers
+p2p_export(se::DeviceEnsemble) = (h = zeros(UInt8, 64);
+    check(se.ctx, ccall((:dmt_p2p_export, libdmt), Int32, (Ptr{Cvoid}, Ptr{UInt8}), se.ctx, h)); h)
+p2p_init!(se::DeviceEnsemble, n_ranks::Integer, rank::Integer, handles::Matrix{UInt8}) =   # handles: 64 x n_ranks
+    check(se.ctx, ccall((:dmt_p2p_init, libdmt), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{UInt8}), se.ctx, n_ranks, rank, handles))
+
 # ---- parameters (src/block_ensemble.jl:242-255 -> src/biblock.jl:334-371).  The name translation of
 # src/param_names_collections.jl stays here on the host: `pnames` is its result for the target law,
 # a vector of (index into θ°) => (index into the model's parameter vector) pairs.

@@ -157,3 +157,28 @@ def test_checkpoint_resume_is_bit_exact(tmp_path):
     assert np.array_equal(se2.ctx.get_X(0), Xa) and np.array_equal(se2.ctx.get_W(0), Wa)
     assert all(np.array_equal(se2.ctx.get_ll(be.layout, 0), l) for be, l in zip(bes2, lla))
     se2.ctx.close()
+
+
+def test_history_setters_and_recompute_path_exports():
+    """set_ll!, set_accepted!, recompute_path! (exports of src/DiffusionMCMCTools.jl:38-45) through the host API"""
+    nit = 3
+    prob = configs.make_problem("fhn", 9, K=4, dt=0.005, seed=2, rho=0.9)
+    se = H.SamplingEnsemble(prob.model, recordings_of(prob), (prob.n_pts, prob.tt), seed=4, two_sided_laws=True)
+    se.init_paths()
+    be = H.BlockEnsemble(se, [(0, 1), (2, 3)], 0.9, nit)
+    H.set_obs(be); H.recompute_guiding_term(be); H.find_W_for_X(be); H.loglikhd(be)
+    H.set_accepted(be, 1, True)
+    H.set_accepted(be, 2, np.arange(2 * 9).reshape(2, 9) % 2 == 0)
+    H.set_ll(be, 1, -3.5)
+    H.set_ll(be, 2, np.full((2, 9), 7.25), side=1)
+    acc = se.ctx.get_accept_history(be.layout, 0, nit - 1)
+    assert not acc[0].any() and acc[1].all() and np.array_equal(acc[2], np.arange(18).reshape(2, 9) % 2 == 0)
+    assert np.all(se.ctx.get_ll_history(be.layout, 0, 1, 1) == -3.5) and np.all(se.ctx.get_ll_history(be.layout, 1, 2, 2) == 7.25)
+    assert np.allclose(H.accpt_rate(be, (1, 2)), [(9 + 5) / 18.0, (9 + 4) / 18.0])
+    # recompute_path!(b°, b.WW): same law on both sides => the proposal path reproduces the accepted one and its ll
+    H.recompute_path(be)
+    assert rel_err(se.ctx.get_X(1), se.ctx.get_X(0)) < 1e-12
+    assert rel_err(se.ctx.get_ll(be.layout, 1), se.ctx.get_ll(be.layout, 0)) < 1e-10
+    with pytest.raises(dmt_b200.DmtError):
+        H.set_accepted(be, nit, True)
+    se.ctx.close()
