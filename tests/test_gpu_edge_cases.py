@@ -147,4 +147,14 @@ def test_histories_and_accept_rate_bookkeeping():
     assert hist[:, 1].mean() > hist[:, 0].mean()
     st = ctx.allreduce_stats(0)
     assert st[2:].tolist() == hist[-1].sum(axis=1).tolist() and abs(st[0] - ctx.get_ll(0, 0).sum()) < 1e-9 * abs(st[0])
+    # the peer-memory all-reduce kernel with a world of one rank is the identity (several calls: sequence numbers, both parities)
+    with pytest.raises(dmt_b200.DmtError):
+        ctx.p2p_init(1, 0, np.zeros((1, 64), np.uint8))              # export first
+    h = ctx.p2p_export()
+    assert h.shape == (64,) and h.any()
+    ctx.p2p_init(1, 0, h[None, :])
+    for _ in range(3):
+        assert np.array_equal(ctx.allreduce_stats(0), st)
+    with pytest.raises(dmt_b200.DmtError):
+        ctx.p2p_init(17, 0, np.zeros((17, 64), np.uint8))
     ctx.close()
