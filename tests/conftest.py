@@ -10,12 +10,13 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu under gpurun)")
+    config.addinivalue_line("markers", "own_lanes: the test picks the forward kernel's lanes itself (not repeated per lane setting)")
 
 
 def pytest_generate_tests(metafunc):
     # every GPU test runs once per forward-kernel mapping: 1 lane per (chain, block) (the path large ensembles take), 4 lanes,
     # and automatic (8 lanes at the test sizes); results must not depend on it
-    if metafunc.definition.get_closest_marker("gpu") is not None:
+    if metafunc.definition.get_closest_marker("gpu") is not None and metafunc.definition.get_closest_marker("own_lanes") is None:
         metafunc.fixturenames.append("_fwd_lanes")
         metafunc.parametrize("_fwd_lanes", [1, 4, 0], ids=["lanes1", "lanes4", "lanes_auto"], indirect=True)
 

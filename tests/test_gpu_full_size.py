@@ -1,0 +1,103 @@
+"""BASELINE config C3 AT FULL SIZE (Lorenz, 4096 chains, 200 x 100 EM steps, 10/11 staggered blocks): the oracle cannot run
+8e7 steps per sweep in test time, so the whole ensemble is checked through size-independent properties, and a slice of it
+(three chains out of 4096, with their global random streams) is replayed call by call on the oracle."""
+import copy
+
+import numpy as np
+import pytest
+
+import dmt_b200
+from dmt_b200 import _lib, configs
+from harness import OracleEnsemble, make_ctx, rel_err
+
+pytestmark = [pytest.mark.gpu, pytest.mark.own_lanes]
+
+SLICE = slice(2501, 2504)
+
+
+@pytest.fixture(scope="module")
+def full():
+    prob = configs.named_config("c3", seed=123)
+    assert (prob.M, prob.P, prob.K, prob.steps_per_chain) == (4096, 4096, 200, 20000)
+    ctx = make_ctx(prob, seed=123, n_layouts=3)
+    ctx.set_blocks(2, [(0, prob.K - 1)], 0.0)
+    ctx.recompute_guiding_term(2, _lib.P_ONLY)
+    assert ctx.init_paths(2, 0, 50) == 0
+    yield prob, ctx
+    ctx.close()
+
+
+def test_full_size_properties(full):
+    prob, ctx = full
+    X0, W0 = ctx.get_X(0), ctx.get_W(0)
+    assert np.isfinite(X0).all() and np.isfinite(W0).all()
+    # (1) K5 o K2 = identity: the noise recovered from the initial paths under the law that made them is the noise that made them
+    ctx.find_W_for_X(2)
+    assert rel_err(ctx.get_W(0), W0) < 1e-8
+    ctx.set_W(W0, 0)
+    # (2) checksum of checksums: fetch_ll (fixed-order device tree) == sum of the per-(block, chain) values
+    ctx.loglikhd(2, 0, 0)
+    ll = ctx.get_ll(2, 0)
+    tot, per_block = ctx.fetch_ll(2, 0)
+    assert abs(tot - ll.sum()) < 1e-10 * abs(tot) and np.allclose(per_block, ll.sum(axis=1), rtol=1e-10)
+    # (3) rho = 1: the pCN proposal is the accepted path (same noise, same law), and so is its log-likelihood
+    ctx.set_rho(2, [1.0])
+    ctx.draw_proposal_path(2, 5)
+    assert np.array_equal(ctx.get_W(1), W0)
+    assert rel_err(ctx.get_X(1), X0) < 1e-11 and rel_err(ctx.get_ll(2, 1), ll) < 1e-10
+    # (4) one blocking sweep per layout: fused pass == the three separate passes; cached K1 == full backward filter
+    for lay in (0, 1):
+        ctx.set_artificial_obs(lay)
+        ctx.recompute_guiding_term(lay, _lib.P_ONLY)
+        ctx.find_W_for_X(lay); ctx.loglikhd(lay, 0, 0); ctx.draw_proposal_path(lay, 7)
+        Wa, Xp, Wp = ctx.get_W(0), ctx.get_X(1), ctx.get_W(1)
+        lla, llp, ok = ctx.get_ll(lay, 0), ctx.get_ll(lay, 1), ctx.get_success(lay)
+        assert ok.mean() > 0.999
+        ctx.find_W_loglikhd_draw(lay, 7)
+        assert np.array_equal(ctx.get_success(lay), ok)
+        assert rel_err(ctx.get_W(0), Wa) < 1e-10 and rel_err(ctx.get_ll(lay, 0), lla) < 1e-10
+        good = ok.all(axis=0)
+        assert rel_err(ctx.get_X(1)[:, :, good], Xp[:, :, good]) < 1e-9 and rel_err(ctx.get_W(1)[:, :, good], Wp[:, :, good]) < 1e-9
+        assert rel_err(ctx.get_ll(lay, 1)[:, good], llp[:, good]) < 1e-9
+        # determinism: the same call again gives the same bits
+        X1 = ctx.get_X(1)
+        ctx.find_W_loglikhd_draw(lay, 7)
+        assert np.array_equal(ctx.get_X(1), X1, equal_nan=True)
+        # guiding cache: F = F0 + Psi v reproduces the backward filter
+        kb = (40, 30)[lay]                                   # first interval of a block (c is only kept where it is read)
+        H, F, c = ctx.get_guiding_term(kb, 0, 0)
+        ctx.enable_guiding_cache(lay)
+        ctx.recompute_guiding_term(lay, _lib.P_ONLY)
+        Hc, Fc, cc = ctx.get_layout_guiding_term(lay, kb)
+        assert rel_err(Hc[:-1], H[:-1]) < 1e-10 and rel_err(Fc[:-1], F[:-1]) < 1e-9 and np.abs(cc[0] - c[0]).max() < 1e-8 * np.abs(c[0]).max()
+        ctx.enable_guiding_cache(lay, False)
+        # (5) accept bookkeeping: ll after the step is ll° where accepted, else ll; decisions follow E > -(ll° - ll)
+        ll0, ll1 = ctx.get_ll(lay, 0).copy(), ctx.get_ll(lay, 1).copy()
+        E = np.random.default_rng(lay).exponential(size=ll0.shape)
+        ctx.accept_reject_path(lay, 7, E)
+        acc = ctx.get_last_accept(lay)
+        assert np.array_equal(acc, E > -(ll1 - ll0))
+        assert np.array_equal(ctx.get_ll(lay, 0), np.where(acc, ll1, ll0))
+        assert 0.2 < acc.mean() < 0.8
+
+
+def test_slice_of_the_full_ensemble_replayed_on_the_oracle(full, orc, olib):
+    """chains 2501..2503 of 4096: same data, same global Philox counters -> the oracle reproduces the device's sweep"""
+    prob, ctx = full
+    sub = copy.copy(prob)
+    sub.M = sub.P = SLICE.stop - SLICE.start
+    sub.v, sub.xbar, sub.x0 = prob.v[:, :, SLICE].copy(), prob.xbar[:, :, SLICE].copy(), prob.x0[:, SLICE].copy()
+    ora = OracleEnsemble(orc, olib, sub, seed=123, chain_offset=SLICE.start)
+    X, W = ctx.get_X(0)[:, :, SLICE], ctx.get_W(0)[:, :, SLICE]
+    for s in (0, 1):
+        ora.set_X(s, np.ascontiguousarray(X)); ora.set_W(s, np.ascontiguousarray(W))
+    for lay, it in ((0, 11), (1, 12)):
+        ctx.blocking_sweep(lay, it)
+        ora.set_artificial_obs(lay); ora.recompute_guiding_term(lay); ora.find_W_for_X(lay); ora.loglikhd(lay); ora.draw(lay, it)
+        assert rel_err(ctx.get_W(0)[:, :, SLICE], ora.W(0)) < 1e-9
+        assert rel_err(ctx.get_X(1)[:, :, SLICE], ora.X(1)) < 1e-9 and rel_err(ctx.get_W(1)[:, :, SLICE], ora.W(1)) < 1e-9
+        assert rel_err(ctx.get_ll(lay, 0)[:, SLICE], ora.ll(lay, 0)) < 1e-9 and rel_err(ctx.get_ll(lay, 1)[:, SLICE], ora.ll(lay, 1)) < 1e-9
+        ctx.accept_reject_path(lay, it)
+        acc_o, _ = ora.accept(lay, it, layout_id=lay)
+        assert np.array_equal(ctx.get_last_accept(lay)[:, SLICE], acc_o)
+        assert rel_err(ctx.get_X(0)[:, :, SLICE], ora.X(0)) < 1e-9
