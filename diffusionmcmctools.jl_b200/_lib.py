@@ -89,6 +89,8 @@ SIGNATURES = {
     "dmt_nccl_unique_id": (C.c_int32, [_bp]),
     "dmt_comm_init": (C.c_int32, [_vp, C.c_int32, C.c_int32, _bp]),
     "dmt_allreduce_stats": (C.c_int32, [_vp, C.c_int32, _dp]),
+    "dmt_snapshot_paths_async": (C.c_int32, [_vp, C.c_int32, C.c_int32, _ip, _dp]),
+    "dmt_snapshot_wait": (C.c_int32, [_vp]),
     "dmt_set_accepted": (C.c_int32, [_vp, C.c_int32, C.c_uint32, _bp]),
     "dmt_set_ll_history": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_uint32, _dp]),
     "dmt_p2p_export": (C.c_int32, [_vp, _bp]),
@@ -274,6 +276,16 @@ class Ctx:
         X = np.empty((self.NP, self.d, self.M))
         self._ck(self.lib.dmt_get_X(self.h, side, _p(X)))
         return X
+
+    def snapshot_paths_async(self, chains, out, side=ACCEPTED):
+        """queue a copy of the paths of `chains` into out [NP, d, len(chains)] (float64, C-contiguous, ideally page-locked);
+        read `out` after snapshot_wait()"""
+        sel = np.ascontiguousarray(chains, dtype=np.int32)
+        assert out.dtype == np.float64 and out.flags.c_contiguous and out.shape == (self.NP, self.d, sel.size)
+        self._ck(self.lib.dmt_snapshot_paths_async(self.h, side, int(sel.size), sel.ctypes.data_as(_ip), _p(out)))
+
+    def snapshot_wait(self):
+        self._ck(self.lib.dmt_snapshot_wait(self.h))
 
     def set_W(self, W, side=ACCEPTED):
         self._ck(self.lib.dmt_set_W(self.h, side, _p(_f64(W, (self.S, self.dw, self.M)))))

@@ -153,6 +153,11 @@ struct dmt_ctx {
     bool p2p_ready = false;
     int n_ranks = 1;
     int fwd_lanes = 0;       // dmt_set_fwd_lanes: 0 = automatic
+    // thinned path saving (dmt_snapshot_paths_async): staging buffer + copy stream
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_gathered = nullptr, ev_copied = nullptr;
+    DevBuf<double> d_snap;
+    DevBuf<int> d_snap_sel;
     bool tma_ok = false;     // P == M with the identity pset map: the TMA fast path of fwd_kernel is usable
     bool parP_mixed = false; // a masked swap_PP! made the law parity chain-dependent
 
@@ -621,6 +626,9 @@ int32_t dmt_destroy(dmt_ctx *ctx) {
         for (int r = 0; r < ctx->p2p.world; r++)
             if (r != ctx->p2p.rank && ctx->p2p.peer[r]) cudaIpcCloseMemHandle(ctx->p2p.peer[r]);
     if (ctx->p2p_local) cudaFree(ctx->p2p_local);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->ev_gathered) cudaEventDestroy(ctx->ev_gathered);
+    if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
     delete ctx;
     return DMT_OK;
@@ -801,6 +809,38 @@ int32_t dmt_set_X(dmt_ctx *ctx, int32_t side, const double *X) { return guarded(
 int32_t dmt_get_X(dmt_ctx *ctx, int32_t side, double *X) { return guarded(ctx, [&] { xfer_paths(ctx, side, X, true, false); }); }
 int32_t dmt_set_W(dmt_ctx *ctx, int32_t side, const double *W) { return guarded(ctx, [&] { xfer_paths(ctx, side, (double *)W, false, true); }); }
 int32_t dmt_get_W(dmt_ctx *ctx, int32_t side, double *W) { return guarded(ctx, [&] { xfer_paths(ctx, side, W, false, false); }); }
+
+int32_t dmt_snapshot_paths_async(dmt_ctx *ctx, int32_t side, int32_t n_sel, const int32_t *chains, double *host_out) {
+    return guarded(ctx, [&] {
+        check_side(ctx, side);
+        REQUIRE(n_sel >= 1 && chains && host_out, DMT_ERR_ARG, "bad snapshot arguments");
+        for (int i = 0; i < n_sel; i++) REQUIRE(chains[i] >= 0 && chains[i] < ctx->M, DMT_ERR_ARG, "chain index out of range");
+        if (!ctx->copy_stream) {
+            CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&ctx->ev_gathered, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming));
+            CK(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
+        }
+        const size_t n = (size_t)ctx->NP * ctx->D * n_sel;
+        // the staging buffer is reused: the gather may not start before the previous snapshot has left the device
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied, 0));
+        if (ctx->d_snap.n < n) { CK(cudaStreamSynchronize(ctx->copy_stream)); ctx->d_snap.alloc(n, false); }
+        if (ctx->d_snap_sel.n < (size_t)n_sel) { CK(cudaStreamSynchronize(ctx->copy_stream)); ctx->d_snap_sel.alloc(n_sel, false); }
+        CK(cudaMemcpyAsync(ctx->d_snap_sel.p, chains, sizeof(int) * n_sel, cudaMemcpyHostToDevice, ctx->stream));
+        gather_X_kernel<<<dim3((n_sel + 63) / 64, ctx->K), 64, 0, ctx->stream>>>(ctx->dev, side, ctx->D, ctx->d_snap_sel.p, n_sel, ctx->d_snap.p);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev_gathered, ctx->stream));
+        // the copy runs on its own stream: the compute stream goes on with the next sweep while the paths travel
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_gathered, 0));
+        CK(cudaMemcpyAsync(host_out, ctx->d_snap.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_stream));
+        CK(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
+    });
+}
+int32_t dmt_snapshot_wait(dmt_ctx *ctx) {
+    return guarded(ctx, [&] {
+        if (ctx->copy_stream) CK(cudaStreamSynchronize(ctx->copy_stream));
+    });
+}
 
 int32_t dmt_init_paths(dmt_ctx *ctx, int32_t layout, uint32_t iter0, int32_t max_tries, int32_t *n_failed) {
     return guarded(ctx, [&] {

@@ -957,6 +957,21 @@ __global__ void xfer_X_kernel(const DevCtx cx, int side, int D, double *nat, int
         }
     }
 }
+// paths of a FEW chains (thinned path saving): device tiles -> out[point][dim][n_sel], parity-resolved like xfer_X_kernel
+__global__ void gather_X_kernel(const DevCtx cx, int side, int D, const int *sel, int n_sel, double *out) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+    if (s >= n_sel) return;
+    const size_t M = cx.M;
+    const int c = sel[s];
+    const int sl = side ^ cx.parX[(size_t)k * M + c];
+    const int nst = cx.nsteps[k], p0 = cx.pt0[k], t0 = cx.tile0[k];
+    for (int i = 0; i < D; i++) {
+        out[((size_t)p0 * D + i) * n_sel + s] = cx.X0[(size_t)sl * cx.X0buf + ((size_t)k * D + i) * M + c];
+        for (int j = 0; j < nst; j++)
+            out[((size_t)(p0 + j + 1) * D + i) * n_sel + s] =
+                cx.X[(size_t)sl * cx.Xbuf + (((size_t)(t0 + (j >> 2)) * D + i) * M + c) * 4 + (j & 3)];
+    }
+}
 __global__ void xfer_W_kernel(const DevCtx cx, int side, int DW, double *nat, int dir) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
     if (c >= cx.M) return;

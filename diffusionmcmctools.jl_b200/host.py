@@ -354,6 +354,39 @@ def set_proposal_law(be, theta_o, pnames, critical_change=None, skip=0):
     be.ctx.set_proposal_law(be.layout, critical_change, skip)
 
 
+# ---- thinned path saving (docs/src/tutorials/biblock/smoothing.md:55: `paths[i ÷ 400] = deepcopy(bb.b.XX)`) ------------------------
+class PathSaver:
+    """Keeps the accepted paths of a few recordings every `every` iterations without stalling the sampler: each save is an
+    asynchronous device-side gather + device-to-host copy on a second stream into page-locked memory.
+        saver = PathSaver(se, chains=[0, 5], every=400);  in the loop: saver(i);  at the end: saver.paths() -> [(i, X[NP, d, n]), ...]"""
+
+    def __init__(self, se, chains, every=1, side=0):
+        self.se, self.chains, self.every, self.side = se, np.asarray(chains, dtype=np.int32), int(every), side
+        self._saved = []
+
+    def _buffer(self):
+        shape = (self.se.ctx.NP, self.se.ctx.d, self.chains.size)
+        try:
+            import torch
+            t = torch.empty(shape, dtype=torch.float64, pin_memory=True)
+            return t, t.numpy()
+        except Exception:
+            a = np.empty(shape)
+            return a, a
+
+    def __call__(self, mcmciter):
+        if mcmciter % self.every:
+            return False
+        keep, arr = self._buffer()
+        self.se.ctx.snapshot_paths_async(self.chains, arr, self.side)
+        self._saved.append((mcmciter, keep, arr))
+        return True
+
+    def paths(self):
+        self.se.ctx.snapshot_wait()
+        return [(i, arr) for i, _, arr in self._saved]
+
+
 # ---- checkpoint / resume (not in the reference, which keeps its state in Julia objects; SURVEY §5 / §8f item 3) -------------
 def save_state(se, path, layouts=()):
     """Everything needed to continue a run bit-exactly: accepted and proposal X and W (resolved through the parity bits), the

@@ -103,6 +103,13 @@ int32_t dmt_set_rho(dmt_ctx *ctx, int32_t layout, const double *rho);
 
 /* ---- paths ---------------------------------------------------------------------------------------------------- */
 int32_t dmt_set_start(dmt_ctx *ctx, const double *x0 /* [d][M] */); /* XX[1].x[1] of u and u° */
+/* Thinned path saving (the tutorials keep one path every few hundred iterations, docs/src/tutorials/biblock/smoothing.md:55):
+ * the paths of the n_sel listed chains, host_out[point][dim][n_sel], as they are at this point of the call sequence.  The call
+ * returns at once: a gather kernel runs in order on the context's stream, the device-to-host copy on a second stream, so the
+ * next sweeps overlap the transfer (pass page-locked memory for a truly asynchronous copy).  host_out may be read after
+ * dmt_snapshot_wait; a further snapshot may be queued before that (it waits for the staging buffer on the device). */
+int32_t dmt_snapshot_paths_async(dmt_ctx *ctx, int32_t side, int32_t n_sel, const int32_t *chains, double *host_out);
+int32_t dmt_snapshot_wait(dmt_ctx *ctx);
 /* init_paths! (src/sampling_unit.jl:83-87): fresh-noise forward_guide! of the whole path into u, retried per chain
  * until success (at most max_tries), then u° = deepcopy(u) (src/sampling_pair.jl:51). Needs the guiding term of a
  * single-terminal-block layout `layout`.  n_failed: chains still failing. */

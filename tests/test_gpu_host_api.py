@@ -182,3 +182,32 @@ def test_history_setters_and_recompute_path_exports():
     with pytest.raises(dmt_b200.DmtError):
         H.set_accepted(be, nit, True)
     se.ctx.close()
+
+
+def test_path_saver_snapshots_are_ordered_and_asynchronous():
+    """PathSaver / dmt_snapshot_paths_async: a snapshot holds the paths as they were when it was queued, even though the next
+    sweeps are enqueued before anyone waits for it (tutorial: save a path every few hundred iterations)"""
+    layouts = [([(0, 2), (3, 5)], 0.5), ([(0, 5)], 0.5)]
+    prob = configs.make_problem("lorenz", 70, K=6, dt=0.01, seed=8, layouts=layouts)
+    se = H.SamplingEnsemble(prob.model, recordings_of(prob), (prob.n_pts, prob.tt), seed=6, two_sided_laws=False)
+    se.init_paths()
+    bes = [H.BlockEnsemble(se, r, rho, 0) for r, rho in layouts]
+    chains = [3, 69, 0, 41]
+    saver = H.PathSaver(se, chains, every=2)
+    truth = {}
+    for i in range(6):
+        for be in bes:
+            H.blocking_sweep(be, i)
+            H.accept_reject_proposal_path(be, i)
+        took = saver(i)
+        assert took == (i % 2 == 0)
+        if took:                              # a synchronous copy right after the snapshot was queued, for comparison
+            truth[i] = se.ctx.get_X(0)[:, :, chains].copy()
+    got = saver.paths()
+    assert [i for i, _ in got] == [0, 2, 4]
+    for i, X in got:
+        assert X.shape == (se.ctx.NP, 3, 4) and np.array_equal(X, truth[i])
+    assert not np.array_equal(got[0][1], got[2][1])          # the chain moved in between
+    with pytest.raises(dmt_b200.DmtError):
+        se.ctx.snapshot_paths_async([70], np.empty((se.ctx.NP, 3, 1)))
+    se.ctx.close()
