@@ -235,7 +235,7 @@ def gpu_arm(a):
                 ctx.find_W_and_loglikhd(l); mark()
         if k1_each_step:  # new parameters (theta jitter keeps the data valid), aux laws re-linearised on the device, K1, then the path update
             ctx.set_params(theta_dev_host, side=0, stores=1)
-            ctx.set_aux_linearised(prob.xbar, side=0, store=_lib.STORE_PP); mark()
+            ctx.set_aux_linearised(None, side=0, store=_lib.STORE_PP); mark()   # same points, new theta: re-linearised on the device
             ctx.recompute_guiding_term(l, _lib.P_ONLY); mark()
         if not fused:
             ctx.draw_proposal_path(l, it); mark()

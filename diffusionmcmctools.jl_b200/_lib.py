@@ -226,7 +226,11 @@ class Ctx:
         self._ck(self.lib.dmt_set_aux(self.h, side, store, k0, k1, _p(B), _p(beta), _p(atil)))
 
     def set_aux_linearised(self, xbar, side=ACCEPTED, store=STORE_PP, k0=None, k1=None):
+        """xbar = None: re-linearise at the points uploaded last for this store (only theta changed)"""
         k0, k1 = self._krange(k0, k1)
+        if xbar is None:
+            self._ck(self.lib.dmt_set_aux_linearised(self.h, side, store, k0, k1, None))
+            return
         xb = self._bc(xbar, (self.d,), k1 - k0 + 1)
         self._ck(self.lib.dmt_set_aux_linearised(self.h, side, store, k0, k1, _p(xb)))
 

@@ -153,6 +153,8 @@ struct dmt_ctx {
     bool p2p_ready = false;
     int n_ranks = 1;
     int fwd_lanes = 0;       // dmt_set_fwd_lanes: 0 = automatic
+    DevBuf<double> d_xbar[2]; // linearisation points [K][D][P] per store, kept so that a parameter update re-linearises on the device
+    std::vector<char> xbar_set[2];
     // thinned path saving (dmt_snapshot_paths_async): staging buffer + copy stream
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_gathered = nullptr, ev_copied = nullptr;
@@ -683,10 +685,15 @@ int32_t dmt_set_aux_linearised(dmt_ctx *ctx, int32_t side, int32_t store, int32_
         check_law_side(ctx, side); check_range(ctx, k0, k1);
         if (side == 0) invalidate_caches(ctx); // the accepted laws change: cached guiding terms are stale
         REQUIRE(store == 0 || store == 1, DMT_ERR_ARG, "store must be 0 (PP) or 1 (PPb)");
-        REQUIRE(xbar, DMT_ERR_ARG, "null xbar");
-        const size_t n = (size_t)(k1 - k0 + 1) * ctx->D * ctx->P;
-        double *tmp = ctx->scratch(n);
-        CK(cudaMemcpyAsync(tmp, xbar, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        const size_t per_k = (size_t)ctx->D * ctx->P, n = (size_t)(k1 - k0 + 1) * per_k;
+        if (ctx->d_xbar[store].n < (size_t)ctx->K * per_k) { ctx->d_xbar[store].alloc((size_t)ctx->K * per_k); ctx->xbar_set[store].assign(ctx->K, 0); }
+        double *tmp = ctx->d_xbar[store].p + (size_t)k0 * per_k;
+        if (xbar) { // new linearisation points: keep them on the device
+            CK(cudaMemcpyAsync(tmp, xbar, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            for (int k = k0; k <= k1; k++) ctx->xbar_set[store][k] = 1;
+        } else {    // NULL: re-linearise at the points of the last call (only theta changed)
+            for (int k = k0; k <= k1; k++) REQUIRE(ctx->xbar_set[store][k], DMT_ERR_STATE, "no linearisation points stored for this interval yet");
+        }
         dim3 grid = pset_grid(ctx, k1 - k0 + 1, 128);
 #define DMT_CASE(MID)                                                                                              \
     case MID: aux_linearise_kernel<Model<MID>><<<grid, 128, 0, ctx->stream>>>(ctx->dev, side, store, k0, k1, tmp); break;

@@ -349,8 +349,9 @@ def set_proposal_law(be, theta_o, pnames, critical_change=None, skip=0):
     be.ctx.equalize_laws(3)                   # GP.equalize_obs_params! / equalize_law_params!  (src/biblock.jl:384-443)
     be.ctx.set_params(th, side=_lib.PROPOSAL, stores=3)
     if critical_change and se.xbar is not None:
-        be.ctx.set_aux_linearised(se.xbar, side=_lib.PROPOSAL, store=_lib.STORE_PP)
-        be.ctx.set_aux_linearised(se.xbar_blocking, side=_lib.PROPOSAL, store=_lib.STORE_PPB)
+        # the linearisation points did not move, only theta did: they are already on the device (uploaded by the constructor)
+        be.ctx.set_aux_linearised(None, side=_lib.PROPOSAL, store=_lib.STORE_PP)
+        be.ctx.set_aux_linearised(None, side=_lib.PROPOSAL, store=_lib.STORE_PPB)
     be.ctx.set_proposal_law(be.layout, critical_change, skip)
 
 

@@ -86,7 +86,9 @@ int32_t dmt_version(void);
 int32_t dmt_set_params(dmt_ctx *ctx, int32_t side, int32_t store_mask, int32_t k0, int32_t k1, const double *theta);
 /* auxiliary law coefficients, host-evaluated: B[k][d*d][P], beta[k][d][P], atil[k][d*d][P] for k = k0..k1 */
 int32_t dmt_set_aux(dmt_ctx *ctx, int32_t side, int32_t store, int32_t k0, int32_t k1, const double *B, const double *beta, const double *atil);
-/* auxiliary law = Jacobian linearisation of the target at xbar[k][d][P] using the law's current theta (device-evaluated) */
+/* auxiliary law = Jacobian linearisation of the target at xbar[k][d][P] using the law's current theta (device-evaluated).
+ * The points are kept on the device per store: xbar = NULL re-linearises at the points of the last call, so a parameter
+ * update (dmt_set_params, then this) uploads npar x P doubles instead of K x d x P. */
 int32_t dmt_set_aux_linearised(dmt_ctx *ctx, int32_t side, int32_t store, int32_t k0, int32_t k1, const double *xbar);
 /* observation at the END of interval k (LinearGsnObs): L[k][m*d][P], Sigma[k][m*m][P], v[k][m][P] */
 int32_t dmt_set_obs(dmt_ctx *ctx, int32_t side, int32_t k0, int32_t k1, const double *L, const double *Sigma, const double *v);

@@ -158,3 +158,33 @@ def test_histories_and_accept_rate_bookkeeping():
     with pytest.raises(dmt_b200.DmtError):
         ctx.p2p_init(17, 0, np.zeros((17, 64), np.uint8))
     ctx.close()
+
+
+def test_relinearise_on_device_equals_fresh_upload():
+    """dmt_set_aux_linearised(xbar = NULL): a parameter update re-linearises at the stored points instead of uploading them again"""
+    prob = configs.make_problem("lorenz", 12, K=4, dt=0.01, seed=3, rho=0.5)
+    a, b = make_ctx(prob, seed=1), make_ctx(prob, seed=1)
+    th = np.repeat(prob.theta[:, None], prob.P, axis=1)
+    th[1] *= 1.0 + 0.02 * np.arange(prob.P)                 # a different rho for every recording
+    for ctx, xb in ((a, prob.xbar), (b, None)):
+        ctx.set_params(th, side=0, stores=3)
+        ctx.set_aux_linearised(xb, side=0, store=_lib.STORE_PP)
+        ctx.recompute_guiding_term(0, _lib.P_ONLY)
+    for k in range(prob.K):
+        for x, y in zip(a.get_guiding_term(k, 0, 0), b.get_guiding_term(k, 0, 0)):
+            assert np.array_equal(x, y, equal_nan=True)
+    H0, _, _ = make_ctx_guiding(prob)
+    assert not np.array_equal(H0[:-1], a.get_guiding_term(1, 0, 0)[0][:-1])         # the parameter change did reach the auxiliary law
+    c = dmt_b200.Ctx(prob.model, prob.n_pts, prob.tt, prob.M, prob.P, obs_dim=prob.m)
+    with pytest.raises(dmt_b200.DmtError):
+        c.set_aux_linearised(None)                                          # nothing stored yet
+    for ctx in (a, b, c):
+        ctx.close()
+
+
+def make_ctx_guiding(prob):
+    ctx = make_ctx(prob, seed=1)
+    ctx.recompute_guiding_term(0, _lib.P_ONLY)
+    out = ctx.get_guiding_term(1, 0, 0)
+    ctx.close()
+    return out
