@@ -186,18 +186,34 @@ def gpu_arm(a):
         for l in range(nlay):
             ctx.enable_guiding_cache(l)
     allreduce_kind = "none"
-    if world > 1 and not os.environ.get("DMT_NO_P2P"):
-        # the small stats all-reduce as the library's own one-shot kernel over NVLink peer memory (dmt_p2p_init)
-        mine = torch.from_numpy(ctx.p2p_export().copy()).to(dev)
-        allh = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(allh, mine)
-        ctx.p2p_init(world, rank, np.stack([h.cpu().numpy() for h in allh]))
-        allreduce_kind = "p2p kernel (NVLink peer memory)"
-    elif world > 1:  # native NCCL communicator inside libdmt
-        uid = torch.from_numpy(ctx.nccl_unique_id() if rank == 0 else np.zeros(128, np.uint8)).to(dev)
-        dist.broadcast(uid, 0)
-        ctx.comm_init(world, rank, uid.cpu().numpy())
-        allreduce_kind = "ncclAllReduce"
+    if world > 1:
+        # the small stats all-reduce as the library's own one-shot kernel over NVLink peer memory (dmt_p2p_init); if any rank cannot
+        # map its peers (IPC not permitted), every rank falls back to the NCCL communicator inside libdmt
+        ok = torch.ones(1, device=dev)
+        if os.environ.get("DMT_NO_P2P"):
+            ok.zero_()
+        else:
+            try:
+                mine = torch.from_numpy(ctx.p2p_export().copy()).to(dev)
+            except Exception:
+                mine = torch.zeros(64, dtype=torch.uint8, device=dev)
+                ok.zero_()
+            allh = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allh, mine)
+            if ok.item():
+                try:
+                    ctx.p2p_init(world, rank, np.stack([h.cpu().numpy() for h in allh]))
+                except Exception:
+                    ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item():
+            allreduce_kind = "p2p kernel (NVLink peer memory)"
+        else:
+            ctx.p2p_disable()
+            uid = torch.from_numpy(ctx.nccl_unique_id() if rank == 0 else np.zeros(128, np.uint8)).to(dev)
+            dist.broadcast(uid, 0)
+            ctx.comm_init(world, rank, uid.cpu().numpy())
+            allreduce_kind = "ncclAllReduce"
     stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
 
     fused = blocking and not a.separate  # find_W_for_X! + loglikhd! + draw_proposal_path! in one pass (dmt_find_W_loglikhd_draw)

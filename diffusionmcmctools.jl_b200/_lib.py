@@ -95,6 +95,7 @@ SIGNATURES = {
     "dmt_set_ll_history": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_uint32, _dp]),
     "dmt_p2p_export": (C.c_int32, [_vp, _bp]),
     "dmt_p2p_init": (C.c_int32, [_vp, C.c_int32, C.c_int32, _bp]),
+    "dmt_p2p_disable": (C.c_int32, [_vp]),
 }
 
 _lib = None
@@ -464,6 +465,9 @@ class Ctx:
         handles = np.ascontiguousarray(handles, dtype=np.uint8)
         assert handles.shape == (n_ranks, 64)
         self._ck(self.lib.dmt_p2p_init(self.h, n_ranks, rank, handles.ctypes.data_as(_bp)))
+
+    def p2p_disable(self):
+        self._ck(self.lib.dmt_p2p_disable(self.h))
 
     def allreduce_stats(self, layout):
         out = np.empty(2 + self.layout_nb[layout])

@@ -1267,6 +1267,9 @@ int32_t dmt_p2p_init(dmt_ctx *ctx, int32_t n_ranks, int32_t rank, const uint8_t 
         ctx->p2p_ready = true;
     });
 }
+int32_t dmt_p2p_disable(dmt_ctx *ctx) {
+    return guarded(ctx, [&] { ctx->p2p_ready = false; });
+}
 int32_t dmt_allreduce_stats(dmt_ctx *ctx, int32_t layout, double *out) {
     return guarded(ctx, [&] {
         Layout &L = layout_of(ctx, layout);

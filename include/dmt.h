@@ -222,6 +222,7 @@ int32_t dmt_comm_init(dmt_ctx *ctx, int32_t n_ranks, int32_t rank, const uint8_t
  * all ranks) — no NCCL call on the path.  One process per GPU (IPC handles cannot be opened by the exporting process). */
 int32_t dmt_p2p_export(dmt_ctx *ctx, uint8_t *handle64);
 int32_t dmt_p2p_init(dmt_ctx *ctx, int32_t n_ranks, int32_t rank, const uint8_t *handles /* [n_ranks][64] */);
+int32_t dmt_p2p_disable(dmt_ctx *ctx); /* back to dmt_comm_init's communicator (e.g. another rank could not map its peers) */
 /* out[0]=sum ll, out[1]=sum ll°, out[2..2+n_blocks)=accept counts of the last accept step, summed over ranks */
 int32_t dmt_allreduce_stats(dmt_ctx *ctx, int32_t layout, double *out /* [2+n_blocks] */);
 
