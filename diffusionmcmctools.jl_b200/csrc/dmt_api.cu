@@ -63,7 +63,11 @@ template <class T> struct DevBuf {
         n = count;
         if (count) {
             CK(cudaMalloc(&p, count * sizeof(T)));
-            if (zero) CK(cudaMemset(p, 0, count * sizeof(T)));
+            if (zero) { // the memset runs on the legacy stream, which the contexts' non-blocking streams do NOT order against:
+                        // wait for it here, or the first kernels on ctx->stream may see (or be overwritten by) the zero fill
+                CK(cudaMemsetAsync(p, 0, count * sizeof(T), cudaStreamLegacy));
+                CK(cudaStreamSynchronize(cudaStreamLegacy));
+            }
         }
     }
     void release() {

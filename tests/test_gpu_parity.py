@@ -419,9 +419,13 @@ def test_lanes_per_chain_do_not_change_any_result(name):
         out.append((ctx.get_X(0), ctx.get_W(0), ctx.get_X(1), ctx.get_W(1), ctx.get_ll(0, 0), ctx.get_ll(0, 1),
                     ctx.get_accept_history(0, 0, 2)))
         ctx.close()
-    for o in out[1:]:
-        for a, b in zip(out[0], o):
-            assert np.array_equal(a, b, equal_nan=True)
+    names = ("X", "W", "X_prop", "W_prop", "ll", "ll_prop", "accept history")
+    for lanes, o in zip((2, 4, 8), out[1:]):
+        for nm, a, b in zip(names, out[0], o):
+            if not np.array_equal(a, b, equal_nan=True):
+                bad = np.argwhere(~((a == b) | (np.isnan(a) & np.isnan(b)))) if a.dtype != bool else np.argwhere(a != b)
+                raise AssertionError("%s differs between 1 and %d lanes at %d places, first %s: %r vs %r; chains %s" % (
+                    nm, lanes, len(bad), bad[0], a[tuple(bad[0])], b[tuple(bad[0])], sorted(set(bad[:, -1].tolist()))[:10]))
     with pytest.raises(dmt_b200.DmtError):
         c = make_ctx(prob, seed=1)
         try:
