@@ -431,6 +431,7 @@ void rebuild_ppb_store(dmt_ctx *c) {
     if (t0 == c->ppb_tile0 && nt == c->NTb) return;
     c->ppb_tile0 = t0;
     c->NTb = nt;
+    CK(cudaStreamSynchronize(c->stream)); // kernels in flight still read the old map / the old store
     CK(cudaMemcpy(c->d_ppb_tile0.p, t0.data(), sizeof(int) * c->K, cudaMemcpyHostToDevice));
     for (int s = 0; s < (c->cfg.two_sided_laws ? 2 : 1); s++) {
         c->d_G[s][1].alloc((size_t)std::max(nt, 1) * c->NG * c->P * 4);
@@ -444,6 +445,7 @@ void rebuild_ppb_store(dmt_ctx *c) {
                 for (int q = 0; q < (c->nsteps[k] + 3) / 4; q++) kt[t0[k] + q] = k;
         c->d_k_of_ppbtile.alloc(kt.size());
         CK(cudaMemcpy(c->d_k_of_ppbtile.p, kt.data(), sizeof(int) * kt.size(), cudaMemcpyHostToDevice));
+        CK(cudaStreamSynchronize(cudaStreamLegacy)); // pageable H2D copies return before the DMA lands; ctx->stream does not order against them
         invalidate_caches(c);
     }
 }
@@ -567,6 +569,7 @@ int32_t dmt_create(const dmt_config *cfg, const int32_t *n_pts, const double *tt
         CK(cudaMemcpy(c->d_pset.p, pset.data(), sizeof(int) * c->M, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(c->d_dt.p, dt.data(), sizeof(double) * dt.size(), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(c->d_sqdt.p, sq.data(), sizeof(double) * sq.size(), cudaMemcpyHostToDevice));
+        CK(cudaStreamSynchronize(cudaStreamLegacy)); // pageable H2D copies return before the DMA lands; ctx->stream does not order against them
 
         // ---- SoA containers (SamplingPair: accepted + proposal buffers)
         const size_t M = c->M, P = c->P, NT = c->NT;
