@@ -20,6 +20,18 @@ def _bucket_key(rec):
             np.asarray(rec["L"], dtype=np.float64).tobytes(), np.asarray(rec["Sigma"], dtype=np.float64).tobytes())
 
 
+def bucket_recordings(recordings):
+    """recording ids grouped by (model, time grid, observation operator), buckets in order of first appearance"""
+    keys, members = {}, []
+    for r, rec in enumerate(recordings):
+        k = _bucket_key(rec)
+        if k not in keys:
+            keys[k] = len(members)
+            members.append([])
+        members[keys[k]].append(r)
+    return members
+
+
 class HeterogeneousEnsemble:
     """recordings: list of dicts, one per recording, with
          model (id), theta [npar], L [m, d], Sigma [m, m], v [K, m], x0 [d], xbar [K, d], tts = (n_pts [K], tt [sum n_pts]).
@@ -27,13 +39,7 @@ class HeterogeneousEnsemble:
     bucket b in ascending order and `where[r] = (bucket, index inside it)`."""
 
     def __init__(self, recordings, *, seed=0, device=0, two_sided_laws=True, max_layouts=8, artificial_noise=1e-11):
-        keys, self.members = {}, []
-        for r, rec in enumerate(recordings):
-            k = _bucket_key(rec)
-            if k not in keys:
-                keys[k] = len(self.members)
-                self.members.append([])
-            self.members[keys[k]].append(r)
+        self.members = bucket_recordings(recordings)
         self.where = {r: (b, i) for b, m in enumerate(self.members) for i, r in enumerate(m)}
         self.buckets = []
         off = 0

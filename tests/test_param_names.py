@@ -75,3 +75,15 @@ def test_obs_updates_are_keyed_by_interval():
     # block 0 = intervals 0,(1 as P_last/P_excl); block 1 = 2,3
     assert pa.obs_updates() == [{1: ((1, 1),), 3: ((1, 1), (0, 0))}]
     assert pa.is_critical()
+
+
+def test_heterogeneous_recordings_are_bucketed_by_model_grid_and_observation_operator():
+    from dmt_b200 import hetero
+    tt_a = (np.array([3, 3], np.int32), np.array([0.0, 0.05, 0.1, 0.1, 0.15, 0.2]))
+    tt_b = (np.array([3, 3], np.int32), np.array([0.0, 0.04, 0.1, 0.1, 0.16, 0.2]))          # same counts, different grid
+    L1, L2, S = np.array([[1.0, 0.0]]), np.array([[0.0, 1.0]]), np.array([[0.1]])
+    mk = lambda model, tts, L: dict(model=model, tts=tts, L=L, Sigma=S)
+    recs = [mk(_lib.FHN, tt_a, L1), mk(_lib.LV, tt_a, L1), mk(_lib.FHN, tt_b, L1), mk(_lib.FHN, tt_a, L1), mk(_lib.FHN, tt_a, L2),
+            mk(_lib.LV, tt_a, L1), mk(_lib.FHN, tt_b, L1)]
+    assert hetero.bucket_recordings(recs) == [[0, 3], [1, 5], [2, 6], [4]]
+    assert hetero.bucket_recordings([]) == []
