@@ -13,7 +13,9 @@
  *   - every function returns int32 status (DMT_OK == 0); no C++ exception crosses the boundary; dmt_last_error()
  *     gives the message.  A numerical path failure is NOT an error: the chain's success flag is 0 and its ll is -Inf
  *     (mirrors src/block.jl:163,181 and src/biblock.jl:81-82).
- *   - all pointers are caller-owned HOST pointers, copied during the call, never retained (Julia-GC safe).
+ *   - all pointers are caller-owned HOST pointers, copied during the call, never retained (Julia-GC safe).  The one
+ *     exception is the output buffer of dmt_snapshot_paths_async, which the library writes until dmt_snapshot_wait returns
+ *     (keep it alive and unmoved until then: GC.@preserve / page-locked memory).
  *   - bulk host arrays are structure-of-arrays with the chain (or parameter-set) index FASTEST:
  *       X[point][dim][chain], W[step][dw][chain], theta[par][pset], B[k][row*d+col][pset], ...
  *     "point" runs over the concatenated per-interval grids (interval k has n_k points; boundary points are stored
