@@ -278,3 +278,34 @@ def test_accept_truth_table(orc, olib):
         assert np.array_equal(hist, [ll, llo], equal_nan=True)      # saved BEFORE swap_ll!  (src/biblock.jl:125-126)
         if acc:
             assert bb.ll[0] == llo or (np.isnan(llo) and np.isnan(bb.ll[0]))
+
+
+def test_rk4_on_the_grid_is_closer_to_the_ode_than_an_adaptive_54_solver_at_default_tolerances(orc, olib):
+    """The known deviation from upstream: GuidedProposals integrates (H, F, c) with an adaptive 5(4) Runge-Kutta
+    pair at OrdinaryDiffEq's default tolerances (reltol 1e-3, abstol 1e-6) and interpolates onto the path grid; this repo steps
+    classical RK4 on the grid itself.  Neither can be compared with the other here (no Julia), but both can be compared with a
+    tight solution of the ODE: the grid RK4 must be far inside the error band of a 5(4) pair run at those tolerances, so
+    the difference a user would see against upstream is upstream's own tolerance, not this discretisation."""
+    th = np.array(THETA[2])
+    grid = tau_grid(0.0, 0.1, 1e-3)
+    P = orc.Pair(olib, orc.LORENZ, [len(grid)], grid, 2)
+    Bm, beta, at = orc.linearise(olib, orc.LORENZ, th, XREF[2])
+    L = np.array([[1.0, 0, 0], [0, 1.0, 0]]); Sig = 0.5 * np.eye(2); v = np.array([1.2, -1.1])
+    P.set_theta(th); P.set_aux(0, Bm, beta, at); P.set_obs(0, L, Sig, v)
+    P.recompute_guiding_term(P.biblock(0, 0, True), 0)
+    H, F, c = P.get_HFc(0, 0, 0)
+    rk4 = np.concatenate([H.reshape(-1, 9), F, c[:, None]], axis=1)
+    Si = np.linalg.inv(Sig)
+    y_T = np.concatenate([(L.T @ Si @ L).ravel(), L.T @ Si @ v, [0.5 * (2 * np.log(2 * np.pi) + np.linalg.slogdet(Sig)[1] + v @ Si @ v)]])
+
+    def rhs(t, y):
+        Hm = y[:9].reshape(3, 3); Fv = y[9:12]
+        return np.concatenate([(-Bm.T @ Hm - Hm @ Bm + Hm @ at @ Hm).ravel(), -Bm.T @ Fv + Hm @ at @ Fv + Hm @ beta,
+                               [beta @ Fv + 0.5 * Fv @ at @ Fv - 0.5 * np.trace(Hm @ at)]])
+    tight = solve_ivp(rhs, [0.1, 0.0], y_T, method="DOP853", rtol=1e-13, atol=1e-14, t_eval=grid[::-1]).y[:, ::-1].T
+    loose = solve_ivp(rhs, [0.1, 0.0], y_T, method="RK45", rtol=1e-3, atol=1e-6, t_eval=grid[::-1]).y[:, ::-1].T   # a 5(4) pair + interpolant
+    scale = np.abs(tight).max(axis=0)
+    err_rk4 = (np.abs(rk4 - tight) / scale).max()
+    err_loose = (np.abs(loose - tight) / scale).max()
+    assert err_rk4 < 1e-6
+    assert err_loose > 30 * err_rk4, (err_rk4, err_loose)
