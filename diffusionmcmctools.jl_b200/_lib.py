@@ -49,7 +49,7 @@ SIGNATURES = {
     "dmt_set_aux": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _dp]),
     "dmt_set_aux_linearised": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _dp]),
     "dmt_set_obs": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _dp]),
-    "dmt_equalize_laws": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32]),
+    "dmt_equalize_laws": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, _ip]),
     "dmt_set_blocks": (C.c_int32, [_vp, C.c_int32, C.c_int32, _ip, _ip, _dp, _bp, C.c_int32]),
     "dmt_set_rho": (C.c_int32, [_vp, C.c_int32, _dp]),
     "dmt_set_start": (C.c_int32, [_vp, _dp]),
@@ -83,8 +83,11 @@ SIGNATURES = {
     "dmt_upload_guiding_term": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _dp]),
     "dmt_enable_guiding_cache": (C.c_int32, [_vp, C.c_int32, C.c_int32]),
     "dmt_set_fwd_lanes": (C.c_int32, [_vp, C.c_int32]),
+    "dmt_set_bwd_mode": (C.c_int32, [_vp, C.c_int32]),
+    "dmt_get_X_chains": (C.c_int32, [_vp, C.c_int32, C.c_int32, _ip, _dp]),
+    "dmt_get_W_chains": (C.c_int32, [_vp, C.c_int32, C.c_int32, _ip, _dp]),
     "dmt_get_layout_guiding_term": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _dp]),
-    "dmt_debug_normals": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, _dp]),
+    "dmt_debug_normals": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, _dp]),
     "dmt_debug_exponentials": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, _dp]),
     "dmt_nccl_unique_id": (C.c_int32, [_bp]),
     "dmt_comm_init": (C.c_int32, [_vp, C.c_int32, C.c_int32, _bp]),
@@ -242,8 +245,11 @@ class Ctx:
         self._ck(self.lib.dmt_set_obs(self.h, side, k0, k1, _p(L), _p(Sigma), _p(v)))
 
     def equalize_laws(self, stores=3, k0=None, k1=None):
+        """-> True when a proposal record differed from the accepted one (GP.equalize_*'s return value, src/biblock.jl:362-363)"""
         k0, k1 = self._krange(k0, k1)
-        self._ck(self.lib.dmt_equalize_laws(self.h, stores, k0, k1))
+        ch = C.c_int32(0)
+        self._ck(self.lib.dmt_equalize_laws(self.h, stores, k0, k1, C.byref(ch)))
+        return bool(ch.value)
 
     # -- layouts
     def set_blocks(self, layout, ranges, rho=0.0, last=None, ll_hist_len=-1):
@@ -291,6 +297,19 @@ class Ctx:
 
     def snapshot_wait(self):
         self._ck(self.lib.dmt_snapshot_wait(self.h))
+
+    def get_X_chains(self, chains, side=ACCEPTED):
+        """X [NP, d, len(chains)] of the listed recordings (bb.b.XX of a few recordings)"""
+        sel = np.ascontiguousarray(chains, dtype=np.int32)
+        X = np.empty((self.NP, self.d, sel.size))
+        self._ck(self.lib.dmt_get_X_chains(self.h, side, int(sel.size), sel.ctypes.data_as(_ip), _p(X)))
+        return X
+
+    def get_W_chains(self, chains, side=ACCEPTED):
+        sel = np.ascontiguousarray(chains, dtype=np.int32)
+        W = np.empty((self.S, self.dw, sel.size))
+        self._ck(self.lib.dmt_get_W_chains(self.h, side, int(sel.size), sel.ctypes.data_as(_ip), _p(W)))
+        return W
 
     def set_W(self, W, side=ACCEPTED):
         self._ck(self.lib.dmt_set_W(self.h, side, _p(_f64(W, (self.S, self.dw, self.M)))))
@@ -420,6 +439,10 @@ class Ctx:
         """lanes per (chain, block) in the forward kernel: 0 = automatic, or 1 / 2 / 4 / 8 (results are identical)"""
         self._ck(self.lib.dmt_set_fwd_lanes(self.h, int(lanes)))
 
+    def set_bwd_mode(self, mode):
+        """thread mapping of the backward filter: 0 = automatic, 1 = thread per parameter set, 2 = cooperative lanes"""
+        self._ck(self.lib.dmt_set_bwd_mode(self.h, int(mode)))
+
     # -- guiding cache
     def enable_guiding_cache(self, layout, enable=True):
         self._ck(self.lib.dmt_enable_guiding_cache(self.h, layout, int(bool(enable))))
@@ -431,9 +454,9 @@ class Ctx:
         return H, F, c
 
     # -- test hooks
-    def debug_normals(self, chain0, tile0, it, n_chains, n_tiles):
+    def debug_normals(self, chain0, tile0, it, n_chains, n_tiles, layout=0):
         out = np.empty((n_chains, n_tiles, 4 * self.dw))
-        self._ck(self.lib.dmt_debug_normals(self.h, chain0, tile0, it, n_chains, n_tiles, _p(out)))
+        self._ck(self.lib.dmt_debug_normals(self.h, chain0, tile0, it, layout, n_chains, n_tiles, _p(out)))
         return out
 
     def debug_exponentials(self, chain0, it, layout, n_chains, n_blocks):

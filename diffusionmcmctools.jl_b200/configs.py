@@ -215,9 +215,11 @@ def blocking_layouts(K, block_len, rho):
     return [(A, rho), (B, rho)]
 
 
-def named_config(cfg, M=None, seed=0, chain_offset=0, P=None):
-    """BASELINE.json configs: c1..c5"""
+def named_config(cfg, M=None, seed=0, chain_offset=0, P=None, sim_sub=2):
+    """BASELINE.json configs: c1..c5 (sim_sub: refinement of the grid the synthetic truth is simulated on)"""
     cfg = cfg.lower()
+    import functools
+    make_problem = functools.partial(globals()["make_problem"], sim_sub=sim_sub)
     if cfg == "c1":
         return make_problem("fhn", M or 1, P, seed=seed, rho=0.96, chain_offset=chain_offset)
     if cfg == "c2":

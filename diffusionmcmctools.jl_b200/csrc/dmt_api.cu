@@ -150,6 +150,7 @@ struct dmt_ctx {
     DevBuf<double> d_G[2][2], d_c0[2][2], d_theta[2][2], d_aux[2][2], d_obs[2], d_vart[2];
     DevBuf<double> d_scratch, d_partial, d_stats;
     DevBuf<uint8_t> d_mask;
+    DevBuf<int> d_flag;
     void *nccl_comm = nullptr;
     // peer-memory all-reduce (dmt_p2p_export / dmt_p2p_init)
     P2PBuf *p2p_local = nullptr;
@@ -157,6 +158,7 @@ struct dmt_ctx {
     bool p2p_ready = false;
     int n_ranks = 1;
     int fwd_lanes = 0;       // dmt_set_fwd_lanes: 0 = automatic
+    int bwd_mode = 0;        // dmt_set_bwd_mode: 0 = automatic, 1 = one thread per (pset, block), 2 = lanes cooperate on one pset
     DevBuf<double> d_xbar[2]; // linearisation points [K][D][P] per store, kept so that a parameter update re-linearises on the device
     std::vector<char> xbar_set[2];
     // thinned path saving (dmt_snapshot_paths_async): staging buffer + copy stream
@@ -270,7 +272,9 @@ template <class MD> void launch_bwd_model(dmt_ctx *c, Layout &L, const BwdArgs &
     const int nz = c->cfg.two_sided_laws ? 2 : 1;
     bool all_terminal = true;
     for (int b = 0; b < L.nb; b++) all_terminal = all_terminal && L.last[b];
-    if (MD::ATIL_DIAG && MD::D >= 5 && all_terminal && !getenv("DMT_NO_COOP_K1")) {
+    const bool coop_ok = MD::ATIL_DIAG && MD::D >= 5 && all_terminal;
+    REQUIRE(c->bwd_mode != 2 || coop_ok, DMT_ERR_UNSUPPORTED, "cooperative backward filter not available for this model / layout");
+    if (coop_ok && c->bwd_mode != 1 && !getenv("DMT_NO_COOP_K1")) {
         // wide state, no exact-observation interval: D lanes per parameter set (kernels.cuh, bwd_coop_kernel)
         constexpr int per_cta = 4 * (32 / MD::D);
         bwd_coop_kernel<MD><<<dim3((c->P + per_cta - 1) / per_cta, L.nb, nz), 128, 0, c->stream>>>(c->dev, L.dev, ba);
@@ -348,7 +352,8 @@ void cache_build(dmt_ctx *c, Layout &L) {
         CK(cudaStreamSynchronize(c->stream));
         L.dev.blk_of_k = L.d_blk_of_k.p;
     }
-    cache_set_private(L, true);
+    cache_set_private(L, true); // the probe runs below write the private store through these pointers
+    try {
     const int D = c->D, nruns = 1 + 2 * D + D * (D - 1) / 2;
     const double s = 8.0; // probe scale (a power of two: exact scaling)
     DevBuf<double> Crun;
@@ -375,9 +380,15 @@ void cache_build(dmt_ctx *c, Layout &L) {
     CK(cudaGetLastError());
     cache_apply(c, L); // the actual artificial observations
     CK(cudaStreamSynchronize(c->stream));
+    } catch (...) { // a half-built private store must never be read by the forward kernels
+        cache_set_private(L, false);
+        L.cache_valid = false;
+        throw;
+    }
     L.cache_valid = true;
 }
-// dmt_blocking_sweep forms F on the fly and leaves the private store's F for older end points: materialise it on demand
+// F_stale: the private store's F belongs to older block end points than the current artificial observations (set by paths that
+// defer cache_apply); every forward launch materialises it first.  dmt_blocking_sweep itself applies the cache eagerly.
 void ensure_guiding(dmt_ctx *c, Layout &L) {
     if (L.cache_enabled && L.cache_valid && L.F_stale) cache_apply(c, L);
 }
@@ -394,15 +405,23 @@ __global__ void put_record_kernel(const DevCtx cx, int side, int store, double *
     for (int q = 0; q < ncomp; q++)
         dst[((size_t)k * NREC + off + q) * P + ps] = src[((size_t)(bcast_k ? 0 : (k - k0)) * ncomp + q) * P + ps];
 }
-// accepted -> proposal copy of a whole record (equalize_*)
-__global__ void copy_record_kernel(const DevCtx cx, int store, double *rec0, double *rec1, int NREC, int k0, int k1) {
+// accepted -> proposal copy of a whole record (equalize_*); *changed |= 1 when the proposal record differed (the reference's
+// equalize_obs_params! / equalize_law_params! return exactly that, src/biblock.jl:362-363)
+__global__ void copy_record_kernel(const DevCtx cx, int store, double *rec0, double *rec1, int NREC, int k0, int k1, int *changed) {
     const int ps = blockIdx.x * blockDim.x + threadIdx.x, k = k0 + blockIdx.y;
     if (ps >= cx.P || k > k1) return;
     const size_t P = cx.P;
     const int sa = cx.parP[store][(size_t)k * P + ps];
     const double *src = sa ? rec1 : rec0;
     double *dst = sa ? rec0 : rec1;
-    for (int q = 0; q < NREC; q++) dst[((size_t)k * NREC + q) * P + ps] = src[((size_t)k * NREC + q) * P + ps];
+    bool diff = false;
+    for (int q = 0; q < NREC; q++) {
+        const double v = src[((size_t)k * NREC + q) * P + ps];
+        double *d = &dst[((size_t)k * NREC + q) * P + ps];
+        diff = diff || !(*d == v);
+        *d = v;
+    }
+    if (diff) atomicOr(changed, 1);
 }
 
 void put_record(dmt_ctx *c, int side, int store, double *rec0, double *rec1, int NREC, int off, int ncomp, int k0, int k1,
@@ -727,17 +746,25 @@ int32_t dmt_set_obs(dmt_ctx *ctx, int32_t side, int32_t k0, int32_t k1, const do
     });
 }
 
-int32_t dmt_equalize_laws(dmt_ctx *ctx, int32_t store_mask, int32_t k0, int32_t k1) {
+int32_t dmt_equalize_laws(dmt_ctx *ctx, int32_t store_mask, int32_t k0, int32_t k1, int32_t *changed) {
     return guarded(ctx, [&] {
         check_law_side(ctx, 1); check_range(ctx, k0, k1);
         dim3 grid = pset_grid(ctx, k1 - k0 + 1, 128);
+        if (ctx->d_flag.n < 1) ctx->d_flag.alloc(1);
+        CK(cudaMemsetAsync(ctx->d_flag.p, 0, sizeof(int), ctx->stream));
         for (int st = 0; st < 2; st++) {
             if (!((store_mask >> st) & 1)) continue;
-            copy_record_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->dev, st, ctx->d_theta[0][st].p, ctx->d_theta[1][st].p, ctx->NPAR, k0, k1);
-            copy_record_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->dev, st, ctx->d_aux[0][st].p, ctx->d_aux[1][st].p, ctx->NAUX, k0, k1);
-            if (st == 0) copy_record_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->dev, 0, ctx->d_obs[0].p, ctx->d_obs[1].p, ctx->NOBS, k0, k1);
+            copy_record_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->dev, st, ctx->d_theta[0][st].p, ctx->d_theta[1][st].p, ctx->NPAR, k0, k1, ctx->d_flag.p);
+            copy_record_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->dev, st, ctx->d_aux[0][st].p, ctx->d_aux[1][st].p, ctx->NAUX, k0, k1, ctx->d_flag.p);
+            if (st == 0) copy_record_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->dev, 0, ctx->d_obs[0].p, ctx->d_obs[1].p, ctx->NOBS, k0, k1, ctx->d_flag.p);
         }
         CK(cudaGetLastError());
+        if (changed) { // b° had to be changed: its guiding term belongs to other parameters => the caller escalates critical_change
+            int h = 0;
+            CK(cudaMemcpyAsync(&h, ctx->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            *changed = h;
+        }
     });
 }
 
@@ -849,6 +876,30 @@ int32_t dmt_snapshot_paths_async(dmt_ctx *ctx, int32_t side, int32_t n_sel, cons
         CK(cudaMemcpyAsync(host_out, ctx->d_snap.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_stream));
         CK(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
     });
+}
+// bb.b.XX / bb.b.WW of a few recordings (the reference reads them per recording: be.recordings[i].blocks[j].b.XX)
+static void get_paths_of(dmt_ctx *ctx, int side, int n_sel, const int32_t *chains, double *out, bool is_x) {
+    check_side(ctx, side);
+    REQUIRE(n_sel >= 1 && chains && out, DMT_ERR_ARG, "bad chain selection");
+    for (int i = 0; i < n_sel; i++) REQUIRE(chains[i] >= 0 && chains[i] < ctx->M, DMT_ERR_ARG, "chain index out of range");
+    const size_t n = (is_x ? (size_t)ctx->NP * ctx->D : (size_t)ctx->S * ctx->DW) * n_sel;
+    DevBuf<double> d;
+    DevBuf<int> sel;
+    d.alloc(n, false);
+    sel.alloc(n_sel, false);
+    CK(cudaMemcpyAsync(sel.p, chains, sizeof(int) * n_sel, cudaMemcpyHostToDevice, ctx->stream));
+    const dim3 grid((n_sel + 63) / 64, ctx->K);
+    if (is_x) gather_X_kernel<<<grid, 64, 0, ctx->stream>>>(ctx->dev, side, ctx->D, sel.p, n_sel, d.p);
+    else gather_W_kernel<<<grid, 64, 0, ctx->stream>>>(ctx->dev, side, ctx->DW, sel.p, n_sel, d.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, d.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+}
+int32_t dmt_get_X_chains(dmt_ctx *ctx, int32_t side, int32_t n_sel, const int32_t *chains, double *X) {
+    return guarded(ctx, [&] { get_paths_of(ctx, side, n_sel, chains, X, true); });
+}
+int32_t dmt_get_W_chains(dmt_ctx *ctx, int32_t side, int32_t n_sel, const int32_t *chains, double *W) {
+    return guarded(ctx, [&] { get_paths_of(ctx, side, n_sel, chains, W, false); });
 }
 int32_t dmt_snapshot_wait(dmt_ctx *ctx) {
     return guarded(ctx, [&] {
@@ -1156,6 +1207,12 @@ static void xfer_guiding(dmt_ctx *ctx, int side, int store, int k, double *H, do
         CK(cudaMemcpyAsync(c, dc.p, dc.n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     }
     CK(cudaStreamSynchronize(ctx->stream));
+    if (!upload && Gpriv) { // the cache refreshes c only where it is read: at the first interval of each block, accepted PP store
+        bool block_start = false;
+        for (int b = 0; b < priv->nb; b++) block_start = block_start || (priv->i0[b] == k && store == 0);
+        if (!block_start)
+            for (size_t p = 0; p < P; p++) c[p] = NAN;
+    }
 }
 int32_t dmt_get_guiding_term(dmt_ctx *ctx, int32_t side, int32_t store, int32_t k, double *H, double *F, double *c) {
     return guarded(ctx, [&] { xfer_guiding(ctx, side, store, k, H, F, c, false); });
@@ -1172,6 +1229,12 @@ int32_t dmt_set_fwd_lanes(dmt_ctx *ctx, int32_t lanes) {
         ctx->fwd_lanes = lanes;
     });
 }
+int32_t dmt_set_bwd_mode(dmt_ctx *ctx, int32_t mode) {
+    return guarded(ctx, [&] {
+        if (mode < 0 || mode > 2) throw DmtError(DMT_ERR_ARG, "mode must be 0 (auto), 1 (thread per parameter set) or 2 (cooperative)");
+        ctx->bwd_mode = mode;
+    });
+}
 int32_t dmt_enable_guiding_cache(dmt_ctx *ctx, int32_t layout, int32_t enable) {
     return guarded(ctx, [&] {
         Layout &L = layout_of(ctx, layout);
@@ -1186,7 +1249,7 @@ int32_t dmt_enable_guiding_cache(dmt_ctx *ctx, int32_t layout, int32_t enable) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------- test hooks
-int32_t dmt_debug_normals(dmt_ctx *ctx, uint32_t chain0, uint32_t tile0, uint32_t iter, int32_t n_chains, int32_t n_tiles, double *out) {
+int32_t dmt_debug_normals(dmt_ctx *ctx, uint32_t chain0, uint32_t tile0, uint32_t iter, uint32_t layout, int32_t n_chains, int32_t n_tiles, double *out) {
     return guarded(ctx, [&] {
         REQUIRE(out && n_chains > 0 && n_tiles > 0, DMT_ERR_ARG, "bad arguments");
         const size_t n = (size_t)n_chains * n_tiles * 4 * ctx->DW;
@@ -1195,10 +1258,10 @@ int32_t dmt_debug_normals(dmt_ctx *ctx, uint32_t chain0, uint32_t tile0, uint32_
         const int tot = n_chains * n_tiles;
         dim3 grid((tot + 127) / 128);
         switch (ctx->DW) {
-        case 1: debug_normals_kernel<1><<<grid, 128, 0, ctx->stream>>>(ctx->cfg.seed, chain0, tile0, iter, n_chains, n_tiles, d.p); break;
-        case 2: debug_normals_kernel<2><<<grid, 128, 0, ctx->stream>>>(ctx->cfg.seed, chain0, tile0, iter, n_chains, n_tiles, d.p); break;
-        case 3: debug_normals_kernel<3><<<grid, 128, 0, ctx->stream>>>(ctx->cfg.seed, chain0, tile0, iter, n_chains, n_tiles, d.p); break;
-        default: debug_normals_kernel<4><<<grid, 128, 0, ctx->stream>>>(ctx->cfg.seed, chain0, tile0, iter, n_chains, n_tiles, d.p); break;
+        case 1: debug_normals_kernel<1><<<grid, 128, 0, ctx->stream>>>(ctx->cfg.seed, chain0, tile0, iter, layout, n_chains, n_tiles, d.p); break;
+        case 2: debug_normals_kernel<2><<<grid, 128, 0, ctx->stream>>>(ctx->cfg.seed, chain0, tile0, iter, layout, n_chains, n_tiles, d.p); break;
+        case 3: debug_normals_kernel<3><<<grid, 128, 0, ctx->stream>>>(ctx->cfg.seed, chain0, tile0, iter, layout, n_chains, n_tiles, d.p); break;
+        default: debug_normals_kernel<4><<<grid, 128, 0, ctx->stream>>>(ctx->cfg.seed, chain0, tile0, iter, layout, n_chains, n_tiles, d.p); break;
         }
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(out, d.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

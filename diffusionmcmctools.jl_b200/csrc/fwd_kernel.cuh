@@ -273,8 +273,8 @@ __global__ void DMT_FWD_BOUNDS fwd_kernel(const DevCtx cx, const LayoutDev ly, c
 #pragma unroll
                     for (int s = 0; s < 4 * DW; s++) z[s] = 0.5;
 #else
-                    if (G > 1) tile_normals_coop<DW, G>(cx.seed, cx.chain_offset + (uint32_t)c, (uint32_t)(t0 + q), fa.iter, sub, z);
-                    else tile_normals<DW>(cx.seed, cx.chain_offset + (uint32_t)c, (uint32_t)(t0 + q), fa.iter, z);
+                    if (G > 1) tile_normals_coop<DW, G>(cx.seed, cx.chain_offset + (uint32_t)c, (uint32_t)(t0 + q), fa.iter, (uint32_t)ly.id, sub, z);
+                    else tile_normals<DW>(cx.seed, cx.chain_offset + (uint32_t)c, (uint32_t)(t0 + q), fa.iter, (uint32_t)ly.id, z);
 #endif
                 }
                 if (!SWEEP) { // K3: dW° = rho dW + sqrt(1-rho^2) sqrt(dt) xi   (A.2)

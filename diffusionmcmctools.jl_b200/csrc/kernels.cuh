@@ -977,6 +977,18 @@ __global__ void gather_X_kernel(const DevCtx cx, int side, int D, const int *sel
                 cx.X[(size_t)sl * cx.Xbuf + (((size_t)(t0 + (j >> 2)) * D + i) * M + c) * 4 + (j & 3)];
     }
 }
+// noise of a FEW chains: device tiles -> out[step][dw][n_sel], parity-resolved like xfer_W_kernel
+__global__ void gather_W_kernel(const DevCtx cx, int side, int DW, const int *sel, int n_sel, double *out) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+    if (s >= n_sel) return;
+    const size_t M = cx.M;
+    const int c = sel[s];
+    const int sl = side ^ cx.parW[(size_t)k * M + c];
+    const int nst = cx.nsteps[k], s0 = cx.step0[k], t0 = cx.tile0[k];
+    for (int i = 0; i < DW; i++)
+        for (int j = 0; j < nst; j++)
+            out[((size_t)(s0 + j) * DW + i) * n_sel + s] = cx.W[(size_t)sl * cx.Wbuf + (((size_t)(t0 + (j >> 2)) * DW + i) * M + c) * 4 + (j & 3)];
+}
 __global__ void xfer_W_kernel(const DevCtx cx, int side, int DW, double *nat, int dir) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
     if (c >= cx.M) return;
@@ -1051,12 +1063,12 @@ __global__ void xfer_guiding_kernel(const DevCtx cx, int side, int store, int k,
 
 // test hook: the device's Philox -> N(0,1) / Exp(1) streams for given counters (checked against the oracle's libm versions)
 template <int DW>
-__global__ void debug_normals_kernel(uint64_t seed, uint32_t chain0, uint32_t tile0, uint32_t iter, int n_chains, int n_tiles, double *out) {
+__global__ void debug_normals_kernel(uint64_t seed, uint32_t chain0, uint32_t tile0, uint32_t iter, uint32_t layout, int n_chains, int n_tiles, double *out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_chains * n_tiles) return;
     const int c = i / n_tiles, q = i % n_tiles;
     double z[4 * DW];
-    tile_normals<DW>(seed, chain0 + (uint32_t)c, tile0 + (uint32_t)q, iter, z);
+    tile_normals<DW>(seed, chain0 + (uint32_t)c, tile0 + (uint32_t)q, iter, layout, z);
     for (int k = 0; k < 4 * DW; k++) out[(size_t)i * 4 * DW + k] = z[k];
 }
 __global__ void debug_exponentials_kernel(uint64_t seed, uint32_t chain0, uint32_t iter, uint32_t layout, int n_chains, int n_blocks, double *out) {

@@ -2,8 +2,11 @@
 // transforms for the pCN refresh (K3) and the Metropolis test (K6).
 // Replaces `Wnr`-driven sampling inside GP.rand! (/root/reference/src/biblock.jl:95-98) and
 // rand(Exponential(1.0)) (/root/reference/src/biblock.jl:122).  Counter layout (documented in DESIGN.md §4; the test oracle restates it):
-//   pCN   : ctr = (global chain, global tile, iteration, STREAM_PCN<<8 | call), call = 0 .. 2*DW-1
-//   accept: ctr = (global chain, block,       iteration, STREAM_ACC<<8 | layout)
+//   pCN   : ctr = (global chain, global tile, iteration, STREAM_PCN<<24 | layout<<8 | call), call = 0 .. 2*DW-1
+//   accept: ctr = (global chain, block,       iteration, STREAM_ACC<<24 | layout<<8)
+// The LAYOUT ID is part of both counters: the reference loop runs every layout's sweep with the SAME iteration index
+// (`for i; for B in blocks; draw_proposal_path!(B); accept_reject_proposal_path!(B, i)`,
+// /root/reference/docs/src/tutorials/biblock/smoothing_with_blocking.md:32-59), and the innovations of two sweeps must be independent.
 //   key   = (seed lo, seed hi)
 // One call -> 128 bits -> two 53-bit uniforms -> one Box–Muller pair.  Z never touches HBM.
 #pragma once
@@ -55,13 +58,15 @@ __device__ __forceinline__ void box_muller(u32x4 o, double &z0, double &z1) {
     z1 = r * s;
 }
 
+__host__ __device__ __forceinline__ uint32_t ctr_word3(uint32_t stream, uint32_t layout, uint32_t call) { return (stream << 24) | (layout << 8) | call; }
+
 // 4*DW standard normals of one tile (4 EM steps): normal n = slot*DW + j lives in call n/2 (even: cos, odd: sin)
 template <int DW>
-__device__ __forceinline__ void tile_normals(uint64_t seed, uint32_t chain, uint32_t gtile, uint32_t iter, double *z) {
+__device__ __forceinline__ void tile_normals(uint64_t seed, uint32_t chain, uint32_t gtile, uint32_t iter, uint32_t layout, double *z) {
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
     for (int call = 0; call < 2 * DW; call++) {
-        u32x4 c = {chain, gtile, iter, (STREAM_PCN << 8) | (uint32_t)call};
+        u32x4 c = {chain, gtile, iter, ctr_word3(STREAM_PCN, layout, (uint32_t)call)};
         box_muller(philox4x32_10(c, k0, k1), z[2 * call], z[2 * call + 1]);
     }
 }
@@ -69,14 +74,14 @@ __device__ __forceinline__ void tile_normals(uint64_t seed, uint32_t chain, uint
 // the same 4*DW normals, produced by G adjacent lanes together: lane `sub` of the group evaluates calls sub, sub+G, ... and the
 // group all-gathers the pairs with shuffles (every lane of the warp must call this)
 template <int DW, int G>
-__device__ __forceinline__ void tile_normals_coop(uint64_t seed, uint32_t chain, uint32_t gtile, uint32_t iter, int sub, double *z) {
+__device__ __forceinline__ void tile_normals_coop(uint64_t seed, uint32_t chain, uint32_t gtile, uint32_t iter, uint32_t layout, int sub, double *z) {
     constexpr int NC = 2 * DW, PER = (NC + G - 1) / G;
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     double zl[2 * PER];
 #pragma unroll
     for (int p = 0; p < PER; p++) {
         const int call = min(sub + p * G, NC - 1); // (a lane past the end repeats the last call; its result is not gathered)
-        u32x4 c = {chain, gtile, iter, (STREAM_PCN << 8) | (uint32_t)call};
+        u32x4 c = {chain, gtile, iter, ctr_word3(STREAM_PCN, layout, (uint32_t)call)};
         box_muller(philox4x32_10(c, k0, k1), zl[2 * p], zl[2 * p + 1]);
     }
 #pragma unroll
@@ -87,7 +92,7 @@ __device__ __forceinline__ void tile_normals_coop(uint64_t seed, uint32_t chain,
 }
 
 __device__ __forceinline__ double accept_exponential(uint64_t seed, uint32_t chain, uint32_t block, uint32_t iter, uint32_t layout) {
-    u32x4 c = {chain, block, iter, (STREAM_ACC << 8) | layout};
+    u32x4 c = {chain, block, iter, ctr_word3(STREAM_ACC, layout, 0u)};
     u32x4 o = philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
     uint64_t w0 = ((uint64_t)o.y << 32) | o.x;
 #if DMT_LIBDEVICE_MATH

@@ -175,8 +175,10 @@ class BlockEnsemble:
 
 
 # ---- imputation --------------------------------------------------------------------------------------------------------
-def draw_proposal_path(be, mcmciter=0, Z=None):
-    """draw_proposal_path!(be)  src/block_ensemble.jl:50.  `mcmciter` only seeds the counter-based generator."""
+def draw_proposal_path(be, mcmciter, Z=None):
+    """draw_proposal_path!(be)  src/block_ensemble.jl:50.  `mcmciter` is REQUIRED: with (seed, recording, layout, time tile) it
+    is the counter of the generator, so calling twice with the same value reproduces the same innovations.  Layouts may share
+    one iteration index (the reference loop does): the layout id is part of the counter."""
     be.ctx.draw_proposal_path(be.layout, mcmciter, Z)
 
 
@@ -326,6 +328,10 @@ def set_proposal_law(be, theta_o, pnames, critical_change=None, skip=0):
     se = be.se
     th = se.theta.copy()                      # equalize_law_params!: everything not updated is shared with the accepted law
     theta_o = np.asarray(theta_o, dtype=np.float64)
+    # GP.equalize_obs_params! / equalize_law_params! FIRST (src/biblock.jl:362-363): b° := b for every record; if b° had to be
+    # changed, its guiding term belongs to other parameters and the update becomes critical
+    changed = be.ctx.equalize_laws(3)
+    obs_update = None
     if isinstance(pnames, ParamNamesAllObs):
         if critical_change is None:
             critical_change = pnames.is_critical()
@@ -338,16 +344,18 @@ def set_proposal_law(be, theta_o, pnames, critical_change=None, skip=0):
         if any(ou):
             if se.obs_param_hook is None:
                 raise NotImplementedError("θ° updates observation parameters: set se.obs_param_hook(updates, theta_o) -> (L, Sigma, v)")
-            Lm, Sg, vv = se.obs_param_hook(ou, theta_o)
-            be.ctx.set_obs(Lm, Sg, vv, side=_lib.PROPOSAL)
+            obs_update = se.obs_param_hook(ou, theta_o)
     else:
         if critical_change is None:
             raise ValueError("critical_change must be given with a bare pair list")
         for i_src, j_dst in pnames:
             th[j_dst, :] = theta_o[i_src]
+    critical_change = bool(critical_change) or changed
     se.theta_o = th
-    be.ctx.equalize_laws(3)                   # GP.equalize_obs_params! / equalize_law_params!  (src/biblock.jl:384-443)
-    be.ctx.set_params(th, side=_lib.PROPOSAL, stores=3)
+    be.ctx.set_params(th, side=_lib.PROPOSAL, stores=3)     # DD.set_parameters!(bb.b°.PP / P_last / P_excl / Pb_excl, θ°, ...)  :364-367
+    if obs_update is not None:
+        Lm, Sg, vv = obs_update
+        be.ctx.set_obs(Lm, Sg, vv, side=_lib.PROPOSAL)
     if critical_change and se.xbar is not None:
         # the linearisation points did not move, only theta did: they are already on the device (uploaded by the constructor)
         be.ctx.set_aux_linearised(None, side=_lib.PROPOSAL, store=_lib.STORE_PP)
@@ -391,23 +399,45 @@ class PathSaver:
 # ---- checkpoint / resume (not in the reference, which keeps its state in Julia objects) -------------
 def save_state(se, path, layouts=()):
     """Everything needed to continue a run bit-exactly: accepted and proposal X and W (resolved through the parity bits), the
-    accepted parameters, and per layout the ll fields.  The counter-based generator needs no state beyond (seed, iteration)."""
+    accepted and proposal parameters θ / θ°, and per layout the ll fields and the ll / accept histories.  The counter-based
+    generator needs no state beyond (seed, layout, iteration)."""
     ctx = se.ctx
     d = dict(X0=ctx.get_X(0), X1=ctx.get_X(1), W0=ctx.get_W(0), W1=ctx.get_W(1), theta=se.theta, theta_o=se.theta_o,
              n_pts=ctx.n_pts, tt=ctx.tt, chain_lo=se.chain_lo, chain_hi=se.chain_hi)
     for be in layouts:
         d["ll0_%d" % be.layout] = ctx.get_ll(be.layout, 0)
         d["ll1_%d" % be.layout] = ctx.get_ll(be.layout, 1)
+        if be.ll_hist_len > 0:
+            d["acc_hist_%d" % be.layout] = ctx.get_accept_history(be.layout, 0, be.ll_hist_len - 1)
+            for s in (0, 1):
+                d["ll_hist%d_%d" % (s, be.layout)] = ctx.get_ll_history(be.layout, s, 0, be.ll_hist_len - 1)
     np.savez_compressed(path, **d)
 
 
 def load_state(se, path, layouts=()):
-    """Restore a state written by save_state into an ensemble built with the same recordings, grids, seed and layouts."""
+    """Restore a state written by save_state into an ensemble built with the same recordings, grids, seed and layouts.
+    The laws are restored too: θ / θ° go back to the device (through the law parity, so it does not matter how many
+    swap_PP! the saved run had made), the Jacobian-linearised auxiliary laws are re-evaluated at the stored points, and the guiding
+    term of every layout in `layouts` is recomputed (in order; layouts sharing the store are recomputed by the sweep loop anyway)."""
     z = np.load(path)
     ctx = se.ctx
     if not (np.array_equal(z["n_pts"], ctx.n_pts) and np.array_equal(z["tt"], ctx.tt) and int(z["chain_lo"]) == se.chain_lo and int(z["chain_hi"]) == se.chain_hi):
         raise ValueError("checkpoint belongs to a different ensemble (grid or chain slice differ)")
     ctx.set_X(z["X0"], 0); ctx.set_X(z["X1"], 1); ctx.set_W(z["W0"], 0); ctx.set_W(z["W1"], 1)
+    se.theta, se.theta_o = z["theta"].copy(), z["theta_o"].copy()
+    sides = ((0, se.theta), (1, se.theta_o)) if se.two_sided else ((0, se.theta),)
+    for side, th in sides:
+        ctx.set_params(th, side=side, stores=3)
+        if se.xbar is not None:
+            ctx.set_aux_linearised(None, side=side, store=_lib.STORE_PP)
+            ctx.set_aux_linearised(None, side=side, store=_lib.STORE_PPB)
     for be in layouts:
         ctx.set_ll(be.layout, z["ll0_%d" % be.layout], 0)
         ctx.set_ll(be.layout, z["ll1_%d" % be.layout], 1)
+        if be.ll_hist_len > 0 and ("acc_hist_%d" % be.layout) in z:
+            acc = z["acc_hist_%d" % be.layout]
+            for i in range(be.ll_hist_len):
+                ctx.set_accepted(be.layout, i, acc[i])
+                for s in (0, 1):
+                    ctx.set_ll_history(be.layout, s, i, z["ll_hist%d_%d" % (s, be.layout)][i])
+        ctx.recompute_guiding_term(be.layout, _lib.P_BOTH if se.two_sided else _lib.P_ONLY)

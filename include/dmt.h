@@ -95,8 +95,10 @@ int32_t dmt_set_aux_linearised(dmt_ctx *ctx, int32_t side, int32_t store, int32_
 /* observation at the END of interval k (LinearGsnObs): L[k][m*d][P], Sigma[k][m*m][P], v[k][m][P] */
 int32_t dmt_set_obs(dmt_ctx *ctx, int32_t side, int32_t k0, int32_t k1, const double *L, const double *Sigma, const double *v);
 /* GP.equalize_*: copy the law records (theta, aux, obs; NOT the guiding term) of intervals k0..k1 accepted -> proposal
- * (src/biblock.jl:384-443 expressed as "copy slots"). */
-int32_t dmt_equalize_laws(dmt_ctx *ctx, int32_t store_mask, int32_t k0, int32_t k1);
+ * (src/biblock.jl:384-443 expressed as "copy slots").  *changed (may be NULL) := 1 when a proposal record had to be changed,
+ * the value GP.equalize_obs_params! / equalize_law_params! return: the caller then escalates critical_change
+ * (src/biblock.jl:362-363), because the proposal slot's guiding term belongs to other parameters. */
+int32_t dmt_equalize_laws(dmt_ctx *ctx, int32_t store_mask, int32_t k0, int32_t k1, int32_t *changed);
 
 /* ---- block layouts (src/block_collection.jl:20-30; src/biblock.jl:49-62) ------------------------------------ */
 /* last[] NULL => only block n_blocks-1 is terminal (BlockCollection rule i==N).  rho[] per block (src/biblock.jl:46).
@@ -122,6 +124,10 @@ int32_t dmt_set_X(dmt_ctx *ctx, int32_t side, const double *X /* [NP][d][M] */);
 int32_t dmt_get_X(dmt_ctx *ctx, int32_t side, double *X);
 int32_t dmt_set_W(dmt_ctx *ctx, int32_t side, const double *W /* [S][dw][M] increments */);
 int32_t dmt_get_W(dmt_ctx *ctx, int32_t side, double *W);
+/* the same for a few recordings only — what reading be.recordings[i].blocks[j].b.XX / .WW does in the reference
+ * (src/block_ensemble.jl:17-19, src/block.jl:49-58): X[NP][d][n_sel], W[S][dw][n_sel] of the listed chains */
+int32_t dmt_get_X_chains(dmt_ctx *ctx, int32_t side, int32_t n_sel, const int32_t *chains, double *X);
+int32_t dmt_get_W_chains(dmt_ctx *ctx, int32_t side, int32_t n_sel, const int32_t *chains, double *W);
 
 /* ---- the hot path --------------------------------------------------------------------------------------------- */
 /* GP.set_obs!(be)                          src/block_ensemble.jl:192 -> src/biblock.jl:275-280            (K7) */
@@ -206,10 +212,15 @@ int32_t dmt_get_layout_guiding_term(dmt_ctx *ctx, int32_t layout, int32_t store,
  * per-recording loop, src/block_ensemble.jl:50, is serial). */
 int32_t dmt_set_fwd_lanes(dmt_ctx *ctx, int32_t lanes);
 
+/* ---- tuning: thread mapping of the backward filter (K1) -------------------------------------------------------------
+ * 0 (default) = automatic; 1 = one thread per (parameter set, block, side); 2 = d lanes share one parameter set, lane r owning
+ * row r of H (wide states; DMT_ERR_UNSUPPORTED where it is not implemented).  Results agree to FP64 rounding. */
+int32_t dmt_set_bwd_mode(dmt_ctx *ctx, int32_t mode);
+
 /* ---- test hooks: the device's counter-based random streams for given counters ------------------------------- */
 /* out[n_chains][n_tiles][4*dw]: the N(0,1) draws the pCN refresh (K3) uses for chains chain0.., tiles tile0.., iteration iter.
  * Replaces nothing in the reference (its Wnr/randn draws are not reproducible elsewhere); lets tests pin the generator. */
-int32_t dmt_debug_normals(dmt_ctx *ctx, uint32_t chain0, uint32_t tile0, uint32_t iter, int32_t n_chains, int32_t n_tiles, double *out);
+int32_t dmt_debug_normals(dmt_ctx *ctx, uint32_t chain0, uint32_t tile0, uint32_t iter, uint32_t layout, int32_t n_chains, int32_t n_tiles, double *out);
 /* out[n_chains][n_blocks]: the Exp(1) draws of accept_reject_proposal_path! (src/biblock.jl:122) */
 int32_t dmt_debug_exponentials(dmt_ctx *ctx, uint32_t chain0, uint32_t iter, uint32_t layout, int32_t n_chains, int32_t n_blocks, double *out);
 

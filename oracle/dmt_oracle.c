@@ -265,11 +265,15 @@ static void box_muller(const uint32_t o[4], double *z0, double *z1) {
     *z1 = r * sin(ang);
 }
 
-void orc_tile_normals(uint64_t seed, uint32_t chain, uint32_t gtile, uint32_t iter, int dw, double *z) {
+/* counter word 3 = stream<<24 | layout<<8 | call: the layout id keeps the innovations of two layouts swept with the same
+ * iteration index independent (the reference loop, docs/src/tutorials/biblock/smoothing_with_blocking.md:32-59, does that) */
+static uint32_t ctr_word3(uint32_t stream, uint32_t layout, uint32_t call) { return (stream << 24) | (layout << 8) | call; }
+
+void orc_tile_normals(uint64_t seed, uint32_t chain, uint32_t gtile, uint32_t iter, uint32_t layout, int dw, double *z) {
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
     int ncall = 2 * dw; /* 4*dw normals */
     for (int call = 0; call < ncall; call++) {
-        uint32_t ctr[4] = {chain, gtile, iter, (STREAM_PCN << 8) | (uint32_t)call}, o[4];
+        uint32_t ctr[4] = {chain, gtile, iter, ctr_word3(STREAM_PCN, layout, (uint32_t)call)}, o[4];
         orc_philox4x32_10(ctr, key, o);
         box_muller(o, &z[2 * call], &z[2 * call + 1]);
     }
@@ -277,7 +281,7 @@ void orc_tile_normals(uint64_t seed, uint32_t chain, uint32_t gtile, uint32_t it
 
 double orc_accept_exponential(uint64_t seed, uint32_t chain, uint32_t block, uint32_t iter, uint32_t layout) {
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
-    uint32_t ctr[4] = {chain, block, iter, (STREAM_ACC << 8) | layout}, o[4];
+    uint32_t ctr[4] = {chain, block, iter, ctr_word3(STREAM_ACC, layout, 0u)}, o[4];
     orc_philox4x32_10(ctr, key, o);
     uint64_t w0 = ((uint64_t)o[1] << 32) | o[0];
     double u = (double)((w0 >> 11) + 1) * 0x1.0p-53;
@@ -771,7 +775,7 @@ static void pcn_interval(const orc_pair *p, int k, double rho, const double *dW,
 }
 
 static void interval_normals(const orc_pair *p, int k, const double *Zblock, size_t *zoff, uint64_t seed, uint32_t chain,
-                             uint32_t iter, const int *gtile0, double *xi) {
+                             uint32_t iter, uint32_t layout, const int *gtile0, double *xi) {
     int dw = p->dw, ns = p->n[k] - 1;
     if (Zblock) {
         memcpy(xi, Zblock + *zoff, sizeof(double) * ns * dw);
@@ -780,7 +784,7 @@ static void interval_normals(const orc_pair *p, int k, const double *Zblock, siz
     }
     double z[4 * ORC_MAXD];
     for (int i = 0; i < ns; i++) {
-        if (i % 4 == 0) orc_tile_normals(seed, chain, (uint32_t)(gtile0[k] + i / 4), iter, dw, z);
+        if (i % 4 == 0) orc_tile_normals(seed, chain, (uint32_t)(gtile0[k] + i / 4), iter, layout, dw, z);
         for (int w = 0; w < dw; w++) xi[(size_t)i * dw + w] = z[(i % 4) * dw + w];
     }
 }
@@ -788,7 +792,7 @@ static void interval_normals(const orc_pair *p, int k, const double *Zblock, siz
 /* src/biblock.jl:80-106: law = ACCEPTED bb.b.PP (+ bb.b.P_last), noise in = bb.b.WW, out = bb.b°.XX / bb.b°.WW,
  * start = bb.b.XX[1].x[1]; ll° = loglikhd_obs(PP[1], y1) + sum ll_k; failure => ll° = failing value, stop. */
 int orc_draw_proposal_path(orc_pair *p, orc_biblock *bb, const double *Z, uint64_t seed, uint32_t chain, uint32_t iter,
-                           const int *gtile0) {
+                           uint32_t layout, const int *gtile0) {
     orc_unit *u = &p->u[0], *uo = &p->u[1];
     int d = p->d, nmax = 0;
     for (int k = bb->i0; k <= bb->i1; k++) if (p->n[k] > nmax) nmax = p->n[k];
@@ -801,7 +805,7 @@ int orc_draw_proposal_path(orc_pair *p, orc_biblock *bb, const double *Z, uint64
     for (int k = bb->i0; k <= bb->i1 && ok; k++) {
         const orc_law *l = (k <= kend) ? u->PP[k] : u->PPb[k];
         double llk;
-        interval_normals(p, k, Z, &zoff, seed, chain, iter, gtile0, xi);
+        interval_normals(p, k, Z, &zoff, seed, chain, iter, layout, gtile0, xi);
         pcn_interval(p, k, bb->rho, u->WW[k], xi, uo->WW[k]);
         ok = solve_and_ll(p, l, k, y1, uo->WW[k], uo->XX[k], 0, &llk);
         if (!ok) { ll = llk; break; }
@@ -887,7 +891,7 @@ double orc_sweep_many(orc_pair **pairs, orc_biblock *blocks, int M, int nb, uint
             for (int b = 0; b < nb; b++) orc_find_W_for_X(p, &bbs[b]);
             for (int b = 0; b < nb; b++) orc_loglikhd(p, &bbs[b], 0, 0);
         }
-        for (int b = 0; b < nb; b++) orc_draw_proposal_path(p, &bbs[b], 0, seed, chain0 + (uint32_t)c, iter, gtile0);
+        for (int b = 0; b < nb; b++) orc_draw_proposal_path(p, &bbs[b], 0, seed, chain0 + (uint32_t)c, iter, layout, gtile0);
         for (int b = 0; b < nb; b++) {
             double E = orc_accept_exponential(seed, chain0 + (uint32_t)c, (uint32_t)b, iter, layout);
             nacc += orc_accept_reject(p, &bbs[b], E, 0);

@@ -40,7 +40,7 @@ void orc_linearise(int model, const double *th, const double *xbar, double *B, d
 /* ---- Philox4x32-10 (Salmon et al. 2011, Random123) and the normal/exponential transforms ---- */
 void   orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 /* 4*dw standard normals of one 4-step tile: normal index n = slot*dw + j, call n/2, cos for even n */
-void   orc_tile_normals(uint64_t seed, uint32_t chain, uint32_t gtile, uint32_t iter, int dw, double *z);
+void   orc_tile_normals(uint64_t seed, uint32_t chain, uint32_t gtile, uint32_t iter, uint32_t layout, int dw, double *z);
 double orc_accept_exponential(uint64_t seed, uint32_t chain, uint32_t block, uint32_t iter, uint32_t layout);
 
 /* ---- one recording = SamplingPair (src/sampling_pair.jl:36-55) ---- */
@@ -79,9 +79,9 @@ void orc_find_W_for_X(orc_pair *p, const orc_biblock *bb);
 /* loglikhd!(bb) / loglikhd°!(bb)       src/biblock.jl:240,248 -> src/block.jl:140-152 */
 double orc_loglikhd(orc_pair *p, orc_biblock *bb, int side, int skip);
 /* draw_proposal_path!(bb)              src/biblock.jl:80-106.  Z: standard normals, block-local layout
- * [step][dw] over the block's intervals in order (NULL => Philox with (seed,chain,iter)). Returns success. */
+ * [step][dw] over the block's intervals in order (NULL => Philox with (seed,chain,iter,layout)). Returns success. */
 int orc_draw_proposal_path(orc_pair *p, orc_biblock *bb, const double *Z, uint64_t seed, uint32_t chain,
-                           uint32_t iter, const int *gtile0 /*[K] global tile offset per interval*/);
+                           uint32_t iter, uint32_t layout, const int *gtile0 /*[K] global tile offset per interval*/);
 /* recompute_path!(b°, b.WW; skip)      src/block.jl:161-187 with law side `law_side`, noise side `w_side`,
  * output into X of `law_side`; sets bb->ll[law_side]. Returns success. */
 int orc_recompute_path(orc_pair *p, orc_biblock *bb, int law_side, int w_side, int skip);

@@ -49,7 +49,7 @@ def load(omp=False):
         "orc_bound_ok": (C.c_int, [C.c_int, _dp, _dp]),
         "orc_linearise": (None, [C.c_int, _dp, _dp, _dp, _dp, _dp]),
         "orc_philox4x32_10": (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
-        "orc_tile_normals": (None, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, _dp]),
+        "orc_tile_normals": (None, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, _dp]),
         "orc_accept_exponential": (C.c_double, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
         "orc_pair_create": (vp, [C.c_int, C.c_int, _ip, _dp, C.c_int, C.c_double]),
         "orc_pair_destroy": (None, [vp]),
@@ -67,7 +67,7 @@ def load(omp=False):
         "orc_recompute_guiding_term": (None, [vp, bbp, C.c_int]),
         "orc_find_W_for_X": (None, [vp, bbp]),
         "orc_loglikhd": (C.c_double, [vp, bbp, C.c_int, C.c_int]),
-        "orc_draw_proposal_path": (C.c_int, [vp, bbp, _dp, C.c_uint64, C.c_uint32, C.c_uint32, _ip]),
+        "orc_draw_proposal_path": (C.c_int, [vp, bbp, _dp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, _ip]),
         "orc_recompute_path": (C.c_int, [vp, bbp, C.c_int, C.c_int, C.c_int]),
         "orc_accept_reject": (C.c_int, [vp, bbp, C.c_double, _dp]),
         "orc_swap_XX": (None, [vp, bbp]),
@@ -105,9 +105,9 @@ def philox(lib, ctr, key):
     return list(o)
 
 
-def tile_normals(lib, seed, chain, gtile, it, dw):
+def tile_normals(lib, seed, chain, gtile, it, dw, layout=0):
     z = np.zeros(4 * dw)
-    lib.orc_tile_normals(seed, chain, gtile, it, dw, z.ctypes.data_as(_dp))
+    lib.orc_tile_normals(seed, chain, gtile, it, layout, dw, z.ctypes.data_as(_dp))
     return z
 
 
@@ -216,12 +216,12 @@ class Pair:
     def loglikhd(self, bb, side=0, skip=0):
         return self.lib.orc_loglikhd(self.h, C.byref(bb), side, skip)
 
-    def draw_proposal_path(self, bb, Z=None, seed=0, chain=0, it=0):
+    def draw_proposal_path(self, bb, Z=None, seed=0, chain=0, it=0, layout=0):
         if Z is not None:
             Z_, zp = _d(Z)
         else:
             zp = None
-        return bool(self.lib.orc_draw_proposal_path(self.h, C.byref(bb), zp, seed, chain, it,
+        return bool(self.lib.orc_draw_proposal_path(self.h, C.byref(bb), zp, seed, chain, it, layout,
                                                     self.gtile0.ctypes.data_as(_ip)))
 
     def recompute_path(self, bb, law_side=1, w_side=0, skip=0):

@@ -8,7 +8,7 @@ import pytest
 
 import dmt_b200
 from dmt_b200 import _lib, configs
-from harness import OracleEnsemble, make_ctx, rel_err
+from harness import OracleEnsemble, make_ctx, note_err, rel_err
 
 pytestmark = [pytest.mark.gpu, pytest.mark.own_lanes]
 
@@ -101,3 +101,93 @@ def test_slice_of_the_full_ensemble_replayed_on_the_oracle(full, orc, olib):
         acc_o, _ = ora.accept(lay, it, layout_id=lay)
         assert np.array_equal(ctx.get_last_accept(lay)[:, SLICE], acc_o)
         assert rel_err(ctx.get_X(0)[:, :, SLICE], ora.X(0)) < 1e-9
+
+
+# ---- the other BASELINE configs at their full sizes --------------------------------------------------------------------------
+FULL = {  # config -> (expected (M, K, steps per chain), chains replayed on the oracle)
+    "c2": ((1024, 50, 5000), [700, 701, 1023]),
+    "c4": ((16384, 100, 10000), [9001, 16383]),
+    "c5": ((8192, 500, 50000), [5000, 8191]),
+}
+
+
+@pytest.mark.parametrize("cfg", sorted(FULL))
+def test_other_baseline_configs_at_full_size(cfg, orc, olib):
+    """C2 (Lotka-Volterra, 1024 chains), C4 (Prokaryote, 16384 chains, state-dependent diffusion), C5 (Jansen-Rit, 8192 chains,
+    50,000 steps each, K1 every sweep): the whole ensemble through size-independent properties, and a few of its chains — with
+    their global Philox counters — replayed call by call on the oracle (paths of single recordings travel through
+    dmt_get_X_chains / dmt_get_W_chains; the full arrays are tens of GB)."""
+    (M, K, S), chains = FULL[cfg]
+    prob = configs.named_config(cfg, seed=123, sim_sub=1)
+    assert (prob.M, prob.P, prob.K, prob.steps_per_chain) == (M, M, K, S)
+    ctx = make_ctx(prob, seed=123, n_layouts=1)
+    ctx.recompute_guiding_term(0, _lib.P_ONLY)
+    assert ctx.init_paths(0, 1 << 20, 100) == 0
+    ctx.loglikhd(0, 0, 0)
+    ll = ctx.get_ll(0, 0)
+    assert np.isfinite(ll).all()
+    tot, per_block = ctx.fetch_ll(0, 0)
+    assert abs(tot - ll.sum()) < 1e-10 * abs(tot)                       # checksum of checksums (fixed-order device tree)
+    # the slice on the oracle
+    sub = copy.copy(prob)
+    sub.M = sub.P = len(chains)
+    sub.v, sub.xbar, sub.x0 = prob.v[:, :, chains].copy(), prob.xbar[:, :, chains].copy(), prob.x0[:, chains].copy()
+
+    class Sliced(OracleEnsemble):                                       # global chain ids are not contiguous here
+        def draw(self, l, it, Z=None, layout_id=None):
+            ok = np.zeros((1, self.prob.M), bool)
+            for c, b, P, bb in self.each(l):
+                ok[b, c] = P.draw_proposal_path(bb, None, seed=self.seed, chain=chains[c], it=it, layout=l)
+            return ok
+
+        def accept(self, l, it, E=None, layout_id=None):
+            acc = np.zeros((1, self.prob.M), bool)
+            for c, b, P, bb in self.each(l):
+                acc[b, c], _ = P.accept_reject(bb, float(self.olib.orc_accept_exponential(self.seed, chains[c], b, it, l)))
+            return acc, None
+    ora = Sliced(orc, olib, sub, seed=123)
+    X, W = ctx.get_X_chains(chains, 0), ctx.get_W_chains(chains, 0)
+    assert np.isfinite(X).all() and np.isfinite(W).all()
+    for s in (0, 1):
+        ora.set_X(s, X); ora.set_W(s, W)
+    ora.recompute_guiding_term(0); ora.loglikhd(0)
+    tag = "full/%s/" % cfg
+    assert rel_err(ll[:, chains], ora.ll(0, 0), tag=tag + "ll") < 1e-10
+    for k in (0, K // 2, K - 1):                                        # K1 at full size for the replayed parameter sets
+        H, F, c = ctx.get_guiding_term(k, 0, 0); Ho, Fo, co = ora.guiding(k, 0, 0)
+        assert rel_err(H[:-1][..., chains], Ho[:-1], tag=tag + "H") < 1e-10 and rel_err(F[:-1][..., chains], Fo[:-1], tag=tag + "F") < 1e-10
+        assert rel_err(c[0][chains], co[0], tag=tag + "c") < 1e-10
+        del H, F, c
+    # K5 o K2 = identity on the replayed chains (invsolve of the initial path returns the noise that made it)
+    ctx.find_W_for_X(0)
+    assert rel_err(ctx.get_W_chains(chains, 0), W, tag=tag + "K5oK2") < 1e-7
+    ctx.set_rho(0, [0.9])
+    for it in (3, 4):
+        if cfg == "c5" and it == 4:     # BASELINE C5: "each sweep = set_params -> K1 (P = M) -> K2": new parameters, device re-linearisation
+            th = prob.theta * (1 + 1e-3)
+            ctx.set_params(th, side=0, stores=1); ctx.set_aux_linearised(None, side=0, store=_lib.STORE_PP)
+            ctx.recompute_guiding_term(0, _lib.P_ONLY); ctx.loglikhd(0, 0, 0)
+            for c_, P in enumerate(ora.pairs):
+                P.set_theta(th, side=0)
+                for k in range(K):
+                    B, beta, at = orc.linearise(olib, prob.model, th, sub.xbar[k, :, c_])
+                    P.set_aux(k, B, beta, at, side=0, store=0)
+            ora.recompute_guiding_term(0); ora.loglikhd(0)
+            assert rel_err(ctx.get_ll(0, 0)[:, chains], ora.ll(0, 0), tag=tag + "ll_newtheta") < 1e-10
+        ctx.draw_proposal_path(0, it); ok_o = ora.draw(0, it)
+        assert np.array_equal(ctx.get_success(0)[:, chains], ok_o)
+        good = ok_o[0]
+        if good.any():
+            sel = [c for c, g in zip(chains, good) if g]
+            assert rel_err(ctx.get_X_chains(sel, 1), ora.X(1)[:, :, good], tag=tag + "X_prop") < 1e-10
+            assert rel_err(ctx.get_W_chains(sel, 1), ora.W(1)[:, :, good], tag=tag + "W_prop") < 1e-10
+        assert rel_err(ctx.get_ll(0, 1)[:, chains], ora.ll(0, 1), tag=tag + "ll_prop") < 1e-10
+        ll0, ll1 = ctx.get_ll(0, 0).copy(), ctx.get_ll(0, 1).copy()
+        ctx.accept_reject_path(0, it); acc_o, _ = ora.accept(0, it)
+        acc = ctx.get_last_accept(0)
+        assert np.array_equal(acc[:, chains], acc_o)
+        assert np.array_equal(ctx.get_ll(0, 0), np.where(acc, ll1, ll0))  # bookkeeping over the WHOLE ensemble
+        note_err(tag + "accept_frac_it%d" % it, acc.mean())
+        assert acc.mean() < 0.98 and (cfg == "c5" or acc.mean() > 0.02)   # (C5's 50,000-step paths accept rarely at rho = 0.9)
+        assert rel_err(ctx.get_X_chains(chains, 0), ora.X(0), tag=tag + "X") < 1e-10
+    ctx.close()

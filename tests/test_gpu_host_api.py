@@ -37,7 +37,7 @@ def test_simple_smoothing_tutorial(orc, olib):
     for i in range(nit):
         H.draw_proposal_path(bb, i)
         H.accept_reject_proposal_path(bb, i)
-        ora.draw(0, i); ora.accept(0, i, layout_id=bb.layout)
+        ora.draw(0, i, layout_id=bb.layout); ora.accept(0, i, layout_id=bb.layout)
     acc_dev = se.ctx.get_accept_history(bb.layout, 0, nit - 1)
     assert 0.05 < acc_dev.mean() < 0.99
     # oracle history from its ll bookkeeping: replay equality through the final state
@@ -71,7 +71,7 @@ def test_blocking_tutorial(orc, olib):
             ora.set_W(0, se.ctx.get_W(0))
             H.loglikhd(B); ora.loglikhd(l)
             ora.set_ll(l, 0, se.ctx.get_ll(B.layout, 0))
-            H.draw_proposal_path(B, i); ora.draw(l, i)
+            H.draw_proposal_path(B, i); ora.draw(l, i, layout_id=B.layout)
             H.accept_reject_proposal_path(B, i)
             acc_o, _ = ora.accept(l, i, layout_id=B.layout)
             assert np.array_equal(se.ctx.get_last_accept(B.layout), acc_o)
@@ -100,7 +100,7 @@ def test_inference_tutorial_parameter_update(orc, olib):
     n_par_acc = 0
     for i in range(nit):
         H.draw_proposal_path(be, i); H.accept_reject_proposal_path(be, i)
-        ora.draw(0, i); ora.accept(0, i, layout_id=be.layout)
+        ora.draw(0, i, layout_id=be.layout); ora.accept(0, i, layout_id=be.layout)
         # parameter update
         g_o = gamma + 2 * 0.3 * (rng.random() - 0.5)
         H.set_proposal_law(be, [g_o], pnames, True)
@@ -211,3 +211,116 @@ def test_path_saver_snapshots_are_ordered_and_asynchronous():
     with pytest.raises(dmt_b200.DmtError):
         se.ctx.snapshot_paths_async([70], np.empty((se.ctx.NP, 3, 1)))
     se.ctx.close()
+
+
+def test_set_proposal_law_escalates_critical_change_when_the_proposal_laws_had_to_be_equalised():
+    """src/biblock.jl:362-363: `GP.equalize_*!(bb) && (critical_change = true)`.  After a rejected critical update b°'s records
+    AND guiding term belong to the rejected θ°.  A following update flagged non-critical must still recompute b°'s guiding term,
+    otherwise ll° is computed with (B, β, ã) of one parameter and (H, F, c) of another."""
+    prob = configs.make_problem("fhn", 12, K=4, dt=0.005, seed=3, rho=0.9)
+    se = H.SamplingEnsemble(prob.model, recordings_of(prob), (prob.n_pts, prob.tt), seed=1, two_sided_laws=True)
+    se.init_paths()
+    be = H.BlockEnsemble(se, [(0, prob.K - 1)], 0.9, 0)
+    H.recompute_guiding_term(be); H.loglikhd(be)
+    ll = se.ctx.get_ll(be.layout, 0).copy()
+    H.set_proposal_law(be, [prob.theta[2] * 1.2], [(0, 2)], True)          # critical update of gamma ... rejected (no swap)
+    assert np.abs(se.ctx.get_ll(be.layout, 1) - ll).max() > 1e-6
+    # now "update" gamma back to the accepted value, flagged NON-critical: equalisation changes b°, so K1 must run on b° anyway
+    H.set_proposal_law(be, [prob.theta[2]], [(0, 2)], False)
+    assert rel_err(se.ctx.get_ll(be.layout, 1), ll) < 1e-12
+    assert rel_err(se.ctx.get_X(1), se.ctx.get_X(0)) < 1e-12
+    for k in range(prob.K):
+        Ha, Fa, ca = se.ctx.get_guiding_term(k, 0); Ho, Fo, co = se.ctx.get_guiding_term(k, 1)
+        assert np.array_equal(Ha[:-1], Ho[:-1]) and np.array_equal(Fa[:-1], Fo[:-1]) and np.array_equal(ca[0], co[0])
+    # and with nothing to equalise a non-critical update stays non-critical (no K1): the equalize call reports no change
+    assert se.ctx.equalize_laws(3) is False
+    se.ctx.close()
+
+
+def test_observation_parameter_update_reaches_the_proposal_laws(orc, olib):
+    """θ° entries that are parameters of the observations (updt_obs, src/param_names_collections.jl:125-141): the proposal-side
+    (L, Σ, v) must be set AFTER the equalisation (src/biblock.jl:362-367), otherwise equalize_obs_params! wipes them out."""
+    from dmt_b200.param_names import ParamNamesAllObs
+    M = 5
+    prob = configs.make_problem("fhn", M, K=4, dt=0.005, seed=13, rho=0.9)
+    se = H.SamplingEnsemble(prob.model, recordings_of(prob), (prob.n_pts, prob.tt), seed=2, two_sided_laws=True)
+    se.init_paths()
+    be = H.BlockEnsemble(se, [(0, prob.K - 1)], 0.9, 0)
+    H.recompute_guiding_term(be); H.loglikhd(be)
+    names = ["obs_shift"]
+    pdr = [[] for _ in range(M)]
+    odr = [[(("obs_shift", 0),) for _ in range(prob.K)] for _ in range(M)]       # every observation's θ[0] := obs_shift
+    pa = ParamNamesAllObs.build(be, names, pdr, odr)
+    assert pa.is_critical()
+    seen = {}
+
+    def hook(updates, theta_o):                                                  # obs.θ[0] shifts the observed value
+        seen["updates"] = updates
+        return prob.L, prob.Sigma, prob.v + theta_o[0]
+    se.obs_param_hook = hook
+    H.set_proposal_law(be, np.array([0.05]), pa)
+    assert len(seen["updates"]) == M and all(set(u) == set(range(prob.K)) for u in seen["updates"])
+    ora = OracleEnsemble(orc, olib, prob, seed=2)
+    X, W = se.ctx.get_X(0), se.ctx.get_W(0)
+    for s in (0, 1):
+        ora.set_X(s, X); ora.set_W(s, W)
+    for c, P in enumerate(ora.pairs):
+        for k in range(prob.K):
+            P.set_obs(k, prob.L, prob.Sigma, prob.v[k, :, c] + 0.05, side=1)
+    ora.recompute_guiding_term(0, sides=(0, 1)); ora.loglikhd(0); ora.recompute_path(0, 1, 0)
+    for k in range(prob.K):
+        H1, F1, c1 = se.ctx.get_guiding_term(k, 1); Ho, Fo, co = ora.guiding(k, 1)
+        assert rel_err(F1[:-1], Fo[:-1]) < 1e-10 and rel_err(c1[0], co[0]) < 1e-10
+        F0 = se.ctx.get_guiding_term(k, 0)[1]
+        assert np.abs(F1[:-1] - F0[:-1]).max() > 1e-3                            # the proposal side really saw the new observations
+    assert rel_err(se.ctx.get_ll(be.layout, 1), ora.ll(0, 1)) < 1e-9 and rel_err(se.ctx.get_X(1), ora.X(1)) < 1e-9
+    se.ctx.close()
+
+
+def test_checkpoint_resume_with_parameter_updates_is_bit_exact(tmp_path):
+    """save_state / load_state restore θ, θ°, the laws and the histories: an inference run (path update + γ update with
+    swap_XX!/swap_PP!) resumed from a checkpoint continues exactly like the uninterrupted one."""
+    nit = 8
+    prob = configs.make_problem("fhn", 10, K=5, dt=0.005, seed=4, rho=0.9)
+
+    def fresh():
+        se = H.SamplingEnsemble(prob.model, recordings_of(prob), (prob.n_pts, prob.tt), seed=9, two_sided_laws=True)
+        se.init_paths()
+        be = H.BlockEnsemble(se, [(0, prob.K - 1)], 0.9, nit)
+        H.recompute_guiding_term(be); H.loglikhd(be)
+        return se, be
+
+    def run(se, be, its, gamma):
+        for i in its:
+            rng = np.random.default_rng(1000 + i)                        # the host's RNG state is the caller's to checkpoint
+            H.draw_proposal_path(be, i); H.accept_reject_proposal_path(be, i)
+            g_o = gamma + 0.2 * (rng.random() - 0.5)
+            H.set_proposal_law(be, [g_o], [(0, 2)], True)
+            ll, ll_o = H.fetch_ll(be), H.fetch_ll_o(be)
+            acc = rng.exponential() > -(ll_o - ll)
+            if acc:
+                H.swap_XX(be); H.swap_PP(be); gamma = g_o
+            H.save_ll(be, i)
+            if acc:
+                H.swap_ll(be)
+        return gamma
+
+    se, be = fresh()
+    g = run(se, be, range(4), prob.theta[2])
+    assert g != prob.theta[2]                                            # at least one γ update was accepted before the checkpoint
+    ck = str(tmp_path / "state.npz")
+    H.save_state(se, ck, [be])
+    g_end = run(se, be, range(4, nit), g)
+    want = (se.ctx.get_X(0), se.ctx.get_X(1), se.ctx.get_W(0), se.ctx.get_ll(be.layout, 0), se.ctx.get_ll_history(be.layout, 0, 0, nit - 1),
+            se.ctx.get_accept_history(be.layout, 0, nit - 1), se.theta.copy())
+    se.ctx.close()
+    se2, be2 = fresh()
+    H.load_state(se2, ck, [be2])
+    assert np.allclose(se2.theta[2], g)
+    g_end2 = run(se2, be2, range(4, nit), g)
+    got = (se2.ctx.get_X(0), se2.ctx.get_X(1), se2.ctx.get_W(0), se2.ctx.get_ll(be2.layout, 0), se2.ctx.get_ll_history(be2.layout, 0, 0, nit - 1),
+           se2.ctx.get_accept_history(be2.layout, 0, nit - 1), se2.theta.copy())
+    assert g_end2 == g_end
+    for a, b in zip(want, got):
+        assert np.array_equal(a, b, equal_nan=True)
+    se2.ctx.close()

@@ -13,7 +13,12 @@ from harness import OracleEnsemble, compare_guiding, make_ctx, rel_err
 
 pytestmark = pytest.mark.gpu
 
-TOL = 1e-10
+TOL = 1e-10       # BASELINE.json north_star: paths and log-likelihoods within 1e-10 relative, decisions identical
+# The stated exception (derived there and measured by tests/test_gpu_conditioning.py): everything downstream of
+# find_W_for_X! (K5) or of a blocking law's guiding term next to its exact observation inherits the two K1 implementations'
+# rounding difference multiplied by the condition number |x| / (sigma sqrt(dt_min)) of the inverse solve (~4e3 for the Lorenz
+# grids); those quantities are compared at 1e-9, element-wise.  The oracle is NEVER re-seeded from the device.
+TOL_K5 = 1e-9
 NAMES = ["fhn", "lv", "lorenz", "prok", "jr", "ou2"]
 
 
@@ -135,13 +140,25 @@ def test_find_W_for_X_roundtrip(orc, olib, name):
     ctx.close()
 
 
-@pytest.mark.parametrize("name", ["fhn", "lorenz", "prok"])
+def blocking_problem(name, M=37, K=8, seed=4, nsteps=10):
+    layouts = [([(0, 2), (3, 5), (6, 7)], [0.6, 0.7, 0.8]), ([(0, 3), (4, 7)], 0.5)]
+    prob = small_problem(name, M=M, K=K, layouts=layouts, seed=seed, nsteps=nsteps)
+    if name == "jr":
+        # Jansen-Rit is hypoelliptic with noise five integrations away from x3: conditioning on an EXACT full-state observation
+        # (artificial_noise 1e-11) has a condition number ~1e11 and neither implementation means anything there; the blocking
+        # law is exercised with a milder artificial noise (the constructor argument of src/sampling_unit.jl:57)
+        prob.eps = 1e-4
+    return prob
+
+
+@pytest.mark.parametrize("name", NAMES)
 def test_blocking_sweeps(orc, olib, name):
     """Two staggered block layouts alternated (docs/src/tutorials/biblock/smoothing_with_blocking.md:32-59):
-    set_obs! -> recompute_guiding_term!(P only) -> find_W_for_X! -> loglikhd! -> draw -> accept, compared after each call."""
+    set_obs! -> recompute_guiding_term!(P only) -> find_W_for_X! -> loglikhd! -> draw -> accept, compared after each call.
+    Both sides run the whole loop on their own: nothing is copied from the device into the oracle after the initial path."""
     K = 8
-    layouts = [([(0, 2), (3, 5), (6, 7)], [0.6, 0.7, 0.8]), ([(0, 3), (4, 7)], 0.5)]
-    prob = small_problem(name, M=37, K=K, layouts=layouts, seed=4)
+    prob = blocking_problem(name, K=K)
+    layouts = prob.layouts
     ctx = make_ctx(prob, seed=9, ll_hist_len=6, n_layouts=3)
     ora = OracleEnsemble(orc, olib, prob, seed=9)
     # initial path: whole-path guiding term on a single terminal block (layout 2), fresh noise
@@ -161,14 +178,11 @@ def test_blocking_sweeps(orc, olib, name):
             last = (i1 == K - 1)
             for k in range(i0, i1 + 1):
                 store = 1 if (k == i1 and not last) else 0
-                compare_guiding(ctx, ora, k, 0, store, tol=TOL)
+                compare_guiding(ctx, ora, k, 0, store, tol=TOL if it == 0 else TOL_K5, tag="blocking/%s/K1" % name)
         ctx.find_W_for_X(l); ora.find_W_for_X(l)
-        Wd, Wo = ctx.get_W(0), ora.W(0)
-        assert np.abs(Wd - Wo).max() < 1e-9 * np.abs(Wo).max()
-        ora.set_W(0, Wd)   # continue both from the SAME noise (K5 amplifies rounding by 1/sigma/sqrt(dt))
+        assert rel_err(ctx.get_W(0), ora.W(0), tag="blocking/%s/W_K5" % name) < TOL_K5
         ctx.loglikhd(l, 0, 0); ora.loglikhd(l, 0, 0)
-        assert rel_err(ctx.get_ll(l, 0), ora.ll(l, 0)) < 1e-9
-        ora.set_ll(l, 0, ctx.get_ll(l, 0))
+        assert rel_err(ctx.get_ll(l, 0), ora.ll(l, 0), tag="blocking/%s/ll" % name) < TOL_K5
         if it < 3:
             Z = rng.normal(size=(prob.steps_per_chain, prob.dw, prob.M))
             ctx.draw_proposal_path(l, it, Z); ok_o = ora.draw(l, it, Z)
@@ -176,10 +190,12 @@ def test_blocking_sweeps(orc, olib, name):
             ctx.draw_proposal_path(l, it); ok_o = ora.draw(l, it)
         assert np.array_equal(ctx.get_success(l), ok_o)
         lld, llo = ctx.get_ll(l, 1), ora.ll(l, 1)
-        assert rel_err(lld, llo) < 1e-9
-        # ll° - ll is what decides; compare it directly too
+        assert rel_err(lld, llo, tag="blocking/%s/ll_prop" % name) < TOL_K5
+        # ll° - ll is what decides; compare it directly too, against the size of the two terms it is the difference of
         dd, do = lld - ctx.get_ll(l, 0), llo - ora.ll(l, 0)
-        assert np.allclose(dd[np.isfinite(do)], do[np.isfinite(do)], rtol=0, atol=1e-7 * max(1.0, np.abs(do[np.isfinite(do)]).max()))
+        fin = np.isfinite(do)
+        assert np.array_equal(np.isfinite(dd), fin)
+        assert rel_err(dd[fin], do[fin], floor=max(1.0, np.abs(llo[fin]).max()), tag="blocking/%s/ll_diff" % name) < TOL_K5
         if it < 3:
             E = rng.exponential(size=(len(prob.layouts[l][0]), prob.M))
             ctx.accept_reject_path(l, it, E); acc_o, _ = ora.accept(l, it, E)
@@ -187,9 +203,83 @@ def test_blocking_sweeps(orc, olib, name):
             ctx.accept_reject_path(l, it); acc_o, _ = ora.accept(l, it)
         assert np.array_equal(ctx.get_last_accept(l), acc_o)
         n_acc += acc_o.sum()
-        assert rel_err(ctx.get_X(0), ora.X(0)) < 1e-9
-        assert rel_err(ctx.get_W(0), ora.W(0)) < 1e-9
+        assert rel_err(ctx.get_X(0), ora.X(0), tag="blocking/%s/X" % name) < TOL_K5
+        assert rel_err(ctx.get_W(0), ora.W(0), tag="blocking/%s/W" % name) < TOL_K5
     assert n_acc > 0
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_fused_blocking_sweep_against_the_oracle(orc, olib, name):
+    """dmt_blocking_sweep (ONE fused forward pass: K5 + K4 + K3 + K2 + K4, fwd_kernel<Model, OP_SWEEP>) against the oracle's five
+    separate reference calls, six sweeps over two staggered layouts, each side running the loop on its own."""
+    K = 8
+    prob = blocking_problem(name, M=41, K=K, seed=6, nsteps=11)
+    ctx = make_ctx(prob, seed=13, ll_hist_len=6, n_layouts=3)
+    ora = OracleEnsemble(orc, olib, prob, seed=13)
+    ctx.set_blocks(2, [(0, K - 1)], 0.0)
+    ctx.recompute_guiding_term(2, _lib.P_ONLY)
+    assert ctx.init_paths(2, iter0=1000, max_tries=50) == 0
+    X, W = ctx.get_X(0), ctx.get_W(0)
+    for s in (0, 1):
+        ora.set_X(s, X); ora.set_W(s, W)
+    n_acc = 0
+    for it in range(6):
+        l = it % 2
+        i_mc = it // 2                       # the reference loop: ONE iteration index for both layouts
+        ctx.blocking_sweep(l, i_mc)
+        ora.set_artificial_obs(l); ora.recompute_guiding_term(l); ora.find_W_for_X(l); ora.loglikhd(l); ok_o = ora.draw(l, i_mc)
+        assert np.array_equal(ctx.get_success(l), ok_o)
+        assert rel_err(ctx.get_W(0), ora.W(0), tag="fused/%s/W_K5" % name) < TOL_K5
+        assert rel_err(ctx.get_ll(l, 0), ora.ll(l, 0), tag="fused/%s/ll" % name) < TOL_K5
+        assert rel_err(ctx.get_ll(l, 1), ora.ll(l, 1), tag="fused/%s/ll_prop" % name) < TOL_K5
+        good = ok_o.all(axis=0)
+        assert rel_err(ctx.get_X(1)[:, :, good], ora.X(1)[:, :, good], tag="fused/%s/X_prop" % name) < TOL_K5
+        assert rel_err(ctx.get_W(1)[:, :, good], ora.W(1)[:, :, good], tag="fused/%s/W_prop" % name) < TOL_K5
+        ctx.accept_reject_path(l, i_mc); acc_o, hist_o = ora.accept(l, i_mc)
+        assert np.array_equal(ctx.get_last_accept(l), acc_o)
+        assert np.array_equal(ctx.get_accept_history(l, i_mc, i_mc)[0], acc_o)
+        n_acc += acc_o.sum()
+        assert rel_err(ctx.get_X(0), ora.X(0), tag="fused/%s/X" % name) < TOL_K5
+    assert n_acc > 0
+    ctx.close()
+
+
+@pytest.mark.own_lanes
+@pytest.mark.parametrize("blocking", [False, True])
+def test_backward_filter_thread_per_pset_kernel_for_the_wide_model(orc, olib, blocking):
+    """Jansen-Rit (d = 6) K1 through bwd_kernel<JansenRit> — the one-thread-per-parameter-set kernel and its per-grid-point store
+    branch — which the automatic choice never takes for terminal blocks (dmt_set_bwd_mode(1) forces it), against the oracle and
+    against the cooperative kernel; with blocking also the covariance-form recursion at d = 6."""
+    K = 6
+    if blocking:
+        prob = small_problem("jr", M=35, K=K, layouts=[([(0, 2), (3, 5)], 0.7)], seed=3, nsteps=11)
+        prob.eps = 1e-4
+    else:
+        prob = small_problem("jr", M=35, K=K, seed=3, nsteps=11)
+    ora = OracleEnsemble(orc, olib, prob, seed=1)
+    ctx = make_ctx(prob, seed=1)
+    rng = np.random.default_rng(3)
+    if blocking:
+        X = ora.X(0) + 0.0
+        X[:] = np.array(configs.X0[configs.JR])[None, :, None] * (1 + 0.01 * rng.normal(size=X.shape))
+        ctx.set_X(X, 0); ora.set_X(0, X)
+        ctx.set_artificial_obs(0); ora.set_artificial_obs(0)
+    ora.recompute_guiding_term(0)
+    got = {}
+    for mode in ((1,) if blocking else (1, 2)):
+        ctx.set_bwd_mode(mode)
+        ctx.recompute_guiding_term(0, _lib.P_ONLY)
+        for k in range(K):
+            store = 1 if (blocking and k == 2) else 0
+            compare_guiding(ctx, ora, k, 0, store, tol=TOL, tag="jr_k1_mode%d%s" % (mode, "_blocking" if blocking else ""))
+        got[mode] = [ctx.get_guiding_term(k, 0, 0)[:2] for k in range(K)]
+    if not blocking:
+        for (H1, F1), (H2, F2) in zip(got[1], got[2]):
+            assert rel_err(H2[:-1], H1[:-1]) < 1e-11 and rel_err(F2[:-1], F1[:-1]) < 1e-11
+    else:
+        with pytest.raises(dmt_b200.DmtError):       # cooperative kernel: terminal blocks only, refuses instead of falling back
+            ctx.set_bwd_mode(2); ctx.recompute_guiding_term(0, _lib.P_ONLY)
     ctx.close()
 
 

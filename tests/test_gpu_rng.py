@@ -15,9 +15,10 @@ def test_normals_match_oracle(orc, olib, name):
     prob = configs.make_problem(name, 4, K=2, seed=1)
     ctx = make_ctx(prob, seed=0xD1FF00012345)
     nc, nt = 64, 50
-    z = ctx.debug_normals(7, 1000, 3, nc, nt)
-    zo = np.stack([[orc.tile_normals(olib, 0xD1FF00012345, 7 + c, 1000 + q, 3, prob.dw) for q in range(nt)] for c in range(nc)])
-    assert np.abs(z - zo).max() < 1e-14 * max(1.0, np.abs(zo).max())
+    for lay in (0, 5):
+        z = ctx.debug_normals(7, 1000, 3, nc, nt, layout=lay)
+        zo = np.stack([[orc.tile_normals(olib, 0xD1FF00012345, 7 + c, 1000 + q, 3, prob.dw, layout=lay) for q in range(nt)] for c in range(nc)])
+        assert np.abs(z - zo).max() < 1e-14 * max(1.0, np.abs(zo).max())
     ctx.close()
 
 
@@ -46,4 +47,34 @@ def test_normal_moments_and_tails_at_scale():
     zz = z.reshape(-1, 12)
     cm = np.corrcoef(zz.T)
     assert np.abs(cm - np.eye(12)).max() < 6 / np.sqrt(zz.shape[0])
+    ctx.close()
+
+
+def test_layouts_swept_with_the_same_iteration_get_independent_innovations():
+    """The reference loop uses ONE iteration index for all layouts (docs/src/tutorials/biblock/smoothing_with_blocking.md:32-59):
+    the pCN counter carries the layout id, so two sweeps of the same (chain, tile, iteration) never reuse xi."""
+    prob = configs.make_problem("lorenz", 4, K=2, seed=1)
+    ctx = make_ctx(prob, seed=2026)
+    za = ctx.debug_normals(0, 0, 9, 256, 64, layout=0).ravel()
+    zb = ctx.debug_normals(0, 0, 9, 256, 64, layout=1).ravel()
+    assert not np.any(za == zb)
+    assert abs(np.corrcoef(za, zb)[0, 1]) < 6 / np.sqrt(za.size)
+    ctx.close()
+
+
+@pytest.mark.own_lanes
+def test_two_layouts_same_iteration_draws_are_independent_pcn_moves():
+    """End to end: after layout A accepts at iteration i, layout B's proposal at the SAME i must not be rho W + c xi with the xi that is
+    already inside W: with rho = 0 the two proposals' noise must be uncorrelated."""
+    K = 4
+    layouts = [([(0, K - 1)], 0.0), ([(0, K - 1)], 0.0)]
+    prob = configs.make_problem("lorenz", 64, K=K, dt=0.01, seed=3, layouts=layouts)
+    ctx = make_ctx(prob, seed=5)
+    for l in (0, 1):
+        ctx.recompute_guiding_term(l, _lib.P_ONLY)
+    assert ctx.init_paths(0, 1000, 20) == 0
+    ctx.draw_proposal_path(0, 7); Wa = ctx.get_W(1).copy()
+    ctx.draw_proposal_path(1, 7); Wb = ctx.get_W(1).copy()
+    assert not np.array_equal(Wa, Wb)
+    assert abs(np.corrcoef(Wa.ravel(), Wb.ravel())[0, 1]) < 6 / np.sqrt(Wa.size)
     ctx.close()

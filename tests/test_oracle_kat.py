@@ -27,6 +27,20 @@ def test_philox_kat(orc, olib, ctr, key, exp):
     assert tuple(orc.philox(olib, ctr, key)) == exp
 
 
+def test_tile_normals_depend_on_layout(orc, olib):
+    """two layouts swept with the same (chain, tile, iteration) draw different innovations (counter word 3 carries the layout id)"""
+    a = np.concatenate([orc.tile_normals(olib, 1234, c, 7, 3, 3, layout=0) for c in range(2000)])
+    b = np.concatenate([orc.tile_normals(olib, 1234, c, 7, 3, 3, layout=1) for c in range(2000)])
+    assert not np.any(a == b) and abs(np.corrcoef(a, b)[0, 1]) < 6 / np.sqrt(a.size)
+    # counter layout: word3 = stream << 24 | layout << 8 | call, stream 3 = pCN
+    o = orc.philox(olib, [5, 7, 3, (3 << 24) | (2 << 8) | 1], [1234, 0])
+    w0 = (o[1] << 32) | o[0]; w1 = (o[3] << 32) | o[2]
+    u1 = ((w0 >> 11) + 1) * 2.0 ** -53; u2 = (w1 >> 11) * 2.0 ** -53
+    z = orc.tile_normals(olib, 1234, 5, 7, 3, 3, layout=2)
+    r = np.sqrt(-2 * np.log(u1))
+    assert abs(z[2] - r * np.cos(2 * np.pi * u2)) < 1e-14 and abs(z[3] - r * np.sin(2 * np.pi * u2)) < 1e-14
+
+
 def test_tile_normals_moments(orc, olib):
     z = np.concatenate([orc.tile_normals(olib, 1234, c, 7, 3, 3) for c in range(20000)])
     assert abs(z.mean()) < 0.01 and abs(z.std() - 1) < 0.01
