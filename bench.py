@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--one-call", action="store_true", help="blocking sweep through dmt_blocking_sweep (same launches; per-kernel timing is then not available)")
     ap.add_argument("--no-cache", action="store_true", help="blocking sweep with the full backward filter every sweep (no guiding cache)")
     ap.add_argument("--separate", action="store_true", help="blocking sweep with the three separate passes instead of the fused one")
+    ap.add_argument("--sweep-mode", type=int, default=0, help="fused pass: 0 auto (software-pipelined where eligible), 1 register-tile kernel, 2 pipelined")
+    ap.add_argument("--eager-noise", action="store_true", help="blocking sweep stores W_acc / W° every sweep (default: lazy noise, rebuilt on demand)")
     return ap.parse_args()
 
 
@@ -174,6 +176,8 @@ def gpu_arm(a):
     ctx = dmt_b200.Ctx(prob.model, prob.n_pts, prob.tt, prob.M, prob.P, obs_dim=prob.m, device=local, n_layouts=nlay + 1,
                        chain_offset=rank * M, seed=2026, pset_of_chain=prob.pset_of_chain)
     configs.upload(prob, ctx)
+    ctx.set_sweep_mode(a.sweep_mode)
+    lazy = blocking and not a.eager_noise and not a.separate and a.sweep_mode != 1
     whole = nlay
     ctx.set_blocks(whole, [(0, prob.K - 1)], 0.0)
     ctx.recompute_guiding_term(whole, _lib.P_ONLY)
@@ -182,7 +186,9 @@ def gpu_arm(a):
     if not blocking:
         ctx.recompute_guiding_term(0, _lib.P_ONLY)
         ctx.loglikhd(0, 0, 0)
-    elif not a.no_cache:  # smoothing: the laws stay fixed, only the blocks' frozen end points move => K1 through the guiding cache
+    if lazy:
+        ctx.set_lazy_noise(True)
+    if blocking and not a.no_cache:  # smoothing: the laws stay fixed, only the blocks' frozen end points move => K1 through the guiding cache
         for l in range(nlay):
             ctx.enable_guiding_cache(l)
     allreduce_kind = "none"
@@ -306,7 +312,7 @@ def gpu_arm(a):
     if fused:
         # the fused pass reads X_acc and H,F and writes W_acc, W°, X°; the accepted noise never leaves registers, so it moves
         # 8(2d + 2dw) + 8(d(d+1)/2 + d) = 168 B per step for Lorenz — LESS than SURVEY §8(d)'s draw (144) + K5/K4 (48) figures
-        bpu = 8 * (2 * prob.d + 2 * prob.dw) + (8 * (prob.d * (prob.d + 1) // 2 + prob.d) if prob.P == prob.M else 0)
+        bpu = 8 * (2 * prob.d + (0 if lazy else 2 * prob.dw)) + (8 * (prob.d * (prob.d + 1) // 2 + prob.d) if prob.P == prob.M else 0)
         kname, kop = "sweep_fused", "OP_SWEEP"
     algo_bytes = bpu * prob.M * prob.steps_per_chain
     achieved = algo_bytes / (kern_ms[kname] * 1e-3) / 1e9

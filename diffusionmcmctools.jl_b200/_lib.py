@@ -84,6 +84,8 @@ SIGNATURES = {
     "dmt_enable_guiding_cache": (C.c_int32, [_vp, C.c_int32, C.c_int32]),
     "dmt_set_fwd_lanes": (C.c_int32, [_vp, C.c_int32]),
     "dmt_set_bwd_mode": (C.c_int32, [_vp, C.c_int32]),
+    "dmt_set_sweep_mode": (C.c_int32, [_vp, C.c_int32]),
+    "dmt_set_lazy_noise": (C.c_int32, [_vp, C.c_int32]),
     "dmt_get_X_chains": (C.c_int32, [_vp, C.c_int32, C.c_int32, _ip, _dp]),
     "dmt_get_W_chains": (C.c_int32, [_vp, C.c_int32, C.c_int32, _ip, _dp]),
     "dmt_get_layout_guiding_term": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _dp]),
@@ -438,6 +440,14 @@ class Ctx:
     def set_fwd_lanes(self, lanes):
         """lanes per (chain, block) in the forward kernel: 0 = automatic, or 1 / 2 / 4 / 8 (results are identical)"""
         self._ck(self.lib.dmt_set_fwd_lanes(self.h, int(lanes)))
+
+    def set_sweep_mode(self, mode):
+        """fused blocking-sweep pass: 0 = automatic, 1 = register-tile kernel, 2 = software-pipelined kernel (or error)"""
+        self._ck(self.lib.dmt_set_sweep_mode(self.h, int(mode)))
+
+    def set_lazy_noise(self, enable=True):
+        """blocking sweeps stop materialising W / W° (rebuilt from X on demand); see include/dmt.h"""
+        self._ck(self.lib.dmt_set_lazy_noise(self.h, int(bool(enable))))
 
     def set_bwd_mode(self, mode):
         """thread mapping of the backward filter: 0 = automatic, 1 = thread per parameter set, 2 = cooperative lanes"""

@@ -3,6 +3,7 @@
 #include "../../include/dmt.h"
 #include "kernels.cuh"
 #include "fwd_kernel.cuh"
+#include "sweep_kernel.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -167,6 +168,11 @@ struct dmt_ctx {
     DevBuf<double> d_snap;
     DevBuf<int> d_snap_sel;
     bool tma_ok = false;     // P == M with the identity pset map: the TMA fast path of fwd_kernel is usable
+    bool pipe_ok = false;    // P == M with the identity pset map: a warp's guiding-term sectors are contiguous (sweep_pipe_kernel)
+    int sweep_mode = 0;      // dmt_set_sweep_mode: 0 = automatic (pipelined where eligible), 1 = register-tile kernel, 2 = pipelined or error
+    bool lazy_W = false;     // dmt_set_lazy_noise: blocking sweeps do not materialise W_acc / W°
+    int W_stale_layout = -1; // >= 0: W_acc is not materialised; K5 over this layout rebuilds it (ensure_W)
+    int G_owner = -1;        // layout whose K1 wrote the shared accepted-law store last (-1: unknown / laws changed)
     bool parP_mixed = false; // a masked swap_PP! made the law parity chain-dependent
 
     double *scratch(size_t n) {
@@ -255,9 +261,61 @@ template <class MD, int OP> void launch_fwd_model(dmt_ctx *c, Layout &L, const F
 }
 
 void ensure_guiding(dmt_ctx *c, Layout &L);
+void ensure_W(dmt_ctx *c);
+bool covers_all_intervals(dmt_ctx *c, const Layout &L) {
+    std::vector<char> seen(c->K, 0);
+    for (int b = 0; b < L.nb; b++)
+        for (int k = L.i0[b]; k <= L.i1[b]; k++) seen[k] = 1;
+    return std::all_of(seen.begin(), seen.end(), [](char s) { return s != 0; });
+}
+
+// the software-pipelined sweep (sweep_kernel.cuh): one parameter set per chain in chain order, uniform law parity, device RNG
+template <class MD> bool launch_sweep_pipe(dmt_ctx *c, Layout &L, const FwdArgs &fa) {
+    static int env_off = -1;
+    if (env_off < 0) env_off = getenv("DMT_NO_SWEEP_PIPE") ? 1 : 0;
+    const bool eligible = c->pipe_ok && !c->parP_mixed && !fa.Z && fa.skip == 0;
+    if (c->sweep_mode == 2 && !eligible)
+        throw DmtError(DMT_ERR_UNSUPPORTED, "pipelined sweep needs one parameter set per chain in chain order, uniform law parity and device RNG");
+    if (!eligible || c->sweep_mode == 1 || (c->sweep_mode == 0 && (c->fwd_lanes != 0 || env_off))) return false;
+    const bool lazy = c->lazy_W && covers_all_intervals(c, L);
+    constexpr size_t smem = sweep_pipe_smem<MD>();
+    static bool attr_done[64][2] = {};
+    const int dev = c->cfg.device & 63;
+    if (!attr_done[dev][lazy]) {
+        if (lazy) CK(cudaFuncSetAttribute(sweep_pipe_kernel<MD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else CK(cudaFuncSetAttribute(sweep_pipe_kernel<MD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done[dev][lazy] = true;
+    }
+    const dim3 grid((unsigned)((c->M + 31) / 32), L.nb, 1);
+    if (lazy) {
+        sweep_pipe_kernel<MD, true><<<grid, 32, smem, c->stream>>>(c->dev, L.dev, fa);
+        c->W_stale_layout = L.dev.id;
+    } else {
+        sweep_pipe_kernel<MD, false><<<grid, 32, smem, c->stream>>>(c->dev, L.dev, fa);
+    }
+    return true;
+}
 
 template <int OP> void launch_fwd(dmt_ctx *c, Layout &L, const FwdArgs &fa) {
+    // lazy noise (dmt_set_lazy_noise): an op that reads W, or rewrites only part of it, first rebuilds it from X; an op that
+    // rewrites all of it just clears the flag
+    if (c->W_stale_layout >= 0 && OP != OP_LOGLIK) {
+        const bool rewrites_all = (OP == OP_INIT) || ((OP == OP_INVSOLVE || OP == OP_INVSOLVE_LL || OP == OP_SWEEP) && covers_all_intervals(c, L));
+        if (rewrites_all) c->W_stale_layout = -1;
+        else ensure_W(c);
+    }
     ensure_guiding(c, L);
+    if (OP == OP_SWEEP) {
+        bool done = false;
+#define DMT_CASE(MID)                                                                                              \
+    case MID: done = launch_sweep_pipe<Model<MID>>(c, L, fa); break;
+        switch (c->cfg.model) {
+            DMT_FOR_MODELS(DMT_CASE)
+            default: throw DmtError(DMT_ERR_UNSUPPORTED, "model not compiled into this build of libdmt");
+        }
+#undef DMT_CASE
+        if (done) { CK(cudaGetLastError()); return; }
+    }
 #define DMT_CASE(MID)                                                                                              \
     case MID: launch_fwd_model<Model<MID>, OP>(c, L, fa); break;
     switch (c->cfg.model) {
@@ -284,6 +342,7 @@ template <class MD> void launch_bwd_model(dmt_ctx *c, Layout &L, const BwdArgs &
 }
 
 void launch_bwd(dmt_ctx *c, Layout &L, int side_mask, const double *v_override = nullptr) {
+    if ((side_mask & 1) && !(L.cache_enabled && L.dev.Gl[0])) c->G_owner = v_override ? -1 : L.dev.id; // accepted laws, shared store
     BwdArgs ba{};
     ba.side_mask = side_mask;
     if (v_override) {
@@ -316,7 +375,8 @@ void cache_set_private(Layout &L, bool on) {
         L.dev.c0l[st] = on ? L.d_c0l[st].p : nullptr;
     }
 }
-void invalidate_caches(dmt_ctx *c) {
+void invalidate_caches(dmt_ctx *c) { // every caller is about to change the accepted laws (or just did, for parity flips)
+    c->G_owner = -1;
     for (auto &L : c->layouts) {
         L.cache_valid = false;
         L.F_stale = false;
@@ -386,6 +446,15 @@ void cache_build(dmt_ctx *c, Layout &L) {
         throw;
     }
     L.cache_valid = true;
+}
+// dmt_set_lazy_noise: W_acc := the noise that reproduces X_acc under the law of the layout swept last (find_W_for_X!, K5)
+void ensure_W(dmt_ctx *c) {
+    if (c->W_stale_layout < 0) return;
+    Layout &L = c->layouts[c->W_stale_layout];
+    c->W_stale_layout = -1; // (first: launch_fwd below would recurse otherwise)
+    const bool priv = L.cache_enabled && L.cache_valid;
+    if (!priv && c->G_owner != L.dev.id) launch_bwd(c, L, DMT_P_ONLY); // another layout's K1 has overwritten the shared store since
+    launch_fwd<OP_INVSOLVE>(c, L, FwdArgs{0, 0, 0, 0, nullptr});
 }
 // F_stale: the private store's F belongs to older block end points than the current artificial observations (set by paths that
 // defer cache_apply); every forward launch materialises it first.  dmt_blocking_sweep itself applies the cache eagerly.
@@ -577,6 +646,7 @@ int32_t dmt_create(const dmt_config *cfg, const int32_t *n_pts, const double *tt
             bool ident = (c->P == c->M);
             for (int i = 0; i < c->M && ident; i++) ident = (pset[i] == i);
             c->tma_ok = ident && getenv("DMT_TMA") != nullptr;
+            c->pipe_ok = ident;
         }
         c->d_tile0.alloc(K + 1); c->d_step0.alloc(K + 1); c->d_pt0.alloc(K + 1); c->d_nsteps.alloc(K); c->d_ppb_tile0.alloc(K);
         c->d_pset.alloc(c->M); c->d_dt.alloc(dt.size()); c->d_sqdt.alloc(sq.size());
@@ -674,7 +744,7 @@ int32_t dmt_get_stream(dmt_ctx *ctx, void **s) {
 int32_t dmt_set_params(dmt_ctx *ctx, int32_t side, int32_t store_mask, int32_t k0, int32_t k1, const double *theta) {
     return guarded(ctx, [&] {
         check_law_side(ctx, side); check_range(ctx, k0, k1);
-        if (side == 0) invalidate_caches(ctx); // the accepted laws change: cached guiding terms are stale
+        if (side == 0) { ensure_W(ctx); invalidate_caches(ctx); } // the accepted laws change: cached guiding terms are stale
         REQUIRE(theta && (store_mask & 3), DMT_ERR_ARG, "null theta or empty store mask");
         for (int st = 0; st < 2; st++)
             if ((store_mask >> st) & 1)
@@ -685,7 +755,7 @@ int32_t dmt_set_params(dmt_ctx *ctx, int32_t side, int32_t store_mask, int32_t k
 int32_t dmt_set_aux(dmt_ctx *ctx, int32_t side, int32_t store, int32_t k0, int32_t k1, const double *B, const double *beta, const double *atil) {
     return guarded(ctx, [&] {
         check_law_side(ctx, side); check_range(ctx, k0, k1);
-        if (side == 0) invalidate_caches(ctx); // the accepted laws change: cached guiding terms are stale
+        if (side == 0) { ensure_W(ctx); invalidate_caches(ctx); } // the accepted laws change: cached guiding terms are stale
         REQUIRE(store == 0 || store == 1, DMT_ERR_ARG, "store must be 0 (PP) or 1 (PPb)");
         REQUIRE(B && beta && atil, DMT_ERR_ARG, "null aux array");
         const int D = ctx->D, NH = ctx->NH, nk = k1 - k0 + 1;
@@ -709,7 +779,7 @@ int32_t dmt_set_aux(dmt_ctx *ctx, int32_t side, int32_t store, int32_t k0, int32
 int32_t dmt_set_aux_linearised(dmt_ctx *ctx, int32_t side, int32_t store, int32_t k0, int32_t k1, const double *xbar) {
     return guarded(ctx, [&] {
         check_law_side(ctx, side); check_range(ctx, k0, k1);
-        if (side == 0) invalidate_caches(ctx); // the accepted laws change: cached guiding terms are stale
+        if (side == 0) { ensure_W(ctx); invalidate_caches(ctx); } // the accepted laws change: cached guiding terms are stale
         REQUIRE(store == 0 || store == 1, DMT_ERR_ARG, "store must be 0 (PP) or 1 (PPb)");
         const size_t per_k = (size_t)ctx->D * ctx->P, n = (size_t)(k1 - k0 + 1) * per_k;
         if (ctx->d_xbar[store].n < (size_t)ctx->K * per_k) { ctx->d_xbar[store].alloc((size_t)ctx->K * per_k); ctx->xbar_set[store].assign(ctx->K, 0); }
@@ -736,7 +806,7 @@ int32_t dmt_set_aux_linearised(dmt_ctx *ctx, int32_t side, int32_t store, int32_
 int32_t dmt_set_obs(dmt_ctx *ctx, int32_t side, int32_t k0, int32_t k1, const double *L, const double *Sigma, const double *v) {
     return guarded(ctx, [&] {
         check_law_side(ctx, side); check_range(ctx, k0, k1);
-        if (side == 0) invalidate_caches(ctx); // the accepted laws change: cached guiding terms are stale
+        if (side == 0) { ensure_W(ctx); invalidate_caches(ctx); } // the accepted laws change: cached guiding terms are stale
         REQUIRE(L && Sigma && v, DMT_ERR_ARG, "null observation array");
         const int m = ctx->m, D = ctx->D;
         double *r0 = ctx->d_obs[0].p, *r1 = ctx->d_obs[1].p;
@@ -835,6 +905,10 @@ int32_t dmt_set_start(dmt_ctx *ctx, const double *x0) {
 static void xfer_paths(dmt_ctx *ctx, int side, double *host, bool is_x, bool upload) {
     check_side(ctx, side);
     REQUIRE(host, DMT_ERR_ARG, "null host array");
+    if (!is_x) { // lazy noise: reading W materialises it first; overwriting the accepted noise makes it current
+        if (upload && side == 0) ctx->W_stale_layout = -1;
+        else ensure_W(ctx);
+    }
     const size_t n = is_x ? (size_t)ctx->NP * ctx->D * ctx->M : (size_t)ctx->S * ctx->DW * ctx->M;
     DevBuf<double> nat;
     nat.alloc(n, false);
@@ -880,6 +954,7 @@ int32_t dmt_snapshot_paths_async(dmt_ctx *ctx, int32_t side, int32_t n_sel, cons
 // bb.b.XX / bb.b.WW of a few recordings (the reference reads them per recording: be.recordings[i].blocks[j].b.XX)
 static void get_paths_of(dmt_ctx *ctx, int side, int n_sel, const int32_t *chains, double *out, bool is_x) {
     check_side(ctx, side);
+    if (!is_x) ensure_W(ctx);
     REQUIRE(n_sel >= 1 && chains && out, DMT_ERR_ARG, "bad chain selection");
     for (int i = 0; i < n_sel; i++) REQUIRE(chains[i] >= 0 && chains[i] < ctx->M, DMT_ERR_ARG, "chain index out of range");
     const size_t n = (is_x ? (size_t)ctx->NP * ctx->D : (size_t)ctx->S * ctx->DW) * n_sel;
@@ -1052,6 +1127,7 @@ int32_t dmt_swap(dmt_ctx *ctx, int32_t layout, int32_t what, const uint8_t *chai
     return guarded(ctx, [&] {
         Layout &L = layout_of(ctx, layout);
         REQUIRE(what > 0 && what < 16, DMT_ERR_ARG, "empty or unknown swap mask");
+        if (what & (DMT_SWAP_WW | DMT_SWAP_PP)) ensure_W(ctx); // (lazy noise) the noise about to change sides / laws must exist
         const uint8_t *dm = nullptr;
         if (chain_mask) {
             REQUIRE(!(what & DMT_SWAP_PP) || ctx->P == ctx->M, DMT_ERR_UNSUPPORTED, "per-chain swap_PP! needs n_psets == n_chains");
@@ -1184,7 +1260,7 @@ int32_t dmt_accept_counts(dmt_ctx *ctx, int32_t layout, uint32_t it0, uint32_t i
 // ---------------------------------------------------------------------------------------------------------------- guiding term
 static void xfer_guiding(dmt_ctx *ctx, int side, int store, int k, double *H, double *F, double *c, bool upload, Layout *priv = nullptr) {
     check_law_side(ctx, side); check_range(ctx, k, k);
-    if (upload && side == 0) invalidate_caches(ctx);
+    if (upload && side == 0) { ensure_W(ctx); invalidate_caches(ctx); }
     REQUIRE(store == 0 || store == 1, DMT_ERR_ARG, "store must be 0 (PP) or 1 (PPb)");
     REQUIRE(store == 0 || ctx->ppb_tile0[k] >= 0, DMT_ERR_STATE, "interval has no blocking law in any registered layout");
     REQUIRE(H && F && c, DMT_ERR_ARG, "null");
@@ -1227,6 +1303,18 @@ int32_t dmt_set_fwd_lanes(dmt_ctx *ctx, int32_t lanes) {
     return guarded(ctx, [&] {
         if (lanes != 0 && lanes != 1 && lanes != 2 && lanes != 4 && lanes != 8) throw DmtError(DMT_ERR_ARG, "lanes must be 0 (auto), 1, 2, 4 or 8");
         ctx->fwd_lanes = lanes;
+    });
+}
+int32_t dmt_set_sweep_mode(dmt_ctx *ctx, int32_t mode) {
+    return guarded(ctx, [&] {
+        if (mode < 0 || mode > 2) throw DmtError(DMT_ERR_ARG, "mode must be 0 (auto), 1 (register-tile kernel) or 2 (software-pipelined kernel)");
+        ctx->sweep_mode = mode;
+    });
+}
+int32_t dmt_set_lazy_noise(dmt_ctx *ctx, int32_t enable) {
+    return guarded(ctx, [&] {
+        if (!enable) ensure_W(ctx);
+        ctx->lazy_W = enable != 0;
     });
 }
 int32_t dmt_set_bwd_mode(dmt_ctx *ctx, int32_t mode) {

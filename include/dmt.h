@@ -212,6 +212,22 @@ int32_t dmt_get_layout_guiding_term(dmt_ctx *ctx, int32_t layout, int32_t store,
  * per-recording loop, src/block_ensemble.jl:50, is serial). */
 int32_t dmt_set_fwd_lanes(dmt_ctx *ctx, int32_t lanes);
 
+/* ---- tuning: memory schedule of the fused blocking-sweep pass (dmt_blocking_sweep / dmt_find_W_loglikhd_draw) ----------
+ * 0 (default) = automatic: the software-pipelined kernel (guiding term through a TMA shared-memory ring, X double-buffered in
+ * registers; sweep_kernel.cuh) when every chain owns its parameter set in chain order, the law parity is uniform, Z == NULL and
+ * dmt_set_fwd_lanes is automatic; the register-tile kernel otherwise.  1 = always the register-tile kernel.  2 = pipelined kernel or
+ * DMT_ERR_UNSUPPORTED.  Same arithmetic, results equal up to FP64 rounding (different FMA contraction). */
+int32_t dmt_set_sweep_mode(dmt_ctx *ctx, int32_t mode);
+/* Lazy noise.  In the blocking loop find_W_for_X!(be) overwrites b.WW at the start of EVERY sweep
+ * (docs/src/tutorials/block_collection/inference_with_blocking.md:52-58, src/block.jl:120-131), so the accepted noise W and the
+ * proposal noise W° the sweep produces are never read.  With enable = 1 the pipelined sweep over a layout that covers all intervals
+ * does not store them (120 instead of 168 B per step for Lorenz); X, X°, ll, ll° and the accept decisions are unchanged.  The accepted
+ * noise is rebuilt on demand — by K5 over the layout swept last, i.e. exactly what find_W_for_X! would return — before anything
+ * reads it (dmt_get_W, dmt_get_W_chains, a draw or recompute_path! without a preceding find_W_for_X!, swap_WW!) or changes the
+ * accepted laws.  W° is unspecified while the mode is on.  Rebuilding after ANOTHER layout's GP.set_obs! has moved a shared block
+ * end point uses the current artificial observation (a difference of the order of sqrt(artificial_noise) in that block). */
+int32_t dmt_set_lazy_noise(dmt_ctx *ctx, int32_t enable);
+
 /* ---- tuning: thread mapping of the backward filter (K1) -------------------------------------------------------------
  * 0 (default) = automatic; 1 = one thread per (parameter set, block, side); 2 = d lanes share one parameter set, lane r owning
  * row r of H (wide states; DMT_ERR_UNSUPPORTED where it is not implemented).  Results agree to FP64 rounding. */

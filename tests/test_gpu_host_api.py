@@ -240,7 +240,8 @@ def test_set_proposal_law_escalates_critical_change_when_the_proposal_laws_had_t
 def test_observation_parameter_update_reaches_the_proposal_laws(orc, olib):
     """θ° entries that are parameters of the observations (updt_obs, src/param_names_collections.jl:125-141): the proposal-side
     (L, Σ, v) must be set AFTER the equalisation (src/biblock.jl:362-367), otherwise equalize_obs_params! wipes them out."""
-    from dmt_b200.param_names import ParamNamesAllObs
+    from dmt_b200 import param_names
+    ParamNamesAllObs = param_names.ParamNamesAllObs
     M = 5
     prob = configs.make_problem("fhn", M, K=4, dt=0.005, seed=13, rho=0.9)
     se = H.SamplingEnsemble(prob.model, recordings_of(prob), (prob.n_pts, prob.tt), seed=2, two_sided_laws=True)
