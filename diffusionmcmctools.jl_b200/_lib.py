@@ -45,6 +45,7 @@ SIGNATURES = {
     "dmt_get_stream": (C.c_int32, [_vp, C.POINTER(_vp)]),
     "dmt_model_dims": (C.c_int32, [C.c_int32, _ip, _ip, _ip, _ip]),
     "dmt_version": (C.c_int32, []),
+    "dmt_launch_count": (C.c_int32, [C.POINTER(C.c_uint64)]),
     "dmt_set_params": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _dp]),
     "dmt_set_aux": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _dp]),
     "dmt_set_aux_linearised": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _dp]),
@@ -120,6 +121,13 @@ def load():
             f.argtypes = args
         _lib = lib
     return _lib
+
+
+def launch_count():
+    """kernels launched by libdmt in this process so far"""
+    n = C.c_uint64(0)
+    load().dmt_launch_count(C.byref(n))
+    return int(n.value)
 
 
 def model_dims(model):

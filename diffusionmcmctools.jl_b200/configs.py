@@ -143,7 +143,7 @@ class Problem:
         return DIMS[self.model][1]
 
 
-def make_problem(name, M, P=None, K=None, obs_dt=None, dt=None, seed=0, layouts=None, rho=0.9, chain_offset=0, sim_sub=2):
+def make_problem(name, M, P=None, K=None, obs_dt=None, dt=None, seed=0, layouts=None, rho=0.9, chain_offset=0, sim_sub=2, theta=None):
     """Synthetic instance of one of the named configs.  Per-pset data are simulated with a numpy generator seeded by the
     GLOBAL pset index (chain_offset + p), so a sharded ensemble sees the same data as the unsharded one."""
     spec = {
@@ -156,7 +156,7 @@ def make_problem(name, M, P=None, K=None, obs_dt=None, dt=None, seed=0, layouts=
     dt = spec[3] if dt is None else dt
     P = M if P is None else P
     d, dw = DIMS[model]
-    th = np.array(THETA[model], dtype=np.float64)
+    th = np.array(THETA[model] if theta is None else theta, dtype=np.float64)
     L, Sigma = OBS[model]
     m = L.shape[0]
     tobs = obs_dt * np.arange(1, K + 1)

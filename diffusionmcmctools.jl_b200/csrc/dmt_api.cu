@@ -42,6 +42,7 @@ struct DmtError : std::runtime_error {
     } while (0)
 
 std::string g_create_error;
+unsigned long long g_launches = 0; // kernels launched by this library in this process (dmt_launch_count; a ctx is single-threaded)
 
 struct ModelDims { int D, DW, NPAR; bool constdiff; };
 bool model_dims(int model, ModelDims &md) {
@@ -217,7 +218,7 @@ template <class MD, int OP, bool TMA, int G> void launch_fwd_lanes(dmt_ctx *c, L
     }
     if (wave_threads) { *wave_threads = wave[dev]; return; } // query only
     const dim3 grid((unsigned)(((size_t)c->M * G + TPB - 1) / TPB), L.nb, 1);
-    fwd_kernel<MD, OP, TPB, TMA, G><<<grid, TPB, smem, c->stream>>>(c->dev, L.dev, fa);
+    ++g_launches, fwd_kernel<MD, OP, TPB, TMA, G><<<grid, TPB, smem, c->stream>>>(c->dev, L.dev, fa);
 }
 // Lanes per (chain, block): 1 when the ensemble fills the GPU by itself; 2, 4 or 8 when M x blocks x lanes still fits one wave
 // of the cooperative instantiation (the generator is split over the lanes, fwd_kernel.cuh).  DMT_FWD_LANES overrides.
@@ -288,10 +289,10 @@ template <class MD> bool launch_sweep_pipe(dmt_ctx *c, Layout &L, const FwdArgs 
     }
     const dim3 grid((unsigned)((c->M + 31) / 32), L.nb, 1);
     if (lazy) {
-        sweep_pipe_kernel<MD, true><<<grid, 32, smem, c->stream>>>(c->dev, L.dev, fa);
+        ++g_launches, sweep_pipe_kernel<MD, true><<<grid, 32, smem, c->stream>>>(c->dev, L.dev, fa);
         c->W_stale_layout = L.dev.id;
     } else {
-        sweep_pipe_kernel<MD, false><<<grid, 32, smem, c->stream>>>(c->dev, L.dev, fa);
+        ++g_launches, sweep_pipe_kernel<MD, false><<<grid, 32, smem, c->stream>>>(c->dev, L.dev, fa);
     }
     return true;
 }
@@ -335,9 +336,9 @@ template <class MD> void launch_bwd_model(dmt_ctx *c, Layout &L, const BwdArgs &
     if (coop_ok && c->bwd_mode != 1 && !getenv("DMT_NO_COOP_K1")) {
         // wide state, no exact-observation interval: D lanes per parameter set (kernels.cuh, bwd_coop_kernel)
         constexpr int per_cta = 4 * (32 / MD::D);
-        bwd_coop_kernel<MD><<<dim3((c->P + per_cta - 1) / per_cta, L.nb, nz), 128, 0, c->stream>>>(c->dev, L.dev, ba);
+        ++g_launches, bwd_coop_kernel<MD><<<dim3((c->P + per_cta - 1) / per_cta, L.nb, nz), 128, 0, c->stream>>>(c->dev, L.dev, ba);
     } else {
-        bwd_kernel<MD><<<pset_grid(c, L.nb, BWD_TPB, nz), BWD_TPB, 0, c->stream>>>(c->dev, L.dev, ba);
+        ++g_launches, bwd_kernel<MD><<<pset_grid(c, L.nb, BWD_TPB, nz), BWD_TPB, 0, c->stream>>>(c->dev, L.dev, ba);
     }
 }
 
@@ -387,9 +388,9 @@ void cache_apply(dmt_ctx *c, Layout &L) { // the per-sweep K1: F = F0 + Psi v ; 
     L.F_stale = false;
     const dim3 g0((c->P + 127) / 128, c->NT), g1((c->P + 127) / 128, std::max(c->NTb, 1));
     DMT_D_SWITCH(c->D,
-                 cache_apply_kernel<DD><<<g0, 128, 0, c->stream>>>(c->dev, L.dev, 0, c->d_k_of_tile.p);
-                 if (c->NTb > 0) cache_apply_kernel<DD><<<g1, 128, 0, c->stream>>>(c->dev, L.dev, 1, c->d_k_of_ppbtile.p);
-                 cache_apply_c_kernel<DD><<<pset_grid(c, L.nb, 128), 128, 0, c->stream>>>(c->dev, L.dev));
+                 ++g_launches, cache_apply_kernel<DD><<<g0, 128, 0, c->stream>>>(c->dev, L.dev, 0, c->d_k_of_tile.p);
+                 if (c->NTb > 0) ++g_launches, cache_apply_kernel<DD><<<g1, 128, 0, c->stream>>>(c->dev, L.dev, 1, c->d_k_of_ppbtile.p);
+                 ++g_launches, cache_apply_c_kernel<DD><<<pset_grid(c, L.nb, 128), 128, 0, c->stream>>>(c->dev, L.dev));
     CK(cudaGetLastError());
 }
 void cache_build(dmt_ctx *c, Layout &L) {
@@ -427,16 +428,16 @@ void cache_build(dmt_ctx *c, Layout &L) {
         for (int n = m + 1; n < D; n++) { std::vector<double> v(6, 0.0); v[m] = s; v[n] = s; probes.push_back(v); }
     for (int r = 0; r < nruns; r++) {
         launch_bwd(c, L, DMT_P_ONLY, probes[r].data());
-        cache_collect_c_kernel<<<pset_grid(c, L.nb, 128), 128, 0, c->stream>>>(c->dev, L.dev, r, Crun.p);
+        ++g_launches, cache_collect_c_kernel<<<pset_grid(c, L.nb, 128), 128, 0, c->stream>>>(c->dev, L.dev, r, Crun.p);
         if (r <= D) {
             const int mode = r == 0 ? 0 : 1, m = r - 1;
             DMT_D_SWITCH(c->D,
-                         cache_extract_kernel<DD><<<g0, 128, 0, c->stream>>>(c->dev, L.dev, 0, c->d_k_of_tile.p, mode, m, 1.0 / s);
-                         if (c->NTb > 0) cache_extract_kernel<DD><<<g1, 128, 0, c->stream>>>(c->dev, L.dev, 1, c->d_k_of_ppbtile.p, mode, m, 1.0 / s));
+                         ++g_launches, cache_extract_kernel<DD><<<g0, 128, 0, c->stream>>>(c->dev, L.dev, 0, c->d_k_of_tile.p, mode, m, 1.0 / s);
+                         if (c->NTb > 0) ++g_launches, cache_extract_kernel<DD><<<g1, 128, 0, c->stream>>>(c->dev, L.dev, 1, c->d_k_of_ppbtile.p, mode, m, 1.0 / s));
         }
         CK(cudaGetLastError());
     }
-    DMT_D_SWITCH(c->D, cache_solve_cq_kernel<DD><<<pset_grid(c, L.nb, 128), 128, 0, c->stream>>>(c->dev, L.dev, Crun.p, s));
+    DMT_D_SWITCH(c->D, ++g_launches, cache_solve_cq_kernel<DD><<<pset_grid(c, L.nb, 128), 128, 0, c->stream>>>(c->dev, L.dev, Crun.p, s));
     CK(cudaGetLastError());
     cache_apply(c, L); // the actual artificial observations
     CK(cudaStreamSynchronize(c->stream));
@@ -453,8 +454,11 @@ void ensure_W(dmt_ctx *c) {
     Layout &L = c->layouts[c->W_stale_layout];
     c->W_stale_layout = -1; // (first: launch_fwd below would recurse otherwise)
     const bool priv = L.cache_enabled && L.cache_valid;
-    if (!priv && c->G_owner != L.dev.id) launch_bwd(c, L, DMT_P_ONLY); // another layout's K1 has overwritten the shared store since
+    const int prev = c->G_owner;
+    const bool borrow = !priv && prev != L.dev.id; // another layout's K1 has overwritten the shared store since the sweep
+    if (borrow) launch_bwd(c, L, DMT_P_ONLY);
     launch_fwd<OP_INVSOLVE>(c, L, FwdArgs{0, 0, 0, 0, nullptr});
+    if (borrow && prev >= 0) launch_bwd(c, c->layouts[prev], DMT_P_ONLY); // give the store back to the layout the caller prepared it for
 }
 // F_stale: the private store's F belongs to older block end points than the current artificial observations (set by paths that
 // defer cache_apply); every forward launch materialises it first.  dmt_blocking_sweep itself applies the cache eagerly.
@@ -499,7 +503,7 @@ void put_record(dmt_ctx *c, int side, int store, double *rec0, double *rec1, int
     const size_t n = nk * ncomp * c->P;
     double *tmp = c->scratch(n);
     CK(cudaMemcpyAsync(tmp, host, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    put_record_kernel<<<pset_grid(c, k1 - k0 + 1, 128), 128, 0, c->stream>>>(c->dev, side, store, rec0, rec1, NREC, off, ncomp, k0,
+    ++g_launches, put_record_kernel<<<pset_grid(c, k1 - k0 + 1, 128), 128, 0, c->stream>>>(c->dev, side, store, rec0, rec1, NREC, off, ncomp, k0,
                                                                              k1, tmp, bcast_k ? 1 : 0);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream)); // the host buffer is the caller's; scratch is reused
@@ -542,9 +546,9 @@ void fill_stats(dmt_ctx *c, Layout &L, double *host_out /* [2+3nb] */) {
     const int ncta = (c->M + 255) / 256;
     if (c->d_partial.n < (size_t)3 * L.nb * ncta) c->d_partial.alloc((size_t)3 * L.nb * ncta);
     if (c->d_stats.n < (size_t)(2 + 3 * L.nb)) c->d_stats.alloc(2 + 3 * L.nb);
-    reduce_stats_kernel<<<dim3(ncta, L.nb), 256, 0, c->stream>>>(L.d_ll.p, L.d_last_acc.p, c->M, L.nb, c->d_partial.p);
+    ++g_launches, reduce_stats_kernel<<<dim3(ncta, L.nb), 256, 0, c->stream>>>(L.d_ll.p, L.d_last_acc.p, c->M, L.nb, c->d_partial.p);
     CK(cudaGetLastError());
-    finish_stats_kernel<<<1, 64, 0, c->stream>>>(c->d_partial.p, ncta, L.nb, c->d_stats.p);
+    ++g_launches, finish_stats_kernel<<<1, 64, 0, c->stream>>>(c->d_partial.p, ncta, L.nb, c->d_stats.p);
     CK(cudaGetLastError());
     if (host_out) {
         CK(cudaMemcpyAsync(host_out, c->d_stats.p, sizeof(double) * (2 + 3 * L.nb), cudaMemcpyDeviceToHost, c->stream));
@@ -572,7 +576,13 @@ template <class F> int32_t guarded(dmt_ctx *ctx, F &&f) {
 // =============================================================================================================== API
 extern "C" {
 
-int32_t dmt_version(void) { return 100; }
+int32_t dmt_version(void) { return 200; }
+
+int32_t dmt_launch_count(uint64_t *n) {
+    if (!n) return DMT_ERR_ARG;
+    *n = g_launches;
+    return DMT_OK;
+}
 
 int32_t dmt_model_dims(int32_t model, int32_t *d, int32_t *dw, int32_t *npar, int32_t *constdiff) {
     ModelDims md;
@@ -792,7 +802,7 @@ int32_t dmt_set_aux_linearised(dmt_ctx *ctx, int32_t side, int32_t store, int32_
         }
         dim3 grid = pset_grid(ctx, k1 - k0 + 1, 128);
 #define DMT_CASE(MID)                                                                                              \
-    case MID: aux_linearise_kernel<Model<MID>><<<grid, 128, 0, ctx->stream>>>(ctx->dev, side, store, k0, k1, tmp); break;
+    case MID: ++g_launches, aux_linearise_kernel<Model<MID>><<<grid, 128, 0, ctx->stream>>>(ctx->dev, side, store, k0, k1, tmp); break;
         switch (ctx->cfg.model) {
             DMT_FOR_MODELS(DMT_CASE)
         default: throw DmtError(DMT_ERR_UNSUPPORTED, "model not compiled into this build of libdmt");
@@ -824,9 +834,9 @@ int32_t dmt_equalize_laws(dmt_ctx *ctx, int32_t store_mask, int32_t k0, int32_t 
         CK(cudaMemsetAsync(ctx->d_flag.p, 0, sizeof(int), ctx->stream));
         for (int st = 0; st < 2; st++) {
             if (!((store_mask >> st) & 1)) continue;
-            copy_record_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->dev, st, ctx->d_theta[0][st].p, ctx->d_theta[1][st].p, ctx->NPAR, k0, k1, ctx->d_flag.p);
-            copy_record_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->dev, st, ctx->d_aux[0][st].p, ctx->d_aux[1][st].p, ctx->NAUX, k0, k1, ctx->d_flag.p);
-            if (st == 0) copy_record_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->dev, 0, ctx->d_obs[0].p, ctx->d_obs[1].p, ctx->NOBS, k0, k1, ctx->d_flag.p);
+            ++g_launches, copy_record_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->dev, st, ctx->d_theta[0][st].p, ctx->d_theta[1][st].p, ctx->NPAR, k0, k1, ctx->d_flag.p);
+            ++g_launches, copy_record_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->dev, st, ctx->d_aux[0][st].p, ctx->d_aux[1][st].p, ctx->NAUX, k0, k1, ctx->d_flag.p);
+            if (st == 0) ++g_launches, copy_record_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->dev, 0, ctx->d_obs[0].p, ctx->d_obs[1].p, ctx->NOBS, k0, k1, ctx->d_flag.p);
         }
         CK(cudaGetLastError());
         if (changed) { // b° had to be changed: its guiding term belongs to other parameters => the caller escalates critical_change
@@ -914,8 +924,8 @@ static void xfer_paths(dmt_ctx *ctx, int side, double *host, bool is_x, bool upl
     nat.alloc(n, false);
     if (upload) CK(cudaMemcpyAsync(nat.p, host, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     dim3 grid = chain_grid(ctx, ctx->K, 128);
-    if (is_x) xfer_X_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->dev, side, ctx->D, nat.p, upload ? 1 : 0);
-    else xfer_W_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->dev, side, ctx->DW, nat.p, upload ? 1 : 0);
+    if (is_x) ++g_launches, xfer_X_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->dev, side, ctx->D, nat.p, upload ? 1 : 0);
+    else ++g_launches, xfer_W_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->dev, side, ctx->DW, nat.p, upload ? 1 : 0);
     CK(cudaGetLastError());
     if (!upload) CK(cudaMemcpyAsync(host, nat.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -942,7 +952,7 @@ int32_t dmt_snapshot_paths_async(dmt_ctx *ctx, int32_t side, int32_t n_sel, cons
         if (ctx->d_snap.n < n) { CK(cudaStreamSynchronize(ctx->copy_stream)); ctx->d_snap.alloc(n, false); }
         if (ctx->d_snap_sel.n < (size_t)n_sel) { CK(cudaStreamSynchronize(ctx->copy_stream)); ctx->d_snap_sel.alloc(n_sel, false); }
         CK(cudaMemcpyAsync(ctx->d_snap_sel.p, chains, sizeof(int) * n_sel, cudaMemcpyHostToDevice, ctx->stream));
-        gather_X_kernel<<<dim3((n_sel + 63) / 64, ctx->K), 64, 0, ctx->stream>>>(ctx->dev, side, ctx->D, ctx->d_snap_sel.p, n_sel, ctx->d_snap.p);
+        ++g_launches, gather_X_kernel<<<dim3((n_sel + 63) / 64, ctx->K), 64, 0, ctx->stream>>>(ctx->dev, side, ctx->D, ctx->d_snap_sel.p, n_sel, ctx->d_snap.p);
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->ev_gathered, ctx->stream));
         // the copy runs on its own stream: the compute stream goes on with the next sweep while the paths travel
@@ -964,8 +974,8 @@ static void get_paths_of(dmt_ctx *ctx, int side, int n_sel, const int32_t *chain
     sel.alloc(n_sel, false);
     CK(cudaMemcpyAsync(sel.p, chains, sizeof(int) * n_sel, cudaMemcpyHostToDevice, ctx->stream));
     const dim3 grid((n_sel + 63) / 64, ctx->K);
-    if (is_x) gather_X_kernel<<<grid, 64, 0, ctx->stream>>>(ctx->dev, side, ctx->D, sel.p, n_sel, d.p);
-    else gather_W_kernel<<<grid, 64, 0, ctx->stream>>>(ctx->dev, side, ctx->DW, sel.p, n_sel, d.p);
+    if (is_x) ++g_launches, gather_X_kernel<<<grid, 64, 0, ctx->stream>>>(ctx->dev, side, ctx->D, sel.p, n_sel, d.p);
+    else ++g_launches, gather_W_kernel<<<grid, 64, 0, ctx->stream>>>(ctx->dev, side, ctx->DW, sel.p, n_sel, d.p);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, d.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1000,7 +1010,7 @@ int32_t dmt_init_paths(dmt_ctx *ctx, int32_t layout, uint32_t iter0, int32_t max
             for (uint8_t o : ok) bad += !o;
             if (!bad) break;
         }
-        copy_acc_to_prop_kernel<<<chain_grid(ctx, ctx->K, 128), 128, 0, ctx->stream>>>(ctx->dev, ctx->D, ctx->DW);
+        ++g_launches, copy_acc_to_prop_kernel<<<chain_grid(ctx, ctx->K, 128), 128, 0, ctx->stream>>>(ctx->dev, ctx->D, ctx->DW);
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(ctx->stream));
         if (n_failed) *n_failed = bad;
@@ -1011,7 +1021,7 @@ int32_t dmt_init_paths(dmt_ctx *ctx, int32_t layout, uint32_t iter0, int32_t max
 int32_t dmt_set_artificial_obs(dmt_ctx *ctx, int32_t layout) {
     return guarded(ctx, [&] {
         Layout &L = layout_of(ctx, layout);
-        set_artificial_obs_kernel<<<chain_grid(ctx, L.nb, 128), 128, 0, ctx->stream>>>(ctx->dev, L.dev, ctx->D);
+        ++g_launches, set_artificial_obs_kernel<<<chain_grid(ctx, L.nb, 128), 128, 0, ctx->stream>>>(ctx->dev, L.dev, ctx->D);
         CK(cudaGetLastError());
     });
 }
@@ -1078,7 +1088,7 @@ int32_t dmt_find_W_loglikhd_draw(dmt_ctx *ctx, int32_t layout, uint32_t iter, co
 int32_t dmt_blocking_sweep(dmt_ctx *ctx, int32_t layout, uint32_t iter) {
     return guarded(ctx, [&] {
         Layout &L = layout_of(ctx, layout);
-        set_artificial_obs_kernel<<<chain_grid(ctx, L.nb, 128), 128, 0, ctx->stream>>>(ctx->dev, L.dev, ctx->D); // GP.set_obs!(be)
+        ++g_launches, set_artificial_obs_kernel<<<chain_grid(ctx, L.nb, 128), 128, 0, ctx->stream>>>(ctx->dev, L.dev, ctx->D); // GP.set_obs!(be)
         CK(cudaGetLastError());
         if (L.cache_enabled) {                       // recompute_guiding_term!(be, Val(:P_only)) through the guiding cache
             if (!L.cache_valid) cache_build(ctx, L);
@@ -1117,7 +1127,7 @@ int32_t dmt_accept_reject_path(dmt_ctx *ctx, int32_t layout, uint32_t iter, cons
             CK(cudaMemcpyAsync(tmp, E, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
             dE = tmp;
         }
-        accept_kernel<<<chain_grid(ctx, L.nb, 128), 128, 0, ctx->stream>>>(ctx->dev, L.dev, iter, dE);
+        ++g_launches, accept_kernel<<<chain_grid(ctx, L.nb, 128), 128, 0, ctx->stream>>>(ctx->dev, L.dev, iter, dE);
         CK(cudaGetLastError());
         if (E) CK(cudaStreamSynchronize(ctx->stream));
     });
@@ -1136,12 +1146,12 @@ int32_t dmt_swap(dmt_ctx *ctx, int32_t layout, int32_t what, const uint8_t *chai
             dm = ctx->d_mask.p;
         }
         if (what & (DMT_SWAP_XX | DMT_SWAP_WW | DMT_SWAP_LL))
-            swap_paths_kernel<<<chain_grid(ctx, L.nb, 128), 128, 0, ctx->stream>>>(ctx->dev, L.dev, what, dm);
+            ++g_launches, swap_paths_kernel<<<chain_grid(ctx, L.nb, 128), 128, 0, ctx->stream>>>(ctx->dev, L.dev, what, dm);
         if (what & DMT_SWAP_PP) {
             check_law_side(ctx, 1);
             invalidate_caches(ctx); // the accepted laws are now the former proposals (their guiding term is in the shared store)
             if (chain_mask) ctx->parP_mixed = true;
-            swap_laws_kernel<<<pset_grid(ctx, L.nb, 128), 128, 0, ctx->stream>>>(ctx->dev, L.dev, dm);
+            ++g_launches, swap_laws_kernel<<<pset_grid(ctx, L.nb, 128), 128, 0, ctx->stream>>>(ctx->dev, L.dev, dm);
         }
         CK(cudaGetLastError());
         if (chain_mask) CK(cudaStreamSynchronize(ctx->stream));
@@ -1152,7 +1162,7 @@ int32_t dmt_save_ll(dmt_ctx *ctx, int32_t layout, uint32_t iter) {
     return guarded(ctx, [&] {
         Layout &L = layout_of(ctx, layout);
         REQUIRE(L.dev.hist_len > 0 && iter < (uint32_t)L.dev.hist_len, DMT_ERR_ARG, "iteration beyond ll_hist_len");
-        save_ll_kernel<<<chain_grid(ctx, L.nb, 128), 128, 0, ctx->stream>>>(ctx->dev, L.dev, iter);
+        ++g_launches, save_ll_kernel<<<chain_grid(ctx, L.nb, 128), 128, 0, ctx->stream>>>(ctx->dev, L.dev, iter);
         CK(cudaGetLastError());
     });
 }
@@ -1250,7 +1260,7 @@ int32_t dmt_accept_counts(dmt_ctx *ctx, int32_t layout, uint32_t it0, uint32_t i
         REQUIRE(counts && it0 <= it1 && it1 < (uint32_t)L.dev.hist_len, DMT_ERR_ARG, "bad history range");
         DevBuf<unsigned long long> d;
         d.alloc(L.nb);
-        accept_counts_kernel<<<chain_grid(ctx, L.nb, 128), 128, 0, ctx->stream>>>(L.d_acc_hist.p, L.nb, ctx->M, it0, it1, d.p);
+        ++g_launches, accept_counts_kernel<<<chain_grid(ctx, L.nb, 128), 128, 0, ctx->stream>>>(L.d_acc_hist.p, L.nb, ctx->M, it0, it1, d.p);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(counts, d.p, sizeof(int64_t) * L.nb, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
@@ -1275,7 +1285,7 @@ static void xfer_guiding(dmt_ctx *ctx, int side, int store, int k, double *H, do
     if (priv) ensure_guiding(ctx, *priv);
     double *Gpriv = (priv && priv->cache_valid && side == 0) ? priv->d_Gl[store].p : nullptr;
     double *cpriv = Gpriv ? priv->d_c0l[store].p : nullptr;
-    xfer_guiding_kernel<<<pset_grid(ctx, 1, 128), 128, 0, ctx->stream>>>(ctx->dev, side, store, k, ctx->D, dH.p, dF.p, dc.p, upload ? 1 : 0, Gpriv, cpriv);
+    ++g_launches, xfer_guiding_kernel<<<pset_grid(ctx, 1, 128), 128, 0, ctx->stream>>>(ctx->dev, side, store, k, ctx->D, dH.p, dF.p, dc.p, upload ? 1 : 0, Gpriv, cpriv);
     CK(cudaGetLastError());
     if (!upload) {
         CK(cudaMemcpyAsync(H, dH.p, dH.n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1346,10 +1356,10 @@ int32_t dmt_debug_normals(dmt_ctx *ctx, uint32_t chain0, uint32_t tile0, uint32_
         const int tot = n_chains * n_tiles;
         dim3 grid((tot + 127) / 128);
         switch (ctx->DW) {
-        case 1: debug_normals_kernel<1><<<grid, 128, 0, ctx->stream>>>(ctx->cfg.seed, chain0, tile0, iter, layout, n_chains, n_tiles, d.p); break;
-        case 2: debug_normals_kernel<2><<<grid, 128, 0, ctx->stream>>>(ctx->cfg.seed, chain0, tile0, iter, layout, n_chains, n_tiles, d.p); break;
-        case 3: debug_normals_kernel<3><<<grid, 128, 0, ctx->stream>>>(ctx->cfg.seed, chain0, tile0, iter, layout, n_chains, n_tiles, d.p); break;
-        default: debug_normals_kernel<4><<<grid, 128, 0, ctx->stream>>>(ctx->cfg.seed, chain0, tile0, iter, layout, n_chains, n_tiles, d.p); break;
+        case 1: ++g_launches, debug_normals_kernel<1><<<grid, 128, 0, ctx->stream>>>(ctx->cfg.seed, chain0, tile0, iter, layout, n_chains, n_tiles, d.p); break;
+        case 2: ++g_launches, debug_normals_kernel<2><<<grid, 128, 0, ctx->stream>>>(ctx->cfg.seed, chain0, tile0, iter, layout, n_chains, n_tiles, d.p); break;
+        case 3: ++g_launches, debug_normals_kernel<3><<<grid, 128, 0, ctx->stream>>>(ctx->cfg.seed, chain0, tile0, iter, layout, n_chains, n_tiles, d.p); break;
+        default: ++g_launches, debug_normals_kernel<4><<<grid, 128, 0, ctx->stream>>>(ctx->cfg.seed, chain0, tile0, iter, layout, n_chains, n_tiles, d.p); break;
         }
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(out, d.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1362,7 +1372,7 @@ int32_t dmt_debug_exponentials(dmt_ctx *ctx, uint32_t chain0, uint32_t iter, uin
         const int tot = n_chains * n_blocks;
         DevBuf<double> d;
         d.alloc(tot, false);
-        debug_exponentials_kernel<<<(tot + 127) / 128, 128, 0, ctx->stream>>>(ctx->cfg.seed, chain0, iter, layout, n_chains, n_blocks, d.p);
+        ++g_launches, debug_exponentials_kernel<<<(tot + 127) / 128, 128, 0, ctx->stream>>>(ctx->cfg.seed, chain0, iter, layout, n_chains, n_blocks, d.p);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(out, d.p, tot * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
@@ -1436,7 +1446,7 @@ int32_t dmt_allreduce_stats(dmt_ctx *ctx, int32_t layout, double *out) {
         if (ctx->p2p_ready && 2 + L.nb <= P2P_MAX_VALS) { // own one-shot all-reduce over NVLink peer memory (kernels.cuh)
             ctx->p2p.seq++;
             ctx->p2p.nval = 2 + L.nb;
-            p2p_allreduce_kernel<<<1, P2P_MAX_VALS, 0, ctx->stream>>>(ctx->p2p, ctx->d_stats.p);
+            ++g_launches, p2p_allreduce_kernel<<<1, P2P_MAX_VALS, 0, ctx->stream>>>(ctx->p2p, ctx->d_stats.p);
             CK(cudaGetLastError());
             CK(cudaMemcpyAsync(out, ctx->d_stats.p, sizeof(double) * (2 + L.nb), cudaMemcpyDeviceToHost, ctx->stream));
             int err = 0;

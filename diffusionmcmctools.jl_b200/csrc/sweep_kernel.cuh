@@ -173,10 +173,17 @@ __global__ void __launch_bounds__(32, sweep_pipe_minb<MD>()) sweep_pipe_kernel(c
                 const int i = 4 * q + s;
                 if (i < nst) {
                     double Hs[NH], F[D], Bm[D * D], beta[D], gd[D], G = 0.0;
+#ifdef DMT_SWEXP_NOCONF // (experiment only: bank-conflict-free reads of the WRONG elements, to price the 32-byte lane stride)
+#pragma unroll
+                    for (int a = 0; a < NH; a++) Hs[a] = st[a * 128 + s * 32 + lane];
+#pragma unroll
+                    for (int a = 0; a < D; a++) F[a] = st[(NH + a) * 128 + s * 32 + lane];
+#else
 #pragma unroll
                     for (int a = 0; a < NH; a++) Hs[a] = sg[a * 128 + s];
 #pragma unroll
                     for (int a = 0; a < D; a++) F[a] = sg[(NH + a) * 128 + s];
+#endif
 #pragma unroll
                     for (int a = 0; a < D * D; a++) Bm[a] = cst[a * 32 + lane];
 #pragma unroll
@@ -196,7 +203,11 @@ __global__ void __launch_bounds__(32, sweep_pipe_minb<MD>()) sweep_pipe_kernel(c
                     double dwo[DW];
                     static_for<DW>([&](auto j_c) { // K3: dW° = rho dW + sqrt(1-rho^2) sqrt(dt) xi   (A.2); xi generated as it is needed
                         constexpr int j = decltype(j_c)::value;
+#ifdef DMT_SWEXP_NORNG // (experiment only: the pass without the generator)
+                        const double xi = 0.5 + zcarry;
+#else
                         const double xi = tile_normal_at<s * DW + j>(cx.seed, cx.chain_offset + (uint32_t)c, (uint32_t)(t0 + q), fa.iter, (uint32_t)ly.id, zcarry);
+#endif
                         dwo[j] = rho * dwv[j] + crho * sq * xi;
                         if (!LAZYW) { w[j][s] = dwv[j]; wo[j][s] = dwo[j]; }
                     });

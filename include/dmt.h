@@ -81,6 +81,8 @@ int32_t dmt_sync(dmt_ctx *ctx);
 int32_t dmt_get_stream(dmt_ctx *ctx, void **cuda_stream); /* for CUDA-event timing by the caller */
 int32_t dmt_model_dims(int32_t model, int32_t *d, int32_t *dw, int32_t *npar, int32_t *constdiff);
 int32_t dmt_version(void);
+/* number of CUDA kernels this library has launched so far in this process (bench.py's gpu_launches is a difference of two reads) */
+int32_t dmt_launch_count(uint64_t *n);
 
 /* ---- laws: parameters, auxiliary laws, observations --------------------------------------------------------- */
 /* DD.set_parameters!(PP, θ°, ...) result (src/biblock.jl:366-369): theta[npar][P] written into the laws of

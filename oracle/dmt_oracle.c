@@ -309,6 +309,7 @@ struct orc_pair {
     double *t;
     double eps;
     orc_unit u[2];
+    double *xi; /* scratch: the innovations of one interval (max_k (n_k - 1) x dw) */
 };
 
 static orc_law *law_new(int n, int d) {
@@ -330,6 +331,11 @@ orc_pair *orc_pair_create(int model, int K, const int *n, const double *t, int m
     for (int k = 0; k < K; k++) { p->n[k] = n[k]; p->off[k + 1] = p->off[k] + n[k]; }
     p->t = (double *)malloc(sizeof(double) * p->off[K]);
     memcpy(p->t, t, sizeof(double) * p->off[K]);
+    {
+        int nmax = 0;
+        for (int k = 0; k < K; k++) if (n[k] > nmax) nmax = n[k];
+        p->xi = (double *)malloc(sizeof(double) * nmax * p->dw);
+    }
     for (int s = 0; s < 2; s++) { /* u and u° = deepcopy(u), src/sampling_pair.jl:51 */
         orc_unit *u = &p->u[s];
         u->PP = (orc_law **)malloc(sizeof(void *) * K);
@@ -354,7 +360,7 @@ void orc_pair_destroy(orc_pair *p) {
         for (int k = 0; k < p->K; k++) { law_free(u->PP[k]); law_free(u->PPb[k]); free(u->XX[k]); free(u->WW[k]); }
         free(u->PP); free(u->PPb); free(u->XX); free(u->WW);
     }
-    free(p->n); free(p->off); free(p->t); free(p);
+    free(p->n); free(p->off); free(p->t); free(p->xi); free(p);
 }
 
 static orc_law *law_at(orc_pair *p, int side, int store, int k) { return store ? p->u[side].PPb[k] : p->u[side].PP[k]; }
@@ -794,9 +800,8 @@ static void interval_normals(const orc_pair *p, int k, const double *Zblock, siz
 int orc_draw_proposal_path(orc_pair *p, orc_biblock *bb, const double *Z, uint64_t seed, uint32_t chain, uint32_t iter,
                            uint32_t layout, const int *gtile0) {
     orc_unit *u = &p->u[0], *uo = &p->u[1];
-    int d = p->d, nmax = 0;
-    for (int k = bb->i0; k <= bb->i1; k++) if (p->n[k] > nmax) nmax = p->n[k];
-    double *xi = (double *)malloc(sizeof(double) * nmax * p->dw);
+    int d = p->d;
+    double *xi = p->xi;
     size_t zoff = 0;
     double y1[ORC_MAXD];
     memcpy(y1, u->XX[bb->i0], sizeof(double) * d);
@@ -813,7 +818,6 @@ int orc_draw_proposal_path(orc_pair *p, orc_biblock *bb, const double *Z, uint64
         memcpy(y1, uo->XX[k] + (size_t)(p->n[k] - 1) * d, sizeof(double) * d);
     }
     bb->ll[1] = ll;
-    free(xi);
     return ok;
 }
 

@@ -33,11 +33,13 @@ def _d(a):
     return a, a.ctypes.data_as(_dp)
 
 
-def load(omp=False):
-    name = "libdmt_oracle_omp.so" if omp else "libdmt_oracle.so"
-    path = os.path.join(_HERE, name)
-    if not os.path.exists(path):
-        build()
+def load(omp=False, path=None):
+    """path: an explicitly built flavour of the same source (bench.py rebuilds the OpenMP one with -march=native for the host it runs on)"""
+    if path is None:
+        name = "libdmt_oracle_omp.so" if omp else "libdmt_oracle.so"
+        path = os.path.join(_HERE, name)
+        if not os.path.exists(path):
+            build()
     lib = C.CDLL(path)
     vp = C.c_void_p
     bbp = C.POINTER(BiBlock)

@@ -65,9 +65,11 @@ atexit.register(_dump_worst)
 
 
 class OracleEnsemble:
-    def __init__(self, orc, olib, prob, seed=0, chain_offset=0):
+    def __init__(self, orc, olib, prob, seed=0, chain_offset=0, chain_ids=None):
+        """chain_ids: the GLOBAL recording index of each of prob's chains (random-stream counters); default chain_offset + c"""
         self.orc, self.olib, self.prob = orc, olib, prob
         self.seed, self.chain_offset = seed, chain_offset
+        self.chain_ids = [chain_offset + c for c in range(prob.M)] if chain_ids is None else [int(c) for c in chain_ids]
         self.pairs = []
         ps_of = prob.pset_of_chain if prob.pset_of_chain is not None else (np.arange(prob.M) if prob.P == prob.M else np.zeros(prob.M, int))
         self.ps_of = ps_of
@@ -120,7 +122,7 @@ class OracleEnsemble:
             zb = None
             if Z is not None:
                 zb = np.ascontiguousarray(Z[step0[bb.i0]:step0[bb.i1 + 1], :, c])
-            ok[b, c] = P.draw_proposal_path(bb, zb, seed=self.seed, chain=self.chain_offset + c, it=it, layout=lid)
+            ok[b, c] = P.draw_proposal_path(bb, zb, seed=self.seed, chain=self.chain_ids[c], it=it, layout=lid)
         return ok
 
     def recompute_path(self, l, law_side, w_side, skip=0):
@@ -136,7 +138,7 @@ class OracleEnsemble:
         hist = np.zeros((2, nb, self.prob.M))
         lid = l if layout_id is None else layout_id
         for c, b, P, bb in self.each(l):
-            e = E[b, c] if E is not None else self.olib.orc_accept_exponential(self.seed, self.chain_offset + c, b, it, lid)
+            e = E[b, c] if E is not None else self.olib.orc_accept_exponential(self.seed, self.chain_ids[c], b, it, lid)
             acc[b, c], h = P.accept_reject(bb, float(e))
             hist[:, b, c] = h
         return acc, hist

@@ -132,20 +132,7 @@ def test_other_baseline_configs_at_full_size(cfg, orc, olib):
     sub = copy.copy(prob)
     sub.M = sub.P = len(chains)
     sub.v, sub.xbar, sub.x0 = prob.v[:, :, chains].copy(), prob.xbar[:, :, chains].copy(), prob.x0[:, chains].copy()
-
-    class Sliced(OracleEnsemble):                                       # global chain ids are not contiguous here
-        def draw(self, l, it, Z=None, layout_id=None):
-            ok = np.zeros((1, self.prob.M), bool)
-            for c, b, P, bb in self.each(l):
-                ok[b, c] = P.draw_proposal_path(bb, None, seed=self.seed, chain=chains[c], it=it, layout=l)
-            return ok
-
-        def accept(self, l, it, E=None, layout_id=None):
-            acc = np.zeros((1, self.prob.M), bool)
-            for c, b, P, bb in self.each(l):
-                acc[b, c], _ = P.accept_reject(bb, float(self.olib.orc_accept_exponential(self.seed, chains[c], b, it, l)))
-            return acc, None
-    ora = Sliced(orc, olib, sub, seed=123)
+    ora = OracleEnsemble(orc, olib, sub, seed=123, chain_ids=chains)                # global chain ids, not contiguous
     X, W = ctx.get_X_chains(chains, 0), ctx.get_W_chains(chains, 0)
     assert np.isfinite(X).all() and np.isfinite(W).all()
     for s in (0, 1):

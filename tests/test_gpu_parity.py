@@ -140,15 +140,21 @@ def test_find_W_for_X_roundtrip(orc, olib, name):
     ctx.close()
 
 
+# Jansen-Rit with blocking.  The BASELINE constants (a = 100, b = 50 1/s: entries 1e4 in B) make the blocking law's covariance
+# P = H^-1 numerically singular: the noise enters one coordinate and reaches x3 only after five integrations, so next to an (almost)
+# exact full-state observation cond(P) exceeds 1e16 and BOTH implementations lose positive definiteness in FP64 — there is nothing to
+# compare.  The d = 6 blocking code paths (covariance-form K1, OP_SWEEP at NG = 27) are therefore exercised on the same model with
+# slow time constants and a milder artificial noise (the constructor argument of src/sampling_unit.jl:57), where cond(P) ~ 1e4.
+JR_TAME = [3.25, 2.0, 2.2, 1.0, 13.5, 5.0, 6.0, 0.56, 2.2, 1.0]
+
+
 def blocking_problem(name, M=37, K=8, seed=4, nsteps=10):
     layouts = [([(0, 2), (3, 5), (6, 7)], [0.6, 0.7, 0.8]), ([(0, 3), (4, 7)], 0.5)]
-    prob = small_problem(name, M=M, K=K, layouts=layouts, seed=seed, nsteps=nsteps)
     if name == "jr":
-        # Jansen-Rit is hypoelliptic with noise five integrations away from x3: conditioning on an EXACT full-state observation
-        # (artificial_noise 1e-11) has a condition number ~1e11 and neither implementation means anything there; the blocking
-        # law is exercised with a milder artificial noise (the constructor argument of src/sampling_unit.jl:57)
+        prob = configs.make_problem("jr", M, K=K, obs_dt=0.1, dt=0.1 / nsteps, seed=seed, layouts=layouts, rho=0.7, theta=JR_TAME)
         prob.eps = 1e-4
-    return prob
+        return prob
+    return small_problem(name, M=M, K=K, layouts=layouts, seed=seed, nsteps=nsteps)
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -253,7 +259,7 @@ def test_backward_filter_thread_per_pset_kernel_for_the_wide_model(orc, olib, bl
     against the cooperative kernel; with blocking also the covariance-form recursion at d = 6."""
     K = 6
     if blocking:
-        prob = small_problem("jr", M=35, K=K, layouts=[([(0, 2), (3, 5)], 0.7)], seed=3, nsteps=11)
+        prob = configs.make_problem("jr", 35, K=K, obs_dt=0.1, dt=0.1 / 11, seed=3, layouts=[([(0, 2), (3, 5)], 0.7)], rho=0.7, theta=JR_TAME)
         prob.eps = 1e-4
     else:
         prob = small_problem("jr", M=35, K=K, seed=3, nsteps=11)

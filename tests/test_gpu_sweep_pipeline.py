@@ -15,11 +15,12 @@ NAMES = ["fhn", "lv", "lorenz", "prok", "jr", "ou2"]
 
 def problem(name, M, K=8, nsteps=11, seed=12):
     layouts = [([(0, 2), (3, 5), (6, 7)], [0.6, 0.7, 0.8]), ([(0, 3), (4, 7)], 0.5), ([(0, K - 1)], 0.0)]
-    obs_dt = 0.01 if name == "jr" else 0.1
-    prob = configs.make_problem(name, M, K=K, obs_dt=obs_dt, dt=obs_dt / nsteps, seed=seed, layouts=layouts, rho=0.7)
-    if name == "jr":
+    if name == "jr":   # (the tame Jansen-Rit instance of test_gpu_parity.blocking_problem: the BASELINE constants are singular under blocking)
+        from test_gpu_parity import JR_TAME
+        prob = configs.make_problem("jr", M, K=K, obs_dt=0.1, dt=0.1 / nsteps, seed=seed, layouts=layouts, rho=0.7, theta=JR_TAME)
         prob.eps = 1e-4
-    return prob
+        return prob
+    return configs.make_problem(name, M, K=K, obs_dt=0.1, dt=0.1 / nsteps, seed=seed, layouts=layouts, rho=0.7)
 
 
 def start(prob, seed=31, **kw):
@@ -43,7 +44,8 @@ def test_pipelined_sweep_equals_register_tile_sweep(name, M):
         assert np.array_equal(a.get_success(l), b.get_success(l))
         good = a.get_success(l).all(axis=0)
         assert rel_err(b.get_W(0), a.get_W(0)) < 1e-10
-        assert rel_err(b.get_ll(l, 0), a.get_ll(l, 0)) < 1e-11 and rel_err(b.get_ll(l, 1), a.get_ll(l, 1)) < 1e-10
+        assert np.isfinite(a.get_ll(l, 0)).all()
+        assert rel_err(b.get_ll(l, 0), a.get_ll(l, 0)) < 1e-10 and rel_err(b.get_ll(l, 1), a.get_ll(l, 1)) < 1e-10
         assert rel_err(b.get_X(1)[:, :, good], a.get_X(1)[:, :, good]) < 1e-10 and rel_err(b.get_W(1)[:, :, good], a.get_W(1)[:, :, good]) < 1e-10
         a.accept_reject_path(l, it // 2); b.accept_reject_path(l, it // 2)
         assert np.array_equal(a.get_last_accept(l), b.get_last_accept(l))
