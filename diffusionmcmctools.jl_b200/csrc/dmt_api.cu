@@ -96,7 +96,7 @@ struct Layout {
     // guiding cache (dmt_enable_guiding_cache): layout-private accepted-law guiding term + its affine decomposition in v
     bool cache_enabled = false, cache_valid = false;
     bool F_stale = false; // cache valid but F/c of the private store not materialised for the current artificial observations
-    DevBuf<double> d_Gl[2], d_c0l[2], d_FP[2], d_cq;
+    DevBuf<double> d_Gl[2], d_c0l[2], d_FP[2], d_cq, d_vlast;
     DevBuf<int> d_blk_of_k;
 };
 
@@ -404,6 +404,13 @@ void cache_build(dmt_ctx *c, Layout &L) {
     }
     if (L.d_cq.n != (size_t)L.nb * NC * P) L.d_cq.alloc((size_t)L.nb * NC * P);
     L.dev.cq = L.d_cq.p;
+    if (L.d_vlast.n != (size_t)L.nb * c->D * P) L.d_vlast.alloc((size_t)L.nb * c->D * P, false);
+    L.dev.v_last = L.d_vlast.p;
+    {   // "no end point seen yet": NaN compares unequal to everything, so the first apply after a (re)build materialises every block
+        std::vector<double> nan_fill(L.d_vlast.n, NAN);
+        CK(cudaMemcpyAsync(L.d_vlast.p, nan_fill.data(), sizeof(double) * nan_fill.size(), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
     {
         std::vector<int> bk(c->K, 0);
         for (int b = 0; b < L.nb; b++)
@@ -1341,7 +1348,7 @@ int32_t dmt_enable_guiding_cache(dmt_ctx *ctx, int32_t layout, int32_t enable) {
         cache_set_private(L, false);
         if (!enable) {
             for (int st = 0; st < 2; st++) { L.d_Gl[st].release(); L.d_FP[st].release(); L.d_c0l[st].release(); }
-            L.d_cq.release();
+            L.d_cq.release(); L.d_vlast.release();
         }
     });
 }

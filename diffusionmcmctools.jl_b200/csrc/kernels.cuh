@@ -81,6 +81,7 @@ struct LayoutDev {
     // guiding cache: (F, c) of a block are exactly affine / quadratic in the block's artificial end-point observation v
     double *FP[2];     // [store] [tiles][D + D*D][P][4]: F0 (v = 0) then Psi[i][m] = dF_i/dv_m
     double *cq;        // [nb][1 + D + NH][P]: c = c0 + q.v + v'Qv/2 at the block start
+    double *v_last;    // [nb][D][P]: the artificial observation the private F, c were last materialised for
     const int *blk_of_k; // [K] block of this layout that contains interval k
 };
 
@@ -759,8 +760,13 @@ __global__ void cache_apply_kernel(const DevCtx cx, const LayoutDev ly, int stor
     const int kend = ly.i1[b];
     const int sv = cx.parP[1][(size_t)kend * P + ps];
     double v[D];
+    bool same = true; // the block's end point did not move (its last proposal in the other layout was rejected): F is current
 #pragma unroll
-    for (int mm = 0; mm < D; mm++) v[mm] = cx.vart[sv][((size_t)kend * D + mm) * P + ps];
+    for (int mm = 0; mm < D; mm++) {
+        v[mm] = cx.vart[sv][((size_t)kend * D + mm) * P + ps];
+        same = same && (v[mm] == ly.v_last[((size_t)b * D + mm) * P + ps]);
+    }
+    if (same) return;
     double *gp = ly.Gl[store] + (((size_t)t * NG + NH) * P + ps) * 4;
     const double *fp = ly.FP[store] + ((size_t)t * NF * P + ps) * 4;
 #pragma unroll
@@ -823,6 +829,8 @@ template <int D> __global__ void cache_apply_c_kernel(const DevCtx cx, const Lay
     double v[D];
 #pragma unroll
     for (int m = 0; m < D; m++) v[m] = cx.vart[sv][((size_t)kend * D + m) * P + ps];
+#pragma unroll
+    for (int m = 0; m < D; m++) ly.v_last[((size_t)b * D + m) * P + ps] = v[m]; // (after both cache_apply_kernel launches, in stream order)
     const double *cq = ly.cq + (size_t)b * NC * P + ps;
     double c = cq[0];
 #pragma unroll

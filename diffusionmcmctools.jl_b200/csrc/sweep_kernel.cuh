@@ -150,6 +150,31 @@ __global__ void __launch_bounds__(32, sweep_pipe_minb<MD>()) sweep_pipe_kernel(c
 #pragma unroll
                 for (int s = 0; s < 4; s++) xt[i][s] = xnx[i][s];
             prefetch(); // tile t+1: its stage was drained at the end of tile t-1 (the __syncwarp below)
+#ifndef DMT_SW_NO_PFREC
+            if (q == ntl - 1 && k < i1) { // the next interval's law records and start point: pull them into L2 one tile ahead, so that the
+                                          // dependent loads at the interval boundary do not pay a DRAM round trip each (ncu: 12 % of all stall samples)
+                const int k1 = k + 1;
+                const int store1 = (k1 == i1 && !last) ? 1 : 0;
+                const int slot1 = cx.parP[store1][(size_t)k1 * P + ps];
+                const double *tp = cx.theta[slot1][store1] + (size_t)k1 * NPAR * P + ps;
+#pragma unroll
+                for (int i = 0; i < NPAR; i++) prefetch_l2(tp + (size_t)i * P);
+                const double *ap = cx.aux[slot1][store1] + (size_t)k1 * NAUX * P + ps;
+#pragma unroll
+                for (int i = 0; i < (MD::CONSTDIFF ? D * D + D : NAUX); i++) prefetch_l2(ap + (size_t)i * P);
+#pragma unroll
+                for (int i = 0; i < D; i++) {
+                    prefetch_l2(cx.X0 + ((size_t)k1 * D + i) * M + c);
+                    prefetch_l2(cx.X0 + cx.X0buf + ((size_t)k1 * D + i) * M + c);
+                }
+                prefetch_l2(cx.parX + (size_t)k1 * M + c);
+                prefetch_l2(cx.parW + (size_t)k1 * M + c);
+            }
+#endif
+#ifdef DMT_SW_ZTILE // the tile's normals BEFORE the wait for its data: the generator runs while the sectors are still in flight
+            double z[4 * DW];
+            tile_normals<DW>(cx.seed, cx.chain_offset + (uint32_t)c, (uint32_t)(t0 + q), fa.iter, (uint32_t)ly.id, z);
+#endif
 
             mbar_wait(&bars[n_cons & 1], (uint32_t)(n_cons >> 1) & 1u);
             const double *st = ring + (size_t)(n_cons & 1) * STAGE;
@@ -168,10 +193,14 @@ __global__ void __launch_bounds__(32, sweep_pipe_minb<MD>()) sweep_pipe_kernel(c
                 llo = s0; // same law, same start point
             }
             double w[LAZYW ? 1 : DW][4], wo[LAZYW ? 1 : DW][4], xot[D][4], zcarry = 0.0;
-            static_for<4>([&](auto s_c) {
+            // One EM step of the tile.  FULL (every step of the tile exists — always, on grids whose intervals hold a multiple of 4
+            // steps): no branch at all, so the four steps and the generator calls they consume form ONE basic block that ptxas can
+            // interleave; a failed proposal keeps computing (its state is unspecified anyway) and is marked at the end.
+            auto step = [&](auto s_c, auto full_c) {
                 constexpr int s = decltype(s_c)::value;
+                constexpr bool FULL = decltype(full_c)::value;
                 const int i = 4 * q + s;
-                if (i < nst) {
+                if (FULL || i < nst) {
                     double Hs[NH], F[D], Bm[D * D], beta[D], gd[D], G = 0.0;
 #ifdef DMT_SWEXP_NOCONF // (experiment only: bank-conflict-free reads of the WRONG elements, to price the 32-byte lane stride)
 #pragma unroll
@@ -205,13 +234,15 @@ __global__ void __launch_bounds__(32, sweep_pipe_minb<MD>()) sweep_pipe_kernel(c
                         constexpr int j = decltype(j_c)::value;
 #ifdef DMT_SWEXP_NORNG // (experiment only: the pass without the generator)
                         const double xi = 0.5 + zcarry;
+#elif defined(DMT_SW_ZTILE)
+                        const double xi = z[s * DW + j] + 0.0 * zcarry;
 #else
                         const double xi = tile_normal_at<s * DW + j>(cx.seed, cx.chain_offset + (uint32_t)c, (uint32_t)(t0 + q), fa.iter, (uint32_t)ly.id, zcarry);
 #endif
                         dwo[j] = rho * dwv[j] + crho * sq * xi;
                         if (!LAZYW) { w[j][s] = dwv[j]; wo[j][s] = dwo[j]; }
                     });
-                    if (ok) { // K2 + K4 on the proposal, from the noise just refreshed
+                    if (FULL || ok) { // K2 + K4 on the proposal, from the noise just refreshed
                         double swo[D], gdo[D], Go = 0.0, xon[D];
                         const typename MD::Diff dfo(par, xo);
                         guided_terms<MD, true>(par, dfo, Bm, beta, at, Hs, F, xo, gdo, Go);
@@ -222,7 +253,7 @@ __global__ void __launch_bounds__(32, sweep_pipe_minb<MD>()) sweep_pipe_kernel(c
                         bool fin = dfo.ok();
 #pragma unroll
                         for (int a = 0; a < D; a++) fin = fin && isfinite(xon[a]);
-                        if (!(fin && MD::bound_ok(par, xon))) { ok = false; llo = -INFINITY; } // src/block.jl:181
+                        ok = ok && fin && MD::bound_ok(par, xon); // src/block.jl:181 (ll° := -Inf once, after the loop)
 #pragma unroll
                         for (int a = 0; a < D; a++) { xot[a][s] = xon[a]; xo[a] = xon[a]; }
                     } else {
@@ -237,7 +268,13 @@ __global__ void __launch_bounds__(32, sweep_pipe_minb<MD>()) sweep_pipe_kernel(c
                         for (int j = 0; j < DW; j++) { w[j][s] = 0.0; wo[j][s] = 0.0; }
                     }
                 }
-            });
+            };
+#ifdef DMT_SW_NOFULL
+            if (false) {}
+#else
+            if (4 * q + 4 <= nst) static_for<4>([&](auto s_c) { step(s_c, std::true_type{}); });
+#endif
+            else static_for<4>([&](auto s_c) { step(s_c, std::false_type{}); });
             if (live) {
                 if (!LAZYW) {
 #pragma unroll
@@ -253,7 +290,7 @@ __global__ void __launch_bounds__(32, sweep_pipe_minb<MD>()) sweep_pipe_kernel(c
     }
     if (live) {
         ly.ll[(size_t)b * M + c] = ll;
-        ly.ll[((size_t)ly.nb + b) * M + c] = llo;
+        ly.ll[((size_t)ly.nb + b) * M + c] = ok ? llo : -INFINITY;
         ly.ok[(size_t)b * M + c] = ok ? 1 : 0;
     }
 }
