@@ -270,6 +270,30 @@ bool covers_all_intervals(dmt_ctx *c, const Layout &L) {
     return std::all_of(seen.begin(), seen.end(), [](char s) { return s != 0; });
 }
 
+// wave_warps != nullptr: only report how many warps of this instantiation are resident at once on the device
+template <class MD, int G> void launch_sweep_pipe_g(dmt_ctx *c, Layout &L, const FwdArgs &fa, bool lazy, size_t *wave_warps = nullptr) {
+    constexpr size_t smem = sweep_pipe_smem<MD>();
+    static bool attr_done[64][2] = {};
+    static size_t wave[64][2] = {};
+    const int dev = c->cfg.device & 63;
+    if (!attr_done[dev][lazy]) {
+        int per_sm = 0, sms = 0;
+        if (lazy) {
+            CK(cudaFuncSetAttribute(sweep_pipe_kernel<MD, true, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_pipe_kernel<MD, true, G>, 32, smem));
+        } else {
+            CK(cudaFuncSetAttribute(sweep_pipe_kernel<MD, false, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_pipe_kernel<MD, false, G>, 32, smem));
+        }
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->cfg.device));
+        wave[dev][lazy] = (size_t)per_sm * sms;
+        attr_done[dev][lazy] = true;
+    }
+    if (wave_warps) { *wave_warps = wave[dev][lazy]; return; }
+    const dim3 grid((unsigned)((c->M + 32 / G - 1) / (32 / G)), L.nb, 1);
+    if (lazy) ++g_launches, sweep_pipe_kernel<MD, true, G><<<grid, 32, smem, c->stream>>>(c->dev, L.dev, fa);
+    else ++g_launches, sweep_pipe_kernel<MD, false, G><<<grid, 32, smem, c->stream>>>(c->dev, L.dev, fa);
+}
 // the software-pipelined sweep (sweep_kernel.cuh): one parameter set per chain in chain order, uniform law parity, device RNG
 template <class MD> bool launch_sweep_pipe(dmt_ctx *c, Layout &L, const FwdArgs &fa) {
     static int env_off = -1;
@@ -279,21 +303,27 @@ template <class MD> bool launch_sweep_pipe(dmt_ctx *c, Layout &L, const FwdArgs 
         throw DmtError(DMT_ERR_UNSUPPORTED, "pipelined sweep needs one parameter set per chain in chain order, uniform law parity and device RNG");
     if (!eligible || c->sweep_mode == 1 || (c->sweep_mode == 0 && (c->fwd_lanes != 0 || env_off))) return false;
     const bool lazy = c->lazy_W && covers_all_intervals(c, L);
-    constexpr size_t smem = sweep_pipe_smem<MD>();
-    static bool attr_done[64][2] = {};
-    const int dev = c->cfg.device & 63;
-    if (!attr_done[dev][lazy]) {
-        if (lazy) CK(cudaFuncSetAttribute(sweep_pipe_kernel<MD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else CK(cudaFuncSetAttribute(sweep_pipe_kernel<MD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done[dev][lazy] = true;
+    // automatic choice: with the noise stored every sweep the pipelined kernel's live set (two more tile buffers) spills and it loses to the
+    // register-tile kernel (3.9 against 3.5 ms on C3, profiles/r02_tuning.md); it wins where the noise is lazy (2.44 against 3.5 ms)
+    if (c->sweep_mode == 0 && !lazy) return false;
+    // lanes per (chain, block): 4 when the ensemble is too small to give every scheduler a warp and 4 x as many warps still fit one wave
+    // (the lanes split the generator calls; models with one Wiener coordinate have too little generator work to split)
+    constexpr int GW = MD::DW >= 2 ? 4 : 1; // the wide mapping exists for these models only
+    bool g4 = false;
+    if (c->fwd_lanes != 0) { // dmt_set_fwd_lanes together with dmt_set_sweep_mode(2): force the mapping
+        if (c->fwd_lanes != 1 && !(c->fwd_lanes == 4 && GW == 4))
+            throw DmtError(DMT_ERR_UNSUPPORTED, "the pipelined sweep maps 1 or (models with >= 2 Wiener coordinates) 4 lanes to a (chain, block)");
+        g4 = c->fwd_lanes == 4;
+    } else if (GW == 4) {
+        size_t wave1 = 0, wave4 = 0;
+        launch_sweep_pipe_g<MD, 1>(c, L, fa, lazy, &wave1);
+        launch_sweep_pipe_g<MD, GW>(c, L, fa, lazy, &wave4);
+        const size_t warps1 = (size_t)((c->M + 31) / 32) * L.nb, warps4 = (size_t)((c->M + 7) / 8) * L.nb;
+        g4 = warps1 * 4 <= wave1 * 2 && warps4 <= wave4; // fewer than half a wave of one-lane warps, and the 4-lane grid still fits one wave
     }
-    const dim3 grid((unsigned)((c->M + 31) / 32), L.nb, 1);
-    if (lazy) {
-        ++g_launches, sweep_pipe_kernel<MD, true><<<grid, 32, smem, c->stream>>>(c->dev, L.dev, fa);
-        c->W_stale_layout = L.dev.id;
-    } else {
-        ++g_launches, sweep_pipe_kernel<MD, false><<<grid, 32, smem, c->stream>>>(c->dev, L.dev, fa);
-    }
+    if (g4) launch_sweep_pipe_g<MD, GW>(c, L, fa, lazy);
+    else launch_sweep_pipe_g<MD, 1>(c, L, fa, lazy);
+    if (lazy) c->W_stale_layout = L.dev.id;
     return true;
 }
 

@@ -39,8 +39,14 @@ template <class MD> constexpr size_t sweep_pipe_smem() {
     return (size_t)2 * (NG * 128 + 8) * 8 + (size_t)(D * D + D) * 32 * 8 + 2 * 8;
 }
 
-template <class MD, bool LAZYW>
+// G > 1 (ensembles too small to give every scheduler a warp: 512 chains x 10 blocks are 168 warps on 592 schedulers): G adjacent
+// lanes share one (chain, block).  They split the tile's 2 DW Philox + Box-Muller calls and all-gather the normals with shuffles
+// (philox.cuh, tile_normals_coop); everything else is computed redundantly from the same shared-memory sectors and lane 0 of the group
+// stores.  Random stream and results are bit-identical to G = 1.
+template <class MD, bool LAZYW, int G = 1>
 __global__ void __launch_bounds__(32, sweep_pipe_minb<MD>()) sweep_pipe_kernel(const DevCtx cx, const LayoutDev ly, const FwdArgs fa) {
+    static_assert(G == 1 || G == 2 || G == 4 || G == 8, "lanes per (chain, block)");
+    constexpr int CPW = 32 / G; // chains per warp
     constexpr int D = MD::D, DW = MD::DW, NPAR = MD::NPAR, NH = D * (D + 1) / 2, NG = NH + D, NAUX = D * D + D + NH;
     constexpr int STAGE = NG * 128 + 8; // doubles per stage: [component][lane][4] then dt[4], sqrt(dt)[4]
     extern __shared__ __align__(128) unsigned char sw_smem[];
@@ -48,18 +54,18 @@ __global__ void __launch_bounds__(32, sweep_pipe_minb<MD>()) sweep_pipe_kernel(c
     double *cst = ring + 2 * STAGE;                                  // [D*D + D][32]: B (row-major), beta of the current interval
     uint64_t *bars = reinterpret_cast<uint64_t *>(cst + (D * D + D) * 32);
 
-    const int lane = threadIdx.x;
-    const int c0 = blockIdx.x * 32, b = blockIdx.y;
+    const int lane = threadIdx.x, cl = lane / G, sub = lane % G; // chain slot inside the warp, lane inside the chain's group
+    const int c0 = blockIdx.x * CPW, b = blockIdx.y;
     if (c0 >= cx.M) return;
-    const int c_raw = c0 + lane;
+    const int c_raw = c0 + cl;
     const int c = min(c_raw, cx.M - 1); // lanes beyond the ensemble shadow the last chain and never store
-    const bool live = c_raw < cx.M;
+    const bool live = c_raw < cx.M && sub == 0;
     const size_t M = cx.M, P = cx.P;
     const int ps = c;                   // launch condition: one parameter set per chain, in chain order
     const int i0 = ly.i0[b], i1 = ly.i1[b];
     const bool last = ly.last[b] != 0;
     const double rho = ly.rho[b], crho = sqrt(1.0 - rho * rho);
-    const uint32_t chunk_bytes = 32u * (uint32_t)min(32, cx.M - c0);
+    const uint32_t chunk_bytes = 32u * (uint32_t)min(CPW, cx.M - c0);
     const size_t gstr = P * 4;
 
     if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
@@ -171,14 +177,16 @@ __global__ void __launch_bounds__(32, sweep_pipe_minb<MD>()) sweep_pipe_kernel(c
                 prefetch_l2(cx.parW + (size_t)k1 * M + c);
             }
 #endif
-#ifdef DMT_SW_ZTILE // the tile's normals BEFORE the wait for its data: the generator runs while the sectors are still in flight
+#ifndef DMT_SW_ZONDEMAND // the tile's normals BEFORE the wait for its data: the generator runs while the sectors are still in flight
+            // (measured, profiles/r02_tuning.md: 2.44 ms against 2.61-3.08 ms with the normals generated inside the step loop)
             double z[4 * DW];
-            tile_normals<DW>(cx.seed, cx.chain_offset + (uint32_t)c, (uint32_t)(t0 + q), fa.iter, (uint32_t)ly.id, z);
+            if (G > 1) tile_normals_coop<DW, G>(cx.seed, cx.chain_offset + (uint32_t)c, (uint32_t)(t0 + q), fa.iter, (uint32_t)ly.id, sub, z);
+            else tile_normals<DW>(cx.seed, cx.chain_offset + (uint32_t)c, (uint32_t)(t0 + q), fa.iter, (uint32_t)ly.id, z);
 #endif
 
             mbar_wait(&bars[n_cons & 1], (uint32_t)(n_cons >> 1) & 1u);
             const double *st = ring + (size_t)(n_cons & 1) * STAGE;
-            const double *sg = st + lane * 4;
+            const double *sg = st + cl * 4;
             n_cons++;
             if (k == i0 && q == 0) { // loglikhd_obs(PP[1], y1) = -c - y'Hy/2 + F'y  (src/block.jl:178)
                 double s0 = -*gt.c0;
@@ -234,8 +242,9 @@ __global__ void __launch_bounds__(32, sweep_pipe_minb<MD>()) sweep_pipe_kernel(c
                         constexpr int j = decltype(j_c)::value;
 #ifdef DMT_SWEXP_NORNG // (experiment only: the pass without the generator)
                         const double xi = 0.5 + zcarry;
-#elif defined(DMT_SW_ZTILE)
-                        const double xi = z[s * DW + j] + 0.0 * zcarry;
+#elif !defined(DMT_SW_ZONDEMAND)
+                        const double xi = z[s * DW + j];
+                        (void)zcarry;
 #else
                         const double xi = tile_normal_at<s * DW + j>(cx.seed, cx.chain_offset + (uint32_t)c, (uint32_t)(t0 + q), fa.iter, (uint32_t)ly.id, zcarry);
 #endif

@@ -74,6 +74,10 @@ typedef struct {
 void orc_set_artificial_obs(orc_pair *p, const orc_biblock *bb);
 /* recompute_guiding_term!(b::Block)    src/block.jl:104-110; side selects bb.b or bb.b° */
 void orc_recompute_guiding_term(orc_pair *p, const orc_biblock *bb, int side);
+/* the same with upstream's ODE solver: adaptive Tsit5 (OrdinaryDiffEq defaults reltol 1e-3, abstol 1e-6), dense output on the path
+ * grid; returns the number of accepted steps.  See the header comment in dmt_oracle.c for what can be claimed of it. */
+int orc_recompute_guiding_term_tsit5(orc_pair *p, const orc_biblock *bb, int side, double reltol, double abstol);
+void orc_tsit5_tableau(double *c7, double *a7x6, double *btilde7, double *r7x4);
 /* find_W_for_X!(bb)                    src/biblock.jl:300 -> src/block.jl:120-131 */
 void orc_find_W_for_X(orc_pair *p, const orc_biblock *bb);
 /* loglikhd!(bb) / loglikhd°!(bb)       src/biblock.jl:240,248 -> src/block.jl:140-152 */

@@ -67,6 +67,8 @@ def load(omp=False, path=None):
         "orc_set_HFc": (None, [vp, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp]),
         "orc_set_artificial_obs": (None, [vp, bbp]),
         "orc_recompute_guiding_term": (None, [vp, bbp, C.c_int]),
+        "orc_recompute_guiding_term_tsit5": (C.c_int, [vp, bbp, C.c_int, C.c_double, C.c_double]),
+        "orc_tsit5_tableau": (None, [_dp, _dp, _dp, _dp]),
         "orc_find_W_for_X": (None, [vp, bbp]),
         "orc_loglikhd": (C.c_double, [vp, bbp, C.c_int, C.c_int]),
         "orc_draw_proposal_path": (C.c_int, [vp, bbp, _dp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, _ip]),
@@ -211,6 +213,10 @@ class Pair:
 
     def recompute_guiding_term(self, bb, side=0):
         self.lib.orc_recompute_guiding_term(self.h, C.byref(bb), side)
+
+    def recompute_guiding_term_tsit5(self, bb, side=0, reltol=1e-3, abstol=1e-6):
+        """upstream's solver (adaptive Tsit5, OrdinaryDiffEq default tolerances); returns the number of accepted steps"""
+        return self.lib.orc_recompute_guiding_term_tsit5(self.h, C.byref(bb), side, reltol, abstol)
 
     def find_W_for_X(self, bb):
         self.lib.orc_find_W_for_X(self.h, C.byref(bb))

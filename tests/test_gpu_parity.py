@@ -216,12 +216,22 @@ def test_blocking_sweeps(orc, olib, name):
 
 
 @pytest.mark.parametrize("name", NAMES)
-def test_fused_blocking_sweep_against_the_oracle(orc, olib, name):
-    """dmt_blocking_sweep (ONE fused forward pass: K5 + K4 + K3 + K2 + K4, fwd_kernel<Model, OP_SWEEP>) against the oracle's five
-    separate reference calls, six sweeps over two staggered layouts, each side running the loop on its own."""
+@pytest.mark.parametrize("kernel", ["register_tile", "pipelined", "pipelined_lazy"])
+def test_fused_blocking_sweep_against_the_oracle(orc, olib, name, kernel):
+    """dmt_blocking_sweep (ONE fused forward pass: K5 + K4 + K3 + K2 + K4) against the oracle's five separate reference calls, six
+    sweeps over two staggered layouts, each side running the loop on its own — for the register-tile kernel
+    (fwd_kernel<Model, OP_SWEEP>), the software-pipelined one (sweep_pipe_kernel) and the latter with lazy noise."""
     K = 8
     prob = blocking_problem(name, M=41, K=K, seed=6, nsteps=11)
     ctx = make_ctx(prob, seed=13, ll_hist_len=6, n_layouts=3)
+    lazy = kernel == "pipelined_lazy"
+    if kernel != "register_tile":
+        if _lib.DEFAULT_FWD_LANES:
+            pytest.skip("the pipelined kernel has one lane per (chain, block)")
+        ctx.set_sweep_mode(2)
+        ctx.set_lazy_noise(lazy)
+    else:
+        ctx.set_sweep_mode(1)
     ora = OracleEnsemble(orc, olib, prob, seed=13)
     ctx.set_blocks(2, [(0, K - 1)], 0.0)
     ctx.recompute_guiding_term(2, _lib.P_ONLY)
@@ -241,7 +251,8 @@ def test_fused_blocking_sweep_against_the_oracle(orc, olib, name):
         assert rel_err(ctx.get_ll(l, 1), ora.ll(l, 1), tag="fused/%s/ll_prop" % name) < TOL_K5
         good = ok_o.all(axis=0)
         assert rel_err(ctx.get_X(1)[:, :, good], ora.X(1)[:, :, good], tag="fused/%s/X_prop" % name) < TOL_K5
-        assert rel_err(ctx.get_W(1)[:, :, good], ora.W(1)[:, :, good], tag="fused/%s/W_prop" % name) < TOL_K5
+        if not lazy:   # (lazy noise: W° is unspecified; W_acc above was rebuilt by the read itself, K5 over the layout just swept)
+            assert rel_err(ctx.get_W(1)[:, :, good], ora.W(1)[:, :, good], tag="fused/%s/W_prop" % name) < TOL_K5
         ctx.accept_reject_path(l, i_mc); acc_o, hist_o = ora.accept(l, i_mc)
         assert np.array_equal(ctx.get_last_accept(l), acc_o)
         assert np.array_equal(ctx.get_accept_history(l, i_mc, i_mc)[0], acc_o)

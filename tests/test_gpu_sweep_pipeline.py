@@ -32,11 +32,18 @@ def start(prob, seed=31, **kw):
 
 @pytest.mark.parametrize("name", NAMES)
 @pytest.mark.parametrize("M", [41, 64, 7])
-def test_pipelined_sweep_equals_register_tile_sweep(name, M):
-    """same inputs, same random stream, same arithmetic: equal up to FP64 rounding (different FMA contraction), decisions equal"""
+@pytest.mark.parametrize("lanes", [1, 4])
+def test_pipelined_sweep_equals_register_tile_sweep(name, M, lanes):
+    """same inputs, same random stream, same arithmetic: equal up to FP64 rounding (different FMA contraction), decisions equal;
+    with one lane per (chain, block) and with four (the small-ensemble mapping: the lanes split the generator calls)"""
     prob = problem(name, M)
     a, b = start(prob), start(prob)
-    a.set_sweep_mode(1); b.set_sweep_mode(2)
+    a.set_sweep_mode(1); b.set_sweep_mode(2); b.set_fwd_lanes(lanes)
+    if lanes == 4 and prob.dw < 2:
+        with pytest.raises(dmt_b200.DmtError):      # one Wiener coordinate: nothing to split, the wide mapping is not built
+            b.blocking_sweep(0, 0)
+        a.close(); b.close()
+        return
     n_acc = 0
     for it in range(6):
         l = it % 2
