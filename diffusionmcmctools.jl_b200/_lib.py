@@ -22,6 +22,7 @@ ACCEPTED, PROPOSAL = 0, 1
 STORE_PP, STORE_PPB = 0, 1
 P_ONLY, PO_ONLY, P_BOTH = 1, 2, 3
 SWAP_XX, SWAP_WW, SWAP_PP, SWAP_LL = 1, 2, 4, 8
+K1_RK4, K1_TSIT5 = 0, 1
 
 
 class DmtError(RuntimeError):
@@ -85,6 +86,8 @@ SIGNATURES = {
     "dmt_enable_guiding_cache": (C.c_int32, [_vp, C.c_int32, C.c_int32]),
     "dmt_set_fwd_lanes": (C.c_int32, [_vp, C.c_int32]),
     "dmt_set_bwd_mode": (C.c_int32, [_vp, C.c_int32]),
+    "dmt_set_bwd_solver": (C.c_int32, [_vp, C.c_int32, C.c_double, C.c_double]),
+    "dmt_get_bwd_steps": (C.c_int32, [_vp, _ip, _ip]),
     "dmt_set_sweep_mode": (C.c_int32, [_vp, C.c_int32]),
     "dmt_set_lazy_noise": (C.c_int32, [_vp, C.c_int32]),
     "dmt_get_X_chains": (C.c_int32, [_vp, C.c_int32, C.c_int32, _ip, _dp]),
@@ -456,6 +459,15 @@ class Ctx:
     def set_lazy_noise(self, enable=True):
         """blocking sweeps stop materialising W / W° (rebuilt from X on demand); see include/dmt.h"""
         self._ck(self.lib.dmt_set_lazy_noise(self.h, int(bool(enable))))
+
+    def set_bwd_solver(self, solver, reltol=1e-3, abstol=1e-6):
+        """K1_RK4 (default) or K1_TSIT5 (upstream's adaptive solver at OrdinaryDiffEq's default tolerances)"""
+        self._ck(self.lib.dmt_set_bwd_solver(self.h, int(solver), float(reltol), float(abstol)))
+
+    def get_bwd_steps(self):
+        a, r = C.c_int32(0), C.c_int32(0)
+        self._ck(self.lib.dmt_get_bwd_steps(self.h, C.byref(a), C.byref(r)))
+        return a.value, r.value
 
     def set_bwd_mode(self, mode):
         """thread mapping of the backward filter: 0 = automatic, 1 = thread per parameter set, 2 = cooperative lanes"""

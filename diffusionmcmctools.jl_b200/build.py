@@ -9,7 +9,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "dmt_api.cu")
-DEPS = [SRC] + [os.path.join(HERE, "csrc", f) for f in ("kernels.cuh", "fwd_kernel.cuh", "models.cuh", "philox.cuh", "fastmath.cuh")] + [
+DEPS = [os.path.join(HERE, "csrc", f) for f in sorted(os.listdir(os.path.join(HERE, "csrc"))) if f.endswith((".cu", ".cuh"))] + [
     os.path.join(os.path.dirname(HERE), "include", "dmt.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",

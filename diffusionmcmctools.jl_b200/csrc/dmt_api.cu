@@ -4,6 +4,7 @@
 #include "kernels.cuh"
 #include "fwd_kernel.cuh"
 #include "sweep_kernel.cuh"
+#include "tsit5_kernel.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -160,6 +161,9 @@ struct dmt_ctx {
     bool p2p_ready = false;
     int n_ranks = 1;
     int fwd_lanes = 0;       // dmt_set_fwd_lanes: 0 = automatic
+    int bwd_solver = 0;      // dmt_set_bwd_solver: 0 = classical RK4 on the path grid, 1 = adaptive Tsit5 (upstream's solver)
+    double bwd_reltol = 1e-3, bwd_abstol = 1e-6;
+    DevBuf<int> d_steps;     // accepted / rejected steps of the last Tsit5 launch
     int bwd_mode = 0;        // dmt_set_bwd_mode: 0 = automatic, 1 = one thread per (pset, block), 2 = lanes cooperate on one pset
     DevBuf<double> d_xbar[2]; // linearisation points [K][D][P] per store, kept so that a parameter update re-linearises on the device
     std::vector<char> xbar_set[2];
@@ -359,6 +363,14 @@ template <int OP> void launch_fwd(dmt_ctx *c, Layout &L, const FwdArgs &fa) {
 
 template <class MD> void launch_bwd_model(dmt_ctx *c, Layout &L, const BwdArgs &ba) {
     const int nz = c->cfg.two_sided_laws ? 2 : 1;
+    if (c->bwd_solver == 1) { // upstream's solver (tsit5_kernel.cuh); the guiding cache's probes need the fixed-grid discretisation
+        REQUIRE(!ba.use_override, DMT_ERR_UNSUPPORTED, "the guiding cache needs the RK4 backward filter (its F is affine in v only there)");
+        if (c->d_steps.n < 2) c->d_steps.alloc(2);
+        CK(cudaMemsetAsync(c->d_steps.p, 0, 2 * sizeof(int), c->stream));
+        Tsit5Args ta{ba.side_mask, c->bwd_reltol, c->bwd_abstol, c->d_steps.p};
+        ++g_launches, bwd_tsit5_kernel<MD><<<pset_grid(c, L.nb, 32, nz), 32, 0, c->stream>>>(c->dev, L.dev, ta);
+        return;
+    }
     bool all_terminal = true;
     for (int b = 0; b < L.nb; b++) all_terminal = all_terminal && L.last[b];
     const bool coop_ok = MD::ATIL_DIAG && MD::D >= 5 && all_terminal;
@@ -1364,6 +1376,31 @@ int32_t dmt_set_lazy_noise(dmt_ctx *ctx, int32_t enable) {
         ctx->lazy_W = enable != 0;
     });
 }
+int32_t dmt_set_bwd_solver(dmt_ctx *ctx, int32_t solver, double reltol, double abstol) {
+    return guarded(ctx, [&] {
+        if (solver != DMT_K1_RK4 && solver != DMT_K1_TSIT5) throw DmtError(DMT_ERR_ARG, "solver must be DMT_K1_RK4 or DMT_K1_TSIT5");
+        if (solver == DMT_K1_TSIT5) {
+            if (!(reltol > 0.0) || !(abstol >= 0.0)) throw DmtError(DMT_ERR_ARG, "need reltol > 0 and abstol >= 0");
+            for (auto &L : ctx->layouts)
+                if (L.set && L.cache_enabled) throw DmtError(DMT_ERR_STATE, "switch the guiding cache off first: it needs the RK4 backward filter");
+            ctx->bwd_reltol = reltol; ctx->bwd_abstol = abstol;
+        }
+        ensure_W(ctx);
+        invalidate_caches(ctx);
+        ctx->bwd_solver = solver;
+    });
+}
+int32_t dmt_get_bwd_steps(dmt_ctx *ctx, int32_t *accepted, int32_t *rejected) {
+    return guarded(ctx, [&] {
+        int h[2] = {0, 0};
+        if (ctx->d_steps.n >= 2) {
+            CK(cudaMemcpyAsync(h, ctx->d_steps.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+        if (accepted) *accepted = h[0];
+        if (rejected) *rejected = h[1];
+    });
+}
 int32_t dmt_set_bwd_mode(dmt_ctx *ctx, int32_t mode) {
     return guarded(ctx, [&] {
         if (mode < 0 || mode > 2) throw DmtError(DMT_ERR_ARG, "mode must be 0 (auto), 1 (thread per parameter set) or 2 (cooperative)");
@@ -1373,6 +1410,7 @@ int32_t dmt_set_bwd_mode(dmt_ctx *ctx, int32_t mode) {
 int32_t dmt_enable_guiding_cache(dmt_ctx *ctx, int32_t layout, int32_t enable) {
     return guarded(ctx, [&] {
         Layout &L = layout_of(ctx, layout);
+        REQUIRE(!enable || ctx->bwd_solver == 0, DMT_ERR_STATE, "the guiding cache needs the RK4 backward filter (dmt_set_bwd_solver)");
         L.cache_enabled = enable != 0;
         L.cache_valid = false;
         cache_set_private(L, false);

@@ -230,6 +230,18 @@ int32_t dmt_set_sweep_mode(dmt_ctx *ctx, int32_t mode);
  * end point uses the current artificial observation (a difference of the order of sqrt(artificial_noise) in that block). */
 int32_t dmt_set_lazy_noise(dmt_ctx *ctx, int32_t enable);
 
+/* ---- the ODE solver of the backward filter (K1) --------------------------------------------------------------------------
+ * DMT_K1_RK4 (default): classical RK4 on the path grid, covariance form on exact-observation intervals.
+ * DMT_K1_TSIT5: upstream's solver — GuidedProposals integrates (H,F,c) with OrdinaryDiffEq's Tsit5() (OrdinaryDiffEq 5.41.0,
+ * Manifest.toml:352-356; call sites src/sampling_unit.jl:60-66, src/block.jl:104-110): Tsitouras' adaptive 5(4) pair with
+ * OrdinaryDiffEq's default controller and its free interpolant on the path grid; reltol / abstol as passed (OrdinaryDiffEq's defaults:
+ * 1e-3, 1e-6).  Restated from the published method, not bit-equal to upstream (no Julia here) — it carries upstream's O(tolerance)
+ * error, which the RK4 mode does not.  Incompatible with the guiding cache (F is exactly affine in the block end point only under a
+ * fixed-grid discretisation).  dmt_get_bwd_steps: accepted / rejected steps of the last Tsit5 launch, summed over all threads. */
+enum { DMT_K1_RK4 = 0, DMT_K1_TSIT5 = 1 };
+int32_t dmt_set_bwd_solver(dmt_ctx *ctx, int32_t solver, double reltol, double abstol);
+int32_t dmt_get_bwd_steps(dmt_ctx *ctx, int32_t *accepted, int32_t *rejected);
+
 /* ---- tuning: thread mapping of the backward filter (K1) -------------------------------------------------------------
  * 0 (default) = automatic; 1 = one thread per (parameter set, block, side); 2 = d lanes share one parameter set, lane r owning
  * row r of H (wide states; DMT_ERR_UNSUPPORTED where it is not implemented).  Results agree to FP64 rounding. */

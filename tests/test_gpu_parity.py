@@ -539,3 +539,53 @@ def test_lanes_per_chain_do_not_change_any_result(name):
             c.set_fwd_lanes(3)
         finally:
             c.close()
+
+
+@pytest.mark.own_lanes
+@pytest.mark.parametrize("name", ["lorenz", "fhn", "lv", "prok", "jr"])
+@pytest.mark.parametrize("blocking", [False, True])
+def test_tsit5_backward_filter_matches_the_oracle_twin(orc, olib, name, blocking):
+    """dmt_set_bwd_solver(DMT_K1_TSIT5): upstream's solver (adaptive Tsit5, OrdinaryDiffEq default tolerances, dense output on the
+    path grid) on the device against its CPU twin (oracle/dmt_oracle.c).  Both run the same controller, so they take the same steps
+    and agree to rounding-amplified-by-the-controller, far below the solver's own O(1e-4) error against the ODE — which is checked
+    against the RK4 mode here and against scipy in tests/test_oracle_kat.py."""
+    if blocking and name == "jr":
+        pytest.skip("Jansen-Rit with an exact end-point observation is singular (see blocking_problem)")
+    K = 6
+    layouts = [([(0, 2), (3, 5)], 0.7)] if blocking else [([(0, K - 1)], 0.7)]
+    prob = small_problem(name, M=33, K=K, layouts=layouts, seed=7, nsteps=10)
+    ctx = make_ctx(prob, seed=3)
+    ora = OracleEnsemble(orc, olib, prob, seed=3)
+    if blocking:
+        rng = np.random.default_rng(1)
+        X = np.array(configs.X0[prob.model])[None, :, None] * (1 + 0.01 * rng.normal(size=(int(prob.n_pts.sum()), prob.d, prob.M)))
+        ctx.set_X(X, 0); ora.set_X(0, X)
+        ctx.set_artificial_obs(0); ora.set_artificial_obs(0)
+    ctx.recompute_guiding_term(0, _lib.P_ONLY)
+    rk4 = [ctx.get_guiding_term(k, 0, 1 if (blocking and k == 2) else 0) for k in range(K)]
+    ctx.set_bwd_solver(_lib.K1_TSIT5, 1e-3, 1e-6)
+    ctx.recompute_guiding_term(0, _lib.P_ONLY)
+    acc, rej = ctx.get_bwd_steps()
+    n_o = 0
+    for c, b, P, bb in ora.each(0):
+        n_o += P.recompute_guiding_term_tsit5(bb, 0, 1e-3, 1e-6)
+    assert acc > 0 and abs(acc - n_o) <= max(2, 0.01 * n_o), (acc, rej, n_o)      # the same step sequences (a rare straddle of EEst = 1 aside)
+    dev_vs_rk4 = 0.0
+    c_T = float(np.max(np.abs(ora.guiding(2, 0, 1)[2][-1]))) if blocking else 0.0   # v'v / 2 eps: what cancels inside c downstream of it
+    for k in range(K):
+        store = 1 if (blocking and k == 2) else 0
+        compare_guiding(ctx, ora, k, 0, store, tol=1e-7, tag="tsit5/%s%s" % (name, "_blocking" if blocking else ""),
+                        c_cancel=c_T if k <= 2 else 0.0)
+        H, F, c = ctx.get_guiding_term(k, 0, store)
+        dev_vs_rk4 = max(dev_vs_rk4, rel_err(F[:-1], rk4[k][1][:-1]))
+    assert 1e-9 < dev_vs_rk4 < 5e-2, dev_vs_rk4        # it IS a different (looser) discretisation than the default
+    # the forward pass runs on it like on any other guiding term
+    assert ctx.init_paths(0, 100, 50) == 0 if not blocking else True
+    with pytest.raises(dmt_b200.DmtError):
+        ctx.enable_guiding_cache(0)                    # the cache's affine probes need the fixed-grid filter
+    ctx.set_bwd_solver(_lib.K1_RK4)
+    ctx.recompute_guiding_term(0, _lib.P_ONLY)
+    for k in range(K):
+        H, F, c = ctx.get_guiding_term(k, 0, 1 if (blocking and k == 2) else 0)
+        assert np.array_equal(F[:-1], rk4[k][1][:-1])
+    ctx.close()
