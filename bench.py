@@ -215,7 +215,7 @@ class Runner:
         configs.upload(prob, ctx)
         ctx.set_sweep_mode(a.sweep_mode)
         self.fused = self.blocking and not a.separate   # find_W_for_X! + loglikhd! + draw_proposal_path! in one pass
-        self.lazy = self.fused and not a.eager_noise and a.sweep_mode != 1 and prob.P == prob.M
+        self.lazy = self.fused and not a.eager_noise and prob.P == prob.M
         whole = nlay
         ctx.set_blocks(whole, [(0, prob.K - 1)], 0.0)
         ctx.recompute_guiding_term(whole, _lib.P_ONLY)
@@ -436,6 +436,7 @@ def gpu_arm(a):
     value = units_per_step * a.steps / (ms_total * 1e-3)
     ms_per_sweep = ms_total / (a.steps * R)
     kern_ms = run.kernel_ms()
+    fwd_kernel_name = run.ctx.last_forward_kernel()
 
     # ---- roofline of the dominant kernel
     peaks = {}
@@ -457,9 +458,7 @@ def gpu_arm(a):
     units_per_launch = prob.M * prob.steps_per_chain
     algo_bytes = bpu * units_per_launch
     achieved = algo_bytes / (kern_ms[kname] * 1e-3) / 1e9 if kname in kern_ms else None
-    pipelined = fused and a.sweep_mode != 1 and prob.P == prob.M
-    kernel_name = ("sweep_pipe_kernel<%s, lazy=%s>" % (_lib.MODEL_NAMES[prob.model], str(lazy).lower())) if pipelined else \
-        "fwd_kernel<%s, %s>" % (_lib.MODEL_NAMES[prob.model], kop)
+    kernel_name = "%s [%s]" % (fwd_kernel_name, _lib.MODEL_NAMES[prob.model])   # as reported by the library (dmt_get_last_forward_kernel)
     roofline = {"kernel": kernel_name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak if achieved else None, "traffic": None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",

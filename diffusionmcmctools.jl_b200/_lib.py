@@ -72,6 +72,7 @@ SIGNATURES = {
     "dmt_set_proposal_law": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32]),
     "dmt_accept_reject_path": (C.c_int32, [_vp, C.c_int32, C.c_uint32, _dp]),
     "dmt_swap": (C.c_int32, [_vp, C.c_int32, C.c_int32, _bp]),
+    "dmt_swap_blocks": (C.c_int32, [_vp, C.c_int32, C.c_int32, _bp]),
     "dmt_save_ll": (C.c_int32, [_vp, C.c_int32, C.c_uint32]),
     "dmt_fetch_ll": (C.c_int32, [_vp, C.c_int32, C.c_int32, _dp, _dp]),
     "dmt_get_ll": (C.c_int32, [_vp, C.c_int32, C.c_int32, _dp]),
@@ -90,6 +91,7 @@ SIGNATURES = {
     "dmt_get_bwd_steps": (C.c_int32, [_vp, _ip, _ip]),
     "dmt_set_sweep_mode": (C.c_int32, [_vp, C.c_int32]),
     "dmt_set_lazy_noise": (C.c_int32, [_vp, C.c_int32]),
+    "dmt_get_last_forward_kernel": (C.c_int32, [_vp, C.c_char_p, C.c_int32]),
     "dmt_get_X_chains": (C.c_int32, [_vp, C.c_int32, C.c_int32, _ip, _dp]),
     "dmt_get_W_chains": (C.c_int32, [_vp, C.c_int32, C.c_int32, _ip, _dp]),
     "dmt_get_layout_guiding_term": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _dp]),
@@ -386,6 +388,12 @@ class Ctx:
             mp = chain_mask.ctypes.data_as(_bp)
         self._ck(self.lib.dmt_swap(self.h, layout, what, mp))
 
+    def swap_blocks(self, layout, what, mask):
+        """the swaps of dmt_swap for the (block, recording) pairs flagged in mask [n_blocks, M]"""
+        mask = np.ascontiguousarray(mask, dtype=np.uint8)
+        assert mask.shape == (self.layout_nb[layout], self.M)
+        self._ck(self.lib.dmt_swap_blocks(self.h, layout, what, mask.ctypes.data_as(_bp)))
+
     def save_ll(self, layout, it):
         self._ck(self.lib.dmt_save_ll(self.h, layout, it))
 
@@ -453,8 +461,14 @@ class Ctx:
         self._ck(self.lib.dmt_set_fwd_lanes(self.h, int(lanes)))
 
     def set_sweep_mode(self, mode):
-        """fused blocking-sweep pass: 0 = automatic, 1 = register-tile kernel, 2 = software-pipelined kernel (or error)"""
+        """fused blocking-sweep pass: 0 = automatic, 1 = register-tile kernel, 2 = software-pipelined kernel, 3 = warp-specialised kernel (or error)"""
         self._ck(self.lib.dmt_set_sweep_mode(self.h, int(mode)))
+
+    def last_forward_kernel(self):
+        """name / mapping of the forward kernel launched last (diagnostics)"""
+        buf = C.create_string_buffer(96)
+        self._ck(self.lib.dmt_get_last_forward_kernel(self.h, buf, 96))
+        return buf.value.decode()
 
     def set_lazy_noise(self, enable=True):
         """blocking sweeps stop materialising W / W° (rebuilt from X on demand); see include/dmt.h"""

@@ -4,6 +4,7 @@
 #include "kernels.cuh"
 #include "fwd_kernel.cuh"
 #include "sweep_kernel.cuh"
+#include "sweep_ws_kernel.cuh"
 #include "tsit5_kernel.cuh"
 
 #include <algorithm>
@@ -176,6 +177,7 @@ struct dmt_ctx {
     bool pipe_ok = false;    // P == M with the identity pset map: a warp's guiding-term sectors are contiguous (sweep_pipe_kernel)
     int sweep_mode = 0;      // dmt_set_sweep_mode: 0 = automatic (pipelined where eligible), 1 = register-tile kernel, 2 = pipelined or error
     bool lazy_W = false;     // dmt_set_lazy_noise: blocking sweeps do not materialise W_acc / W°
+    char last_fwd_kernel[96] = ""; // name and mapping of the forward kernel launched last (dmt_get_last_forward_kernel)
     int W_stale_layout = -1; // >= 0: W_acc is not materialised; K5 over this layout rebuilds it (ensure_W)
     int G_owner = -1;        // layout whose K1 wrote the shared accepted-law store last (-1: unknown / laws changed)
     bool parP_mixed = false; // a masked swap_PP! made the law parity chain-dependent
@@ -222,6 +224,7 @@ template <class MD, int OP, bool TMA, int G> void launch_fwd_lanes(dmt_ctx *c, L
     }
     if (wave_threads) { *wave_threads = wave[dev]; return; } // query only
     const dim3 grid((unsigned)(((size_t)c->M * G + TPB - 1) / TPB), L.nb, 1);
+    snprintf(c->last_fwd_kernel, sizeof(c->last_fwd_kernel), "fwd_kernel<op=%d, lanes=%d%s%s>", OP, G, TMA ? ", tma" : "", (OP == OP_SWEEP && fa.lazy_w) ? ", lazy" : "");
     ++g_launches, fwd_kernel<MD, OP, TPB, TMA, G><<<grid, TPB, smem, c->stream>>>(c->dev, L.dev, fa);
 }
 // Lanes per (chain, block): 1 when the ensemble fills the GPU by itself; 2, 4 or 8 when M x blocks x lanes still fits one wave
@@ -295,18 +298,70 @@ template <class MD, int G> void launch_sweep_pipe_g(dmt_ctx *c, Layout &L, const
     }
     if (wave_warps) { *wave_warps = wave[dev][lazy]; return; }
     const dim3 grid((unsigned)((c->M + 32 / G - 1) / (32 / G)), L.nb, 1);
+    snprintf(c->last_fwd_kernel, sizeof(c->last_fwd_kernel), "sweep_pipe_kernel<lanes=%d%s>", G, lazy ? ", lazy" : "");
     if (lazy) ++g_launches, sweep_pipe_kernel<MD, true, G><<<grid, 32, smem, c->stream>>>(c->dev, L.dev, fa);
     else ++g_launches, sweep_pipe_kernel<MD, false, G><<<grid, 32, smem, c->stream>>>(c->dev, L.dev, fa);
+}
+// the warp-specialised sweep (sweep_ws_kernel.cuh): a pipeline of warps per group of 32 chains and block.  Two shapes: WsSmall for
+// ensembles that cannot fill the GPU (more helper warps around the one recursion warp, deep rings), WsLarge for full ones
+#ifndef DMT_WS_NR // (tuning builds: -DDMT_WS_NR=.. -DDMT_WS_NSG=.. -DDMT_WS_NSR=..)
+#define DMT_WS_NR 6
+#endif
+#ifndef DMT_WS_NSG
+#define DMT_WS_NSG 8
+#endif
+#ifndef DMT_WS_NSR // depth of the Z, D and X rings
+#define DMT_WS_NSR 4
+#endif
+// ring depths by state dimension: a stage of the G ring is (d(d+1)/2 + d) KiB, the D ring holds the same again per slot
+template <class MD> struct WsShapeOf { using type = WsShape<DMT_WS_NR, (MD::D <= 3 ? DMT_WS_NSG : MD::D == 4 ? 6 : 3), (MD::D <= 3 ? DMT_WS_NSR : MD::D == 4 ? 3 : 2)>; };
+template <class MD, class SH, int MINB> void launch_sweep_ws(dmt_ctx *c, Layout &L, const FwdArgs &fa, bool lazy, size_t *wave_ctas = nullptr) {
+    constexpr size_t smem = sweep_ws_smem<MD, SH>();
+    static_assert(smem <= 227 * 1024, "the rings of the warp-specialised sweep must fit one SM's shared memory");
+    static bool attr_done[64][2] = {};
+    static size_t wave[64][2] = {};
+    const int dev = c->cfg.device & 63;
+    if (!attr_done[dev][lazy]) {
+        int per_sm = 0, sms = 0;
+        if (lazy) {
+            CK(cudaFuncSetAttribute(sweep_ws_kernel<MD, true, SH, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_ws_kernel<MD, true, SH, MINB>, SH::THREADS, smem));
+        } else {
+            CK(cudaFuncSetAttribute(sweep_ws_kernel<MD, false, SH, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_ws_kernel<MD, false, SH, MINB>, SH::THREADS, smem));
+        }
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->cfg.device));
+        wave[dev][lazy] = (size_t)per_sm * sms;
+        attr_done[dev][lazy] = true;
+    }
+    if (wave_ctas) { *wave_ctas = wave[dev][lazy]; return; }
+    const dim3 grid((unsigned)((c->M + 31) / 32), L.nb, 1);
+    snprintf(c->last_fwd_kernel, sizeof(c->last_fwd_kernel), "sweep_ws_kernel<%s>", lazy ? "lazy" : "eager");
+    if (lazy) ++g_launches, sweep_ws_kernel<MD, true, SH, MINB><<<grid, SH::THREADS, smem, c->stream>>>(c->dev, L.dev, fa);
+    else ++g_launches, sweep_ws_kernel<MD, false, SH, MINB><<<grid, SH::THREADS, smem, c->stream>>>(c->dev, L.dev, fa);
 }
 // the software-pipelined sweep (sweep_kernel.cuh): one parameter set per chain in chain order, uniform law parity, device RNG
 template <class MD> bool launch_sweep_pipe(dmt_ctx *c, Layout &L, const FwdArgs &fa) {
     static int env_off = -1;
     if (env_off < 0) env_off = getenv("DMT_NO_SWEEP_PIPE") ? 1 : 0;
     const bool eligible = c->pipe_ok && !c->parP_mixed && !fa.Z && fa.skip == 0;
-    if (c->sweep_mode == 2 && !eligible)
+    if (c->sweep_mode >= 2 && !eligible)
         throw DmtError(DMT_ERR_UNSUPPORTED, "pipelined sweep needs one parameter set per chain in chain order, uniform law parity and device RNG");
     if (!eligible || c->sweep_mode == 1 || (c->sweep_mode == 0 && (c->fwd_lanes != 0 || env_off))) return false;
     const bool lazy = c->lazy_W && covers_all_intervals(c, L);
+    {   // the warp-specialised kernel (one CTA per SM, a fixed ~0.5 ms per round of CTAs on C3): forced by mode 3; automatic while the
+        // grid needs at most 3 rounds — beyond that the one-thread-per-(chain, block) kernels win (profiles/r02_tuning.md)
+        size_t wave_ws = 0;
+        launch_sweep_ws<MD, typename WsShapeOf<MD>::type, 1>(c, L, fa, lazy, &wave_ws);
+        const size_t units = (size_t)((c->M + 31) / 32) * L.nb;
+        static int ws_rounds = -1;
+        if (ws_rounds < 0) { const char *e = getenv("DMT_WS_MAX_ROUNDS"); ws_rounds = e ? atoi(e) : 3; }
+        if (c->sweep_mode == 3 || (c->sweep_mode == 0 && c->fwd_lanes == 0 && wave_ws > 0 && units <= (size_t)ws_rounds * wave_ws)) {
+            launch_sweep_ws<MD, typename WsShapeOf<MD>::type, 1>(c, L, fa, lazy);
+            if (lazy) c->W_stale_layout = L.dev.id;
+            return true;
+        }
+    }
     // automatic choice: with the noise stored every sweep the pipelined kernel's live set (two more tile buffers) spills and it loses to the
     // register-tile kernel (3.9 against 3.5 ms on C3, profiles/r02_tuning.md); it wins where the noise is lazy (2.44 against 3.5 ms)
     if (c->sweep_mode == 0 && !lazy) return false;
@@ -331,7 +386,8 @@ template <class MD> bool launch_sweep_pipe(dmt_ctx *c, Layout &L, const FwdArgs 
     return true;
 }
 
-template <int OP> void launch_fwd(dmt_ctx *c, Layout &L, const FwdArgs &fa) {
+template <int OP> void launch_fwd(dmt_ctx *c, Layout &L, const FwdArgs &fa_in) {
+    FwdArgs fa = fa_in;
     // lazy noise (dmt_set_lazy_noise): an op that reads W, or rewrites only part of it, first rebuilds it from X; an op that
     // rewrites all of it just clears the flag
     if (c->W_stale_layout >= 0 && OP != OP_LOGLIK) {
@@ -350,6 +406,10 @@ template <int OP> void launch_fwd(dmt_ctx *c, Layout &L, const FwdArgs &fa) {
         }
 #undef DMT_CASE
         if (done) { CK(cudaGetLastError()); return; }
+    }
+    if (OP == OP_SWEEP && c->lazy_W && !fa.Z && covers_all_intervals(c, L)) { // the register-tile kernel, lazy noise: same stores skipped
+        fa.lazy_w = 1;
+        c->W_stale_layout = L.dev.id;
     }
 #define DMT_CASE(MID)                                                                                              \
     case MID: launch_fwd_model<Model<MID>, OP>(c, L, fa); break;
@@ -1182,28 +1242,36 @@ int32_t dmt_accept_reject_path(dmt_ctx *ctx, int32_t layout, uint32_t iter, cons
     });
 }
 
+static void swap_impl(dmt_ctx *ctx, int32_t layout, int32_t what, const uint8_t *mask, bool per_block) {
+    Layout &L = layout_of(ctx, layout);
+    REQUIRE(what > 0 && what < 16, DMT_ERR_ARG, "empty or unknown swap mask");
+    if (what & (DMT_SWAP_WW | DMT_SWAP_PP)) ensure_W(ctx); // (lazy noise) the noise about to change sides / laws must exist
+    const uint8_t *dm = nullptr;
+    if (mask) {
+        REQUIRE(!(what & DMT_SWAP_PP) || ctx->P == ctx->M, DMT_ERR_UNSUPPORTED, "masked swap_PP! needs n_psets == n_chains");
+        const size_t n = (size_t)ctx->M * (per_block ? L.nb : 1);
+        if (ctx->d_mask.n < n) ctx->d_mask.alloc(n);
+        CK(cudaMemcpyAsync(ctx->d_mask.p, mask, n, cudaMemcpyHostToDevice, ctx->stream));
+        dm = ctx->d_mask.p;
+    }
+    if (what & (DMT_SWAP_XX | DMT_SWAP_WW | DMT_SWAP_LL))
+        ++g_launches, swap_paths_kernel<<<chain_grid(ctx, L.nb, 128), 128, 0, ctx->stream>>>(ctx->dev, L.dev, what, dm, per_block ? 1 : 0);
+    if (what & DMT_SWAP_PP) {
+        check_law_side(ctx, 1);
+        invalidate_caches(ctx); // the accepted laws are now the former proposals (their guiding term is in the shared store)
+        if (mask) ctx->parP_mixed = true;
+        ++g_launches, swap_laws_kernel<<<pset_grid(ctx, L.nb, 128), 128, 0, ctx->stream>>>(ctx->dev, L.dev, dm, per_block ? 1 : 0);
+    }
+    CK(cudaGetLastError());
+    if (mask) CK(cudaStreamSynchronize(ctx->stream));
+}
 int32_t dmt_swap(dmt_ctx *ctx, int32_t layout, int32_t what, const uint8_t *chain_mask) {
+    return guarded(ctx, [&] { swap_impl(ctx, layout, what, chain_mask, false); });
+}
+int32_t dmt_swap_blocks(dmt_ctx *ctx, int32_t layout, int32_t what, const uint8_t *block_chain_mask) {
     return guarded(ctx, [&] {
-        Layout &L = layout_of(ctx, layout);
-        REQUIRE(what > 0 && what < 16, DMT_ERR_ARG, "empty or unknown swap mask");
-        if (what & (DMT_SWAP_WW | DMT_SWAP_PP)) ensure_W(ctx); // (lazy noise) the noise about to change sides / laws must exist
-        const uint8_t *dm = nullptr;
-        if (chain_mask) {
-            REQUIRE(!(what & DMT_SWAP_PP) || ctx->P == ctx->M, DMT_ERR_UNSUPPORTED, "per-chain swap_PP! needs n_psets == n_chains");
-            if (ctx->d_mask.n < (size_t)ctx->M) ctx->d_mask.alloc(ctx->M);
-            CK(cudaMemcpyAsync(ctx->d_mask.p, chain_mask, ctx->M, cudaMemcpyHostToDevice, ctx->stream));
-            dm = ctx->d_mask.p;
-        }
-        if (what & (DMT_SWAP_XX | DMT_SWAP_WW | DMT_SWAP_LL))
-            ++g_launches, swap_paths_kernel<<<chain_grid(ctx, L.nb, 128), 128, 0, ctx->stream>>>(ctx->dev, L.dev, what, dm);
-        if (what & DMT_SWAP_PP) {
-            check_law_side(ctx, 1);
-            invalidate_caches(ctx); // the accepted laws are now the former proposals (their guiding term is in the shared store)
-            if (chain_mask) ctx->parP_mixed = true;
-            ++g_launches, swap_laws_kernel<<<pset_grid(ctx, L.nb, 128), 128, 0, ctx->stream>>>(ctx->dev, L.dev, dm);
-        }
-        CK(cudaGetLastError());
-        if (chain_mask) CK(cudaStreamSynchronize(ctx->stream));
+        if (!block_chain_mask) throw DmtError(DMT_ERR_ARG, "dmt_swap_blocks needs a [n_blocks][n_chains] mask (dmt_swap swaps everything)");
+        swap_impl(ctx, layout, what, block_chain_mask, true);
     });
 }
 
@@ -1364,9 +1432,15 @@ int32_t dmt_set_fwd_lanes(dmt_ctx *ctx, int32_t lanes) {
         ctx->fwd_lanes = lanes;
     });
 }
+int32_t dmt_get_last_forward_kernel(dmt_ctx *ctx, char *buf, int32_t len) {
+    return guarded(ctx, [&] {
+        if (!buf || len <= 0) throw DmtError(DMT_ERR_ARG, "need a buffer");
+        snprintf(buf, (size_t)len, "%s", ctx->last_fwd_kernel);
+    });
+}
 int32_t dmt_set_sweep_mode(dmt_ctx *ctx, int32_t mode) {
     return guarded(ctx, [&] {
-        if (mode < 0 || mode > 2) throw DmtError(DMT_ERR_ARG, "mode must be 0 (auto), 1 (register-tile kernel) or 2 (software-pipelined kernel)");
+        if (mode < 0 || mode > 3) throw DmtError(DMT_ERR_ARG, "mode must be 0 (auto), 1 (register-tile kernel), 2 (software-pipelined kernel) or 3 (warp-specialised kernel)");
         ctx->sweep_mode = mode;
     });
 }

@@ -406,13 +406,16 @@ __global__ void DMT_FWD_BOUNDS fwd_kernel(const DevCtx cx, const LayoutDev ly, c
                 }
             }
             DMT_CLK(ck3);
-            if (WRITES_W && (!RNG || SWEEP) && live) {
+            const bool keep_w = !SWEEP || !fa.lazy_w; // lazy noise (dmt_set_lazy_noise): the blocking sweep never reads what it would store here
+            if (WRITES_W && (!RNG || SWEEP) && live && keep_w) {
 #pragma unroll
                 for (int j = 0; j < DW; j++) st256(Wout + ((size_t)q * DW + j) * M * 4, w[j]);
             }
             if (SWEEP && live) {
+                if (keep_w) {
 #pragma unroll
-                for (int j = 0; j < DW; j++) st256(Wprop + ((size_t)q * DW + j) * M * 4, wo[j]);
+                    for (int j = 0; j < DW; j++) st256(Wprop + ((size_t)q * DW + j) * M * 4, wo[j]);
+                }
 #pragma unroll
                 for (int i = 0; i < D; i++) st256(Xout + ((size_t)q * D + i) * M * 4, xot[i]);
             }

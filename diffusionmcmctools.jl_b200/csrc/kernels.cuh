@@ -97,11 +97,15 @@ struct FwdArgs {
     uint32_t iter;
     int law_side, w_side, skip;
     const double *Z; // device, [S][DW][M] standard normals or null
+    int lazy_w;      // OP_SWEEP: do not store W_acc / W° (dmt_set_lazy_noise; set by the launcher, never by callers)
 };
 
 // ------------------------------------------------------------------------------------------- 256-bit sector access
 __device__ __forceinline__ void ld256(const double *p, double *v) { // streaming read-only sector
-#if DMT_EVICT_FIRST
+#if defined(DMT_LD256_SPLIT) // (experiment: the sector as two 128-bit loads)
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v[2]), "=d"(v[3]) : "l"(p + 2));
+#elif DMT_EVICT_FIRST
     asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
 #else
     asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
@@ -926,9 +930,11 @@ __global__ void save_ll_kernel(const DevCtx cx, const LayoutDev ly, uint32_t ite
 }
 
 // swap_XX!/swap_WW!/swap_ll! (src/biblock.jl:158-173,206-208) per (chain, block)
-__global__ void swap_paths_kernel(const DevCtx cx, const LayoutDev ly, int what, const uint8_t *mask) {
+// mask: null = every (chain, block); per_block == 0: [M], one flag per chain; per_block == 1: [nb][M], one flag per (block, chain) —
+// the BiBlock-level swaps of one block of one recording (src/biblock.jl:148-209)
+__global__ void swap_paths_kernel(const DevCtx cx, const LayoutDev ly, int what, const uint8_t *mask, int per_block) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
-    if (c >= cx.M || (mask && !mask[c])) return;
+    if (c >= cx.M || (mask && !mask[(per_block ? (size_t)b * cx.M : 0) + c])) return;
     const size_t M = cx.M, idx = (size_t)b * M + c;
     for (int k = ly.i0[b]; k <= ly.i1[b]; ++k) {
         if (what & 1) cx.parX[(size_t)k * M + c] ^= 1;
@@ -942,9 +948,9 @@ __global__ void swap_paths_kernel(const DevCtx cx, const LayoutDev ly, int what,
 }
 // swap_PP! (src/biblock.jl:182-199) per (pset, block): terminal: PP[i0..i1]; non-terminal: PP[i0..i1] (PP + P_excl) and
 // PPb[i0..i1] (Pb_excl + P_last)
-__global__ void swap_laws_kernel(const DevCtx cx, const LayoutDev ly, const uint8_t *mask) {
+__global__ void swap_laws_kernel(const DevCtx cx, const LayoutDev ly, const uint8_t *mask, int per_block) {
     const int ps = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
-    if (ps >= cx.P || (mask && !mask[ps])) return;
+    if (ps >= cx.P || (mask && !mask[(per_block ? (size_t)b * cx.P : 0) + ps])) return;
     const size_t P = cx.P;
     for (int k = ly.i0[b]; k <= ly.i1[b]; ++k) {
         cx.parP[0][(size_t)k * P + ps] ^= 1;

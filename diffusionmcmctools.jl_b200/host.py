@@ -123,7 +123,8 @@ class SamplingEnsemble:
 
 
 class _BlockSide:
-    """bb.b / bb.b° of one (recording, block): read-only view"""
+    """bb.b / bb.b° of one (recording, block) — a `Block` (src/block.jl:17-71) as a view into the device ensemble: XX, WW, ll,
+    ll_history are read on demand (a few KB through dmt_get_X_chains / dmt_get_W_chains), nothing is cached on the host."""
 
     def __init__(self, be, rec, blk, side):
         self._be, self._rec, self._blk, self._side = be, rec, blk, side
@@ -136,8 +137,31 @@ class _BlockSide:
     def ll_history(self):
         return self._be.ctx.get_ll_history(self._be.layout, self._side, 0, self._be.ll_hist_len - 1)[:, self._blk, self._rec]
 
+    @property
+    def XX(self):
+        """the block's paths, one (t [n_k], x [n_k, d]) pair per observation interval — b.XX (src/block.jl:65)"""
+        ctx, (i0, i1) = self._be.ctx, self._be.ranges[self._blk]
+        X = ctx.get_X_chains([self._rec], self._side)[:, :, 0]
+        return [(ctx.tt[ctx.pt0[k]:ctx.pt0[k + 1]].copy(), X[ctx.pt0[k]:ctx.pt0[k + 1]].copy()) for k in range(i0, i1 + 1)]
+
+    @property
+    def WW(self):
+        """the block's driving noise as the reference stores it: per interval a Wiener PATH starting at 0 (cumulative sum of the
+        library's increments) on the interval's time grid — b.WW (src/block.jl:64)"""
+        ctx, (i0, i1) = self._be.ctx, self._be.ranges[self._blk]
+        dW = ctx.get_W_chains([self._rec], self._side)[:, :, 0]
+        out = []
+        for k in range(i0, i1 + 1):
+            inc = dW[ctx.step0[k]:ctx.step0[k + 1]]
+            out.append((ctx.tt[ctx.pt0[k]:ctx.pt0[k + 1]].copy(), np.concatenate([np.zeros((1, ctx.dw)), np.cumsum(inc, axis=0)])))
+        return out
+
 
 class BiBlockView:
+    """`BiBlock` (src/biblock.jl:17-62) of one recording: bb.b, bb.b°, bb.ρ, bb.accpt_history and the BiBlock-level methods that act on
+    ONE block of ONE recording.  The numerical calls (draw_proposal_path!, accept_reject_proposal_path!, loglikhd!, ...) are batched
+    over all recordings and blocks on the device — call them on the BlockEnsemble; here are the ones that make sense per block."""
+
     def __init__(self, be, rec, blk):
         self.b, self.b_o = _BlockSide(be, rec, blk, 0), _BlockSide(be, rec, blk, 1)
         self.rho = float(be.rho[blk])
@@ -147,10 +171,89 @@ class BiBlockView:
     def accpt_history(self):
         return self._be.ctx.get_accept_history(self._be.layout, 0, self._be.ll_hist_len - 1)[:, self._blk, self._rec]
 
+    def _mask(self):
+        m = np.zeros((self._be.n_blocks, self._be.ctx.M), dtype=np.uint8)
+        m[self._blk, self._rec] = 1
+        return m
+
+    # swap_XX!(bb) ... swap_paths!(bb)  src/biblock.jl:148-209
+    def swap_XX(self):
+        self._be.ctx.swap_blocks(self._be.layout, _lib.SWAP_XX, self._mask())
+
+    def swap_WW(self):
+        self._be.ctx.swap_blocks(self._be.layout, _lib.SWAP_WW, self._mask())
+
+    def swap_paths(self):
+        self._be.ctx.swap_blocks(self._be.layout, _lib.SWAP_XX | _lib.SWAP_WW, self._mask())
+
+    def swap_ll(self):
+        self._be.ctx.swap_blocks(self._be.layout, _lib.SWAP_LL, self._mask())
+
+    def swap_PP(self):
+        """(needs one parameter set per recording; the host copy of θ stays with the ensemble — see swap_PP(be, mask))"""
+        self._be.ctx.swap_blocks(self._be.layout, _lib.SWAP_PP, self._mask())
+
+    def set_accepted(self, i, v):
+        """set_accepted!(bb, i, v)  src/biblock.jl:130-135"""
+        ctx, lay = self._be.ctx, self._be.layout
+        a = ctx.get_accept_history(lay, i, i)[0]
+        a[self._blk, self._rec] = bool(v)
+        ctx.set_accepted(lay, i, a)
+
+    def set_ll(self, i, v, side=0):
+        """set_ll!(bb.b, i, v)  src/block.jl:82-86"""
+        ctx, lay = self._be.ctx, self._be.layout
+        h = ctx.get_ll_history(lay, side, i, i)[0]
+        h[self._blk, self._rec] = float(v)
+        ctx.set_ll_history(lay, side, i, h)
+
+    def ll_of_accepted(self, i):
+        """ll_of_accepted(bb, i)  src/biblock.jl:218-225"""
+        return float((self.b_o if self.accpt_history[i] else self.b).ll_history[i])
+
+    def accpt_rate(self, rng):
+        """accpt_rate(bb, range)  src/biblock.jl:228-232"""
+        return float(np.mean(self.accpt_history[rng[0]:rng[-1] + 1]))
+
 
 class BlockCollectionView:
+    """`BlockCollection` (src/block_collection.jl:17-36): all blocks of ONE recording."""
+
     def __init__(self, be, rec):
         self.blocks = [BiBlockView(be, rec, b) for b in range(be.n_blocks)]
+        self._be, self._rec = be, rec
+
+    def _mask(self):
+        m = np.zeros(self._be.ctx.M, dtype=np.uint8)
+        m[self._rec] = 1
+        return m
+
+    # src/block_collection.jl:84-118
+    def swap_XX(self):
+        self._be.ctx.swap(self._be.layout, _lib.SWAP_XX, self._mask())
+
+    def swap_WW(self):
+        self._be.ctx.swap(self._be.layout, _lib.SWAP_WW, self._mask())
+
+    def swap_paths(self):
+        self._be.ctx.swap(self._be.layout, _lib.SWAP_XX | _lib.SWAP_WW, self._mask())
+
+    def swap_ll(self):
+        self._be.ctx.swap(self._be.layout, _lib.SWAP_LL, self._mask())
+
+    def fetch_ll(self):
+        """fetch_ll(bc)  src/block_collection.jl:143: the sum over the recording's blocks"""
+        return float(self._be.ctx.get_ll(self._be.layout, 0)[:, self._rec].sum())
+
+    def fetch_ll_o(self):
+        return float(self._be.ctx.get_ll(self._be.layout, 1)[:, self._rec].sum())
+
+    def accpt_rate(self, rng):
+        """accpt_rate(bc, range)  src/block_collection.jl:175-184: one rate per block"""
+        return [bb.accpt_rate(rng) for bb in self.blocks]
+
+    def ll_of_accepted(self, i):
+        return [bb.ll_of_accepted(i) for bb in self.blocks]
 
 
 class BlockEnsemble:

@@ -167,6 +167,9 @@ int32_t dmt_set_proposal_law(dmt_ctx *ctx, int32_t layout, int32_t critical_chan
 int32_t dmt_accept_reject_path(dmt_ctx *ctx, int32_t layout, uint32_t iter, const double *E);
 /* swap_XX!/swap_WW!/swap_PP!/swap_ll!/swap_paths! (src/biblock.jl:148-209); chain_mask[M] or NULL (= all) */
 int32_t dmt_swap(dmt_ctx *ctx, int32_t layout, int32_t what, const uint8_t *chain_mask);
+/* The same swaps for SOME blocks of SOME recordings: mask[n_blocks][M], 1 = swap — the BiBlock-level methods swap_XX!(bb) ...
+ * swap_ll!(bb) of one block of one recording (src/biblock.jl:148-209) and the BlockCollection-level ones (src/block_collection.jl:84-118). */
+int32_t dmt_swap_blocks(dmt_ctx *ctx, int32_t layout, int32_t what, const uint8_t *block_chain_mask);
 /* save_ll!(be, i)                          src/biblock.jl:256-259 */
 int32_t dmt_save_ll(dmt_ctx *ctx, int32_t layout, uint32_t iter);
 
@@ -218,8 +221,14 @@ int32_t dmt_set_fwd_lanes(dmt_ctx *ctx, int32_t lanes);
  * 0 (default) = automatic: the software-pipelined kernel (guiding term through a TMA shared-memory ring, X double-buffered in
  * registers; sweep_kernel.cuh) when every chain owns its parameter set in chain order, the law parity is uniform, Z == NULL and
  * dmt_set_fwd_lanes is automatic; the register-tile kernel otherwise.  1 = always the register-tile kernel.  2 = pipelined kernel or
- * DMT_ERR_UNSUPPORTED.  Same arithmetic, results equal up to FP64 rounding (different FMA contraction). */
+ * DMT_ERR_UNSUPPORTED.  3 = warp-specialised kernel (sweep_spec_kernel.cuh: per group of 32 chains and block one warp does the inverse
+ * solve and the accepted path's likelihood, two warps generate the normals and one warp runs the proposal recursion, one tile apart)
+ * under the same conditions, or DMT_ERR_UNSUPPORTED.  Same arithmetic, results equal up to FP64 rounding (different FMA contraction). */
 int32_t dmt_set_sweep_mode(dmt_ctx *ctx, int32_t mode);
+/* Diagnostics: name and thread mapping of the forward kernel (K2-K5) this context launched last, e.g. "sweep_ws_kernel<lazy>",
+ * "sweep_pipe_kernel<lanes=1, lazy>", "fwd_kernel<op=6, lanes=4>" — what a benchmark should print instead of guessing the automatic
+ * choice.  No counterpart in the reference. */
+int32_t dmt_get_last_forward_kernel(dmt_ctx *ctx, char *buf, int32_t len);
 /* Lazy noise.  In the blocking loop find_W_for_X!(be) overwrites b.WW at the start of EVERY sweep
  * (docs/src/tutorials/block_collection/inference_with_blocking.md:52-58, src/block.jl:120-131), so the accepted noise W and the
  * proposal noise W° the sweep produces are never read.  With enable = 1 the pipelined sweep over a layout that covers all intervals

@@ -325,3 +325,63 @@ def test_checkpoint_resume_with_parameter_updates_is_bit_exact(tmp_path):
     for a, b in zip(want, got):
         assert np.array_equal(a, b, equal_nan=True)
     se2.ctx.close()
+
+
+def test_biblock_and_block_collection_views():
+    """be.recordings[r] (BlockCollection, src/block_collection.jl:17-36) and .blocks[b] (BiBlock, src/biblock.jl:17-62) as views of the
+    device ensemble: XX / WW in the reference's containers (per-interval time grids, cumulative Wiener paths), the per-block and
+    per-recording swaps (src/biblock.jl:148-209, src/block_collection.jl:84-118) and the history setters / readers."""
+    K, nit = 6, 3
+    prob = configs.make_problem("lorenz", 9, K=K, dt=0.01, seed=5, layouts=[([(0, 1), (2, 5)], 0.8)])
+    se = H.SamplingEnsemble(prob.model, recordings_of(prob), (prob.n_pts, prob.tt), seed=4, two_sided_laws=True)
+    se.init_paths()
+    be = H.BlockEnsemble(se, [(0, 1), (2, 5)], 0.8, nit)
+    ctx = se.ctx
+    H.set_obs(be); H.recompute_guiding_term(be, H.P_only); H.find_W_for_X(be); H.loglikhd(be)
+    for i in range(nit):
+        H.draw_proposal_path(be, i); H.accept_reject_proposal_path(be, i)
+    H.draw_proposal_path(be, nit)                                # leave a proposal in place: both sides differ now
+    X0, X1, W0, W1 = ctx.get_X(0), ctx.get_X(1), ctx.get_W(0), ctx.get_W(1)
+    ll = ctx.get_ll(be.layout, 0), ctx.get_ll(be.layout, 1)
+    rec, blk = 4, 1
+    bc = be.recordings[rec]; bb = bc.blocks[blk]
+    # ---- containers
+    XX, WW = bb.b.XX, bb.b.WW
+    assert len(XX) == 4 and len(WW) == 4                         # intervals 2..5
+    for j, k in enumerate(range(2, 6)):
+        t, x = XX[j]
+        assert np.array_equal(t, prob.tt[ctx.pt0[k]:ctx.pt0[k + 1]]) and np.array_equal(x, X0[ctx.pt0[k]:ctx.pt0[k + 1], :, rec])
+        tw, w = WW[j]
+        assert w.shape == (ctx.n_pts[k], prob.dw) and np.all(w[0] == 0.0) and np.array_equal(tw, t)
+        assert np.allclose(np.diff(w, axis=0), W0[ctx.step0[k]:ctx.step0[k + 1], :, rec], rtol=0, atol=1e-15)
+    assert np.array_equal(bb.b_o.XX[0][1], X1[ctx.pt0[2]:ctx.pt0[3], :, rec])
+    assert bb.b.ll == ll[0][blk, rec] and bb.b_o.ll == ll[1][blk, rec]
+    assert bc.fetch_ll() == ll[0][:, rec].sum() and bc.fetch_ll_o() == ll[1][:, rec].sum()
+    # ---- BiBlock-level swaps touch exactly one block of one recording
+    bb.swap_XX()
+    Y0, Y1 = ctx.get_X(0), ctx.get_X(1)
+    sl = slice(ctx.pt0[2], ctx.pt0[6])
+    assert np.array_equal(Y0[sl, :, rec], X1[sl, :, rec]) and np.array_equal(Y1[sl, :, rec], X0[sl, :, rec])
+    other = np.ones(X0.shape, bool); other[sl, :, rec] = False
+    assert np.array_equal(Y0[other], X0[other]) and np.array_equal(Y1[other], X1[other])
+    bb.swap_XX()
+    assert np.array_equal(ctx.get_X(0), X0)
+    bb.swap_paths(); bb.swap_ll()
+    ws = slice(ctx.step0[2], ctx.step0[6])
+    assert np.array_equal(ctx.get_W(0)[ws, :, rec], W1[ws, :, rec]) and np.array_equal(ctx.get_X(0)[sl, :, rec], X1[sl, :, rec])
+    assert ctx.get_ll(be.layout, 0)[blk, rec] == ll[1][blk, rec] and ctx.get_ll(be.layout, 0)[0, rec] == ll[0][0, rec]
+    bb.swap_paths(); bb.swap_ll()
+    # ---- BlockCollection-level swaps: every block of one recording
+    bc.swap_XX()
+    Y0 = ctx.get_X(0)
+    assert np.array_equal(Y0[:, :, rec], X1[:, :, rec]) and np.array_equal(np.delete(Y0, rec, axis=2), np.delete(X0, rec, axis=2))
+    bc.swap_XX()
+    # ---- histories
+    bb.set_accepted(1, True); bb.set_ll(1, -3.5, side=1)
+    assert bb.accpt_history[1] and bb.ll_of_accepted(1) == -3.5
+    bb.set_accepted(1, False); bb.set_ll(1, -7.25, side=0)
+    assert not bb.accpt_history[1] and bb.ll_of_accepted(1) == -7.25
+    assert bb.accpt_rate((0, nit - 1)) == np.mean(bb.accpt_history)
+    assert bc.accpt_rate((0, nit - 1)) == [b.accpt_rate((0, nit - 1)) for b in bc.blocks]
+    assert np.allclose(H.ll_of_accepted(be, 1)[rec], bc.ll_of_accepted(1))
+    ctx.close()
