@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--no-cache", action="store_true", help="blocking sweep with the full backward filter every sweep (no guiding cache)")
     ap.add_argument("--separate", action="store_true", help="blocking sweep with the three separate passes instead of the fused one")
     ap.add_argument("--sweep-mode", type=int, default=0, help="fused pass: 0 auto (software-pipelined where eligible), 1 register-tile kernel, 2 pipelined")
+    ap.add_argument("--fwd-lanes", type=int, default=0, help="lanes per (chain, block) in the forward kernel (0: automatic)")
     ap.add_argument("--eager-noise", action="store_true", help="the sweep stores W_acc / W° (default: lazy noise, rebuilt from X on demand)")
     return ap.parse_args()
 
@@ -214,6 +215,8 @@ class Runner:
                                       chain_offset=lo, seed=2026, pset_of_chain=prob.pset_of_chain)
         configs.upload(prob, ctx)
         ctx.set_sweep_mode(a.sweep_mode)
+        if a.fwd_lanes:
+            ctx.set_fwd_lanes(a.fwd_lanes)
         self.fused = self.blocking and not a.separate   # find_W_for_X! + loglikhd! + draw_proposal_path! in one pass
         self.lazy = self.fused and not a.eager_noise and prob.P == prob.M
         whole = nlay

@@ -102,6 +102,7 @@ SIGNATURES = {
     "dmt_allreduce_stats": (C.c_int32, [_vp, C.c_int32, _dp]),
     "dmt_snapshot_paths_async": (C.c_int32, [_vp, C.c_int32, C.c_int32, _ip, _dp]),
     "dmt_snapshot_wait": (C.c_int32, [_vp]),
+    "dmt_histories_async": (C.c_int32, [_vp, C.c_int32, C.c_uint32, C.c_uint32, _dp, _bp]),
     "dmt_set_accepted": (C.c_int32, [_vp, C.c_int32, C.c_uint32, _bp]),
     "dmt_set_ll_history": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_uint32, _dp]),
     "dmt_p2p_export": (C.c_int32, [_vp, _bp]),
@@ -309,6 +310,17 @@ class Ctx:
         sel = np.ascontiguousarray(chains, dtype=np.int32)
         assert out.dtype == np.float64 and out.flags.c_contiguous and out.shape == (self.NP, self.d, sel.size)
         self._ck(self.lib.dmt_snapshot_paths_async(self.h, side, int(sel.size), sel.ctypes.data_as(_ip), _p(out)))
+
+    def histories_async(self, layout, it0, it1, out_ll=None, out_acc=None):
+        """queue a copy of ll_history rows it0..it1 into out_ll [n, 2, nb, M] (float64) and / or accpt_history into out_acc [n, nb, M]
+        (uint8); C-contiguous, ideally page-locked; read after snapshot_wait()"""
+        n, nb = it1 - it0 + 1, self.layout_nb[layout]
+        if out_ll is not None:
+            assert out_ll.dtype == np.float64 and out_ll.flags.c_contiguous and out_ll.shape == (n, 2, nb, self.M)
+        if out_acc is not None:
+            assert out_acc.dtype == np.uint8 and out_acc.flags.c_contiguous and out_acc.shape == (n, nb, self.M)
+        self._ck(self.lib.dmt_histories_async(self.h, layout, it0, it1, _p(out_ll) if out_ll is not None else None,
+                                              out_acc.ctypes.data_as(_bp) if out_acc is not None else None))
 
     def snapshot_wait(self):
         self._ck(self.lib.dmt_snapshot_wait(self.h))

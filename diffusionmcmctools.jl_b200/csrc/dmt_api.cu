@@ -170,7 +170,7 @@ struct dmt_ctx {
     std::vector<char> xbar_set[2];
     // thinned path saving (dmt_snapshot_paths_async): staging buffer + copy stream
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_gathered = nullptr, ev_copied = nullptr;
+    cudaEvent_t ev_gathered = nullptr, ev_copied = nullptr, ev_hist = nullptr;
     DevBuf<double> d_snap;
     DevBuf<int> d_snap_sel;
     bool tma_ok = false;     // P == M with the identity pset map: the TMA fast path of fwd_kernel is usable
@@ -239,7 +239,13 @@ template <class MD, int OP, bool TMA> void launch_fwd_variant(dmt_ctx *c, Layout
         const size_t units = (size_t)c->M * L.nb;
         int w = 0;
         if (forced) lanes = forced;
-        else if (MD::DW >= 2) { // with one Wiener coordinate the generator is a small part of the tile: redundant lanes only cost issue slots
+        else if (MD::DW >= 2 && OP == OP_SWEEP) {
+            // the fused sweep: two lanes whenever the doubled grid still fits one wave — measured best at every ensemble size where
+            // it applies (Lorenz, lazy noise, fused pass in ms for 512 / 768 / 1024 / 1536 chains: 1 lane 2.12 / 2.14 / 2.15 / 2.17,
+            // 2 lanes 1.03 / 1.05 / 1.35 / 1.39, 4 lanes 1.14 / 1.17 / 1.81 / 2.29; profiles/r02_tuning.md)
+            launch_fwd_lanes<MD, OP, false, 2>(c, L, fa, &w);
+            if (units * 2 <= (size_t)w) lanes = 2;
+        } else if (MD::DW >= 2) { // with one Wiener coordinate the generator is a small part of the tile: redundant lanes only cost issue slots
                                  // (Jansen-Rit draw, 8192 chains: 87 ms with 1 lane, 121 ms with 4)
             launch_fwd_lanes<MD, OP, false, 8>(c, L, fa, &w);
             if (units * 8 <= (size_t)w) lanes = 8;
@@ -350,12 +356,12 @@ template <class MD> bool launch_sweep_pipe(dmt_ctx *c, Layout &L, const FwdArgs 
     if (!eligible || c->sweep_mode == 1 || (c->sweep_mode == 0 && (c->fwd_lanes != 0 || env_off))) return false;
     const bool lazy = c->lazy_W && covers_all_intervals(c, L);
     {   // the warp-specialised kernel (one CTA per SM, a fixed ~0.5 ms per round of CTAs on C3): forced by mode 3; automatic while the
-        // grid needs at most 3 rounds — beyond that the one-thread-per-(chain, block) kernels win (profiles/r02_tuning.md)
+        // grid needs at most 2 rounds — beyond that the one-thread-per-(chain, block) kernels win (profiles/r02_tuning.md)
         size_t wave_ws = 0;
         launch_sweep_ws<MD, typename WsShapeOf<MD>::type, 1>(c, L, fa, lazy, &wave_ws);
         const size_t units = (size_t)((c->M + 31) / 32) * L.nb;
         static int ws_rounds = -1;
-        if (ws_rounds < 0) { const char *e = getenv("DMT_WS_MAX_ROUNDS"); ws_rounds = e ? atoi(e) : 3; }
+        if (ws_rounds < 0) { const char *e = getenv("DMT_WS_MAX_ROUNDS"); ws_rounds = e ? atoi(e) : 2; }
         if (c->sweep_mode == 3 || (c->sweep_mode == 0 && c->fwd_lanes == 0 && wave_ws > 0 && units <= (size_t)ws_rounds * wave_ws)) {
             launch_sweep_ws<MD, typename WsShapeOf<MD>::type, 1>(c, L, fa, lazy);
             if (lazy) c->W_stale_layout = L.dev.id;
@@ -365,20 +371,20 @@ template <class MD> bool launch_sweep_pipe(dmt_ctx *c, Layout &L, const FwdArgs 
     // automatic choice: with the noise stored every sweep the pipelined kernel's live set (two more tile buffers) spills and it loses to the
     // register-tile kernel (3.9 against 3.5 ms on C3, profiles/r02_tuning.md); it wins where the noise is lazy (2.44 against 3.5 ms)
     if (c->sweep_mode == 0 && !lazy) return false;
-    // lanes per (chain, block): 4 when the ensemble is too small to give every scheduler a warp and 4 x as many warps still fit one wave
-    // (the lanes split the generator calls; models with one Wiener coordinate have too little generator work to split)
+    // lanes per (chain, block) in the pipelined kernel: one.  (The 4-lane instantiation exists and can be forced with dmt_set_fwd_lanes(4), but
+    // it never won: 2.56 against 1.40 ms at 1024 chains.)  Mid-size ensembles — a doubled grid of the register-tile kernel still fits one
+    // wave — go to that kernel with two lanes per (chain, block), which splits the generator: 1.35 against 1.40 ms at 1024 chains, 1.03
+    // against 1.38 ms at 512 (profiles/r02_tuning.md).
     constexpr int GW = MD::DW >= 2 ? 4 : 1; // the wide mapping exists for these models only
     bool g4 = false;
     if (c->fwd_lanes != 0) { // dmt_set_fwd_lanes together with dmt_set_sweep_mode(2): force the mapping
         if (c->fwd_lanes != 1 && !(c->fwd_lanes == 4 && GW == 4))
             throw DmtError(DMT_ERR_UNSUPPORTED, "the pipelined sweep maps 1 or (models with >= 2 Wiener coordinates) 4 lanes to a (chain, block)");
         g4 = c->fwd_lanes == 4;
-    } else if (GW == 4) {
-        size_t wave1 = 0, wave4 = 0;
-        launch_sweep_pipe_g<MD, 1>(c, L, fa, lazy, &wave1);
-        launch_sweep_pipe_g<MD, GW>(c, L, fa, lazy, &wave4);
-        const size_t warps1 = (size_t)((c->M + 31) / 32) * L.nb, warps4 = (size_t)((c->M + 7) / 8) * L.nb;
-        g4 = warps1 * 4 <= wave1 * 2 && warps4 <= wave4; // fewer than half a wave of one-lane warps, and the 4-lane grid still fits one wave
+    } else if (c->sweep_mode == 0 && MD::DW >= 2) {
+        int w2 = 0;
+        launch_fwd_lanes<MD, OP_SWEEP, false, 2>(c, L, fa, &w2);
+        if ((size_t)c->M * L.nb * 2 <= (size_t)w2) return false;
     }
     if (g4) launch_sweep_pipe_g<MD, GW>(c, L, fa, lazy);
     else launch_sweep_pipe_g<MD, 1>(c, L, fa, lazy);
@@ -1094,6 +1100,28 @@ int32_t dmt_get_X_chains(dmt_ctx *ctx, int32_t side, int32_t n_sel, const int32_
 }
 int32_t dmt_get_W_chains(dmt_ctx *ctx, int32_t side, int32_t n_sel, const int32_t *chains, double *W) {
     return guarded(ctx, [&] { get_paths_of(ctx, side, n_sel, chains, W, false); });
+}
+// ll_history / accpt_history (src/block.jl:57-58, src/biblock.jl:47) rows it0..it1 to the host without stalling the sampler: the copy
+// waits (on the copy stream) for everything queued so far on the compute stream, which goes on with the next sweeps
+int32_t dmt_histories_async(dmt_ctx *ctx, int32_t layout, uint32_t it0, uint32_t it1, double *host_ll, uint8_t *host_acc) {
+    return guarded(ctx, [&] {
+        Layout &L = layout_of(ctx, layout);
+        REQUIRE((host_ll || host_acc) && it0 <= it1 && it1 < (uint32_t)L.dev.hist_len, DMT_ERR_ARG, "bad history range");
+        if (!ctx->copy_stream) {
+            CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&ctx->ev_gathered, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming));
+            CK(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
+        }
+        if (!ctx->ev_hist) CK(cudaEventCreateWithFlags(&ctx->ev_hist, cudaEventDisableTiming));
+        const size_t per = (size_t)L.nb * ctx->M, n = (size_t)(it1 - it0 + 1);
+        CK(cudaEventRecord(ctx->ev_hist, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_hist, 0));
+        if (host_ll) // rows are [2][n_blocks][M] (accepted, proposal), contiguous over iterations
+            CK(cudaMemcpyAsync(host_ll, L.d_ll_hist.p + (size_t)it0 * 2 * per, n * 2 * per * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_stream));
+        if (host_acc)
+            CK(cudaMemcpyAsync(host_acc, L.d_acc_hist.p + (size_t)it0 * per, n * per, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    });
 }
 int32_t dmt_snapshot_wait(dmt_ctx *ctx) {
     return guarded(ctx, [&] {

@@ -499,6 +499,43 @@ class PathSaver:
         return [(i, arr) for i, _, arr in self._saved]
 
 
+class HistoryStreamer:
+    """Streams ll_history / accpt_history of a BlockEnsemble to the host in chunks of `every` iterations while the sampler runs
+    (b.ll_history, b°.ll_history src/block.jl:57-58; bb.accpt_history src/biblock.jl:47): call it once per iteration AFTER the
+    iteration's save_ll! / accept step; `collect()` waits and returns (ll [n, 2, nb, M], acc [n, nb, M]) of everything streamed."""
+
+    def __init__(self, be, every=64):
+        self.be, self.every, self._next, self._chunks = be, int(every), 0, []
+
+    def _buffers(self, n):
+        nb, M = self.be.n_blocks, self.be.ctx.M
+        try:
+            import torch
+            a, b = torch.empty((n, 2, nb, M), dtype=torch.float64, pin_memory=True), torch.empty((n, nb, M), dtype=torch.uint8, pin_memory=True)
+            return (a, b), a.numpy(), b.numpy()
+        except Exception:
+            a, b = np.empty((n, 2, nb, M)), np.empty((n, nb, M), dtype=np.uint8)
+            return (a, b), a, b
+
+    def __call__(self, mcmciter, flush=False):
+        """rows self._next .. mcmciter are final; ship them when a chunk is full (or on flush)"""
+        n = mcmciter - self._next + 1
+        if n <= 0 or (n < self.every and not flush):
+            return False
+        keep, ll, acc = self._buffers(n)
+        self.be.ctx.histories_async(self.be.layout, self._next, mcmciter, ll, acc)
+        self._chunks.append((self._next, keep, ll, acc))
+        self._next = mcmciter + 1
+        return True
+
+    def collect(self):
+        self.be.ctx.snapshot_wait()
+        if not self._chunks:
+            nb, M = self.be.n_blocks, self.be.ctx.M
+            return np.empty((0, 2, nb, M)), np.empty((0, nb, M), dtype=bool)
+        return np.concatenate([c[2] for c in self._chunks]), np.concatenate([c[3] for c in self._chunks]).astype(bool)
+
+
 # ---- checkpoint / resume (not in the reference, which keeps its state in Julia objects; SURVEY §5 / §8f item 3) -------------
 def save_state(se, path, layouts=()):
     """Everything needed to continue a run bit-exactly: accepted and proposal X and W (resolved through the parity bits), the

@@ -14,7 +14,7 @@
  *     gives the message.  A numerical path failure is NOT an error: the chain's success flag is 0 and its ll is -Inf
  *     (mirrors src/block.jl:163,181 and src/biblock.jl:81-82).
  *   - all pointers are caller-owned HOST pointers, copied during the call, never retained (Julia-GC safe).  The one
- *     exception is the output buffer of dmt_snapshot_paths_async, which the library writes until dmt_snapshot_wait returns
+ *     exception are the output buffers of dmt_snapshot_paths_async / dmt_histories_async, which the library writes until dmt_snapshot_wait returns
  *     (keep it alive and unmoved until then: GC.@preserve / page-locked memory).
  *   - bulk host arrays are structure-of-arrays with the chain (or parameter-set) index FASTEST:
  *       X[point][dim][chain], W[step][dw][chain], theta[par][pset], B[k][row*d+col][pset], ...
@@ -118,6 +118,12 @@ int32_t dmt_set_start(dmt_ctx *ctx, const double *x0 /* [d][M] */); /* XX[1].x[1
  * dmt_snapshot_wait; a further snapshot may be queued before that (it waits for the staging buffer on the device). */
 int32_t dmt_snapshot_paths_async(dmt_ctx *ctx, int32_t side, int32_t n_sel, const int32_t *chains, double *host_out);
 int32_t dmt_snapshot_wait(dmt_ctx *ctx);
+/* History streaming: rows it0..it1 of a layout's ll_history (host_ll[it][2][n_blocks][M]: accepted, proposal — b.ll_history and
+ * b°.ll_history, src/block.jl:57-58) and accpt_history (host_acc[it][n_blocks][M], src/biblock.jl:47), either may be NULL.  Like the
+ * path snapshots the call returns at once: the copies run on the second stream once everything queued before the call has finished,
+ * and the sampler goes on; read the buffers after dmt_snapshot_wait (page-locked memory keeps the copy asynchronous).  Rows must not be
+ * rewritten (same iteration index) before the wait.  A long run streams its histories in chunks instead of reading them at the end. */
+int32_t dmt_histories_async(dmt_ctx *ctx, int32_t layout, uint32_t it0, uint32_t it1, double *host_ll, uint8_t *host_acc);
 /* init_paths! (src/sampling_unit.jl:83-87): fresh-noise forward_guide! of the whole path into u, retried per chain
  * until success (at most max_tries), then u° = deepcopy(u) (src/sampling_pair.jl:51). Needs the guiding term of a
  * single-terminal-block layout `layout`.  n_failed: chains still failing. */

@@ -373,6 +373,16 @@ DeviceEnsemble(aux_laws, recordings, tts, args=tuple(); device=0, seed=UInt64(0)
 OBS.num_recordings(se::DeviceEnsemble) = se.M
 OBS.num_recordings(be::DBE) = be.se.M
 
+# ---- saving while sampling: thinned paths and history chunks leave on a second stream (include/dmt.h) ----------------------
+# `paths[i ÷ 400] = deepcopy(bb.b.XX)` of the tutorials / reading b.ll_history at the end.  Buffers must stay alive (and should be
+# page-locked) until `snapshot_wait(se)` returns.
+snapshot_paths_async!(out::Array{Float64,3}, se::DeviceEnsemble, recs::AbstractVector{<:Integer}, side::Integer=0) =   # out: (length(recs), d, NP)
+    check(se.ctx, ccall((:dmt_snapshot_paths_async, libdmt), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}, Ptr{Float64}), se.ctx, side, length(recs), Int32.(recs .- 1), out))
+histories_async!(ll::Array{Float64,4}, acc::Array{UInt8,3}, be::DBE, range) =                                            # ll: (M, n_blocks, 2, n), acc: (M, n_blocks, n)
+    check(be.se.ctx, ccall((:dmt_histories_async, libdmt), Int32, (Ptr{Cvoid}, Int32, UInt32, UInt32, Ptr{Float64}, Ptr{UInt8}),
+                           be.se.ctx, be.layout, first(range) - 1, last(range) - 1, ll, acc))
+snapshot_wait(se::DeviceEnsemble) = check(se.ctx, ccall((:dmt_snapshot_wait, libdmt), Int32, (Ptr{Cvoid},), se.ctx))
+
 # ---- BlockCollection / BiBlock views (src/block_collection.jl:17-36, src/biblock.jl:17-62) ---------------------------------
 # `be.recordings[r]` and `.blocks[b]` of the reference.  The numerical calls are batched over all recordings and blocks on the device —
 # call them on the DeviceBlockEnsemble; the views carry what acts on ONE recording / ONE block: reading XX, WW, ll and the histories,

@@ -30,6 +30,7 @@ def test_header_compiles_as_c99(tmp_path):
 
 
 @pytest.mark.gpu
+@pytest.mark.own_lanes
 @pytest.mark.skipif(shutil.which("gcc") is None, reason="no gcc")
 def test_c_program_runs_a_sweep_on_the_device(tmp_path):
     exe = _compile(tmp_path)

@@ -385,3 +385,30 @@ def test_biblock_and_block_collection_views():
     assert bc.accpt_rate((0, nit - 1)) == [b.accpt_rate((0, nit - 1)) for b in bc.blocks]
     assert np.allclose(H.ll_of_accepted(be, 1)[rec], bc.ll_of_accepted(1))
     ctx.close()
+
+
+def test_history_streaming_is_asynchronous_and_ordered():
+    """dmt_histories_async / host.HistoryStreamer: chunks of ll_history / accpt_history leave on the copy stream while later sweeps
+    run; what arrives equals what the synchronous getters return at the end, row by row (ordering: a chunk holds exactly the values
+    the rows had when it was queued, later iterations never leak into it)."""
+    nit = 23
+    prob = configs.make_problem("lv", 50, K=5, dt=0.01, seed=9, rho=0.9)
+    se = H.SamplingEnsemble(prob.model, recordings_of(prob), (prob.n_pts, prob.tt), seed=2, two_sided_laws=False)
+    se.init_paths()
+    be = H.BlockEnsemble(se, [(0, prob.K - 1)], 0.9, nit)
+    H.recompute_guiding_term(be, H.P_only); H.loglikhd(be)
+    hs = H.HistoryStreamer(be, every=5)
+    shipped = 0
+    for i in range(nit):
+        H.draw_proposal_path(be, i); H.accept_reject_proposal_path(be, i)
+        shipped += bool(hs(i))
+    hs(nit - 1, flush=True)
+    ll, acc = hs.collect()
+    assert shipped == 4 and ll.shape == (nit, 2, 1, 50) and acc.shape == (nit, 1, 50)
+    ctx = se.ctx
+    assert np.array_equal(acc, ctx.get_accept_history(be.layout, 0, nit - 1))
+    assert np.array_equal(ll[:, 0], ctx.get_ll_history(be.layout, 0, 0, nit - 1)) and np.array_equal(ll[:, 1], ctx.get_ll_history(be.layout, 1, 0, nit - 1))
+    assert 0.02 < acc.mean() < 0.98
+    with pytest.raises(dmt_b200.DmtError):
+        ctx.histories_async(be.layout, 0, nit, np.empty((nit + 1, 2, 1, 50)), None)        # beyond ll_hist_len
+    ctx.close()
