@@ -222,7 +222,7 @@ class Runner:
         whole = nlay
         ctx.set_blocks(whole, [(0, prob.K - 1)], 0.0)
         ctx.recompute_guiding_term(whole, _lib.P_ONLY)
-        nfail = ctx.init_paths(whole, iter0=1 << 20, max_tries=100)
+        nfail = ctx.init_paths(whole, iter0=1 << 20, max_tries=1000)
         assert nfail == 0, "init_paths left %d failing chains" % nfail
         if not self.blocking:
             ctx.recompute_guiding_term(0, _lib.P_ONLY)

@@ -8,6 +8,7 @@
 #include "tsit5_kernel.cuh"
 
 #include <algorithm>
+#include <type_traits>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -321,6 +322,15 @@ template <class MD, int G> void launch_sweep_pipe_g(dmt_ctx *c, Layout &L, const
 #endif
 // ring depths by state dimension: a stage of the G ring is (d(d+1)/2 + d) KiB, the D ring holds the same again per slot
 template <class MD> struct WsShapeOf { using type = WsShape<DMT_WS_NR, (MD::D <= 3 ? DMT_WS_NSG : MD::D == 4 ? 6 : 3), (MD::D <= 3 ? DMT_WS_NSR : MD::D == 4 ? 3 : 2)>; };
+// the compact shape (two CTAs per SM: at most ~113 KB of shared memory each); the wide states do not fit twice
+#ifndef DMT_WSC_NSG
+#define DMT_WSC_NSG 6
+#endif
+#ifndef DMT_WSC_NSR
+#define DMT_WSC_NSR 2
+#endif
+template <class MD> struct WsCompactOf { using type = WsShape<2, (MD::D <= 3 ? DMT_WSC_NSG : 4), DMT_WSC_NSR, true>; };
+template <class MD> constexpr bool ws_compact_fits() { return sweep_ws_smem<MD, typename WsCompactOf<MD>::type>() <= 113 * 1024; }
 template <class MD, class SH, int MINB> void launch_sweep_ws(dmt_ctx *c, Layout &L, const FwdArgs &fa, bool lazy, size_t *wave_ctas = nullptr) {
     constexpr size_t smem = sweep_ws_smem<MD, SH>();
     static_assert(smem <= 227 * 1024, "the rings of the warp-specialised sweep must fit one SM's shared memory");
@@ -342,7 +352,7 @@ template <class MD, class SH, int MINB> void launch_sweep_ws(dmt_ctx *c, Layout 
     }
     if (wave_ctas) { *wave_ctas = wave[dev][lazy]; return; }
     const dim3 grid((unsigned)((c->M + 31) / 32), L.nb, 1);
-    snprintf(c->last_fwd_kernel, sizeof(c->last_fwd_kernel), "sweep_ws_kernel<%s>", lazy ? "lazy" : "eager");
+    snprintf(c->last_fwd_kernel, sizeof(c->last_fwd_kernel), "sweep_ws_kernel<%s, %s>", SH::COMPACT ? "compact" : "wide", lazy ? "lazy" : "eager");
     if (lazy) ++g_launches, sweep_ws_kernel<MD, true, SH, MINB><<<grid, SH::THREADS, smem, c->stream>>>(c->dev, L.dev, fa);
     else ++g_launches, sweep_ws_kernel<MD, false, SH, MINB><<<grid, SH::THREADS, smem, c->stream>>>(c->dev, L.dev, fa);
 }
@@ -355,15 +365,30 @@ template <class MD> bool launch_sweep_pipe(dmt_ctx *c, Layout &L, const FwdArgs 
         throw DmtError(DMT_ERR_UNSUPPORTED, "pipelined sweep needs one parameter set per chain in chain order, uniform law parity and device RNG");
     if (!eligible || c->sweep_mode == 1 || (c->sweep_mode == 0 && (c->fwd_lanes != 0 || env_off))) return false;
     const bool lazy = c->lazy_W && covers_all_intervals(c, L);
-    {   // the warp-specialised kernel (one CTA per SM, a fixed ~0.5 ms per round of CTAs on C3): forced by mode 3; automatic while the
-        // grid needs at most 2 rounds — beyond that the one-thread-per-(chain, block) kernels win (profiles/r02_tuning.md)
-        size_t wave_ws = 0;
-        launch_sweep_ws<MD, typename WsShapeOf<MD>::type, 1>(c, L, fa, lazy, &wave_ws);
+    {   // the warp-specialised kernel: forced by modes 3 (wide shape, one CTA per SM) and 4 (compact shape, two per SM); automatic while its
+        // grid fits ONE round of the wide shape, else one round of the compact one (profiles/r02_tuning.md: a round costs ~0.5 ms on C3
+        // whatever the ensemble size, so a second round loses to the one-thread-per-(chain, block) kernels)
+        using Wide = typename WsShapeOf<MD>::type;
+        using Compact = typename WsCompactOf<MD>::type;
+        constexpr bool CFITS = ws_compact_fits<MD>();
+        using CompactOrWide = typename std::conditional<CFITS, Compact, Wide>::type; // (never launched when it does not fit)
         const size_t units = (size_t)((c->M + 31) / 32) * L.nb;
+        size_t wave_w = 0, wave_c = 0;
+        launch_sweep_ws<MD, Wide, 1>(c, L, fa, lazy, &wave_w);
+        (void)wave_c;
         static int ws_rounds = -1;
-        if (ws_rounds < 0) { const char *e = getenv("DMT_WS_MAX_ROUNDS"); ws_rounds = e ? atoi(e) : 2; }
-        if (c->sweep_mode == 3 || (c->sweep_mode == 0 && c->fwd_lanes == 0 && wave_ws > 0 && units <= (size_t)ws_rounds * wave_ws)) {
-            launch_sweep_ws<MD, typename WsShapeOf<MD>::type, 1>(c, L, fa, lazy);
+        if (ws_rounds < 0) { const char *e = getenv("DMT_WS_MAX_ROUNDS"); ws_rounds = e ? atoi(e) : 1; }
+        const bool automatic = c->sweep_mode == 0 && c->fwd_lanes == 0;
+        if (c->sweep_mode == 4 && !CFITS) throw DmtError(DMT_ERR_UNSUPPORTED, "the compact warp-specialised sweep does not fit this model's state dimension");
+        if (c->sweep_mode == 3 || (automatic && wave_w > 0 && units <= (size_t)ws_rounds * wave_w)) {
+            launch_sweep_ws<MD, Wide, 1>(c, L, fa, lazy);
+            if (lazy) c->W_stale_layout = L.dev.id;
+            return true;
+        }
+        // (the compact shape is never chosen automatically: one round of it costs 1.03 ms on C3, the same as two lanes per (chain, block)
+        // in the register-tile kernel — 512 / 768 / 896 chains: 1.03 / 1.04 / 1.04 against 1.03 / 1.05 / — ms)
+        if (CFITS && c->sweep_mode == 4) {
+            launch_sweep_ws<MD, CompactOrWide, CFITS ? 2 : 1>(c, L, fa, lazy);
             if (lazy) c->W_stale_layout = L.dev.id;
             return true;
         }
@@ -1468,7 +1493,7 @@ int32_t dmt_get_last_forward_kernel(dmt_ctx *ctx, char *buf, int32_t len) {
 }
 int32_t dmt_set_sweep_mode(dmt_ctx *ctx, int32_t mode) {
     return guarded(ctx, [&] {
-        if (mode < 0 || mode > 3) throw DmtError(DMT_ERR_ARG, "mode must be 0 (auto), 1 (register-tile kernel), 2 (software-pipelined kernel) or 3 (warp-specialised kernel)");
+        if (mode < 0 || mode > 4) throw DmtError(DMT_ERR_ARG, "mode must be 0 (auto), 1 (register-tile kernel), 2 (software-pipelined kernel), 3 or 4 (warp-specialised kernel, wide / compact shape)");
         ctx->sweep_mode = mode;
     });
 }

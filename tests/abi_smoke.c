@@ -101,10 +101,14 @@ int main(int argc, char **argv) {
         if (!isfinite(ll[i])) bad++;
     }
     for (int i = 0; i < K * NPT * 3 * M; i++) if (!isfinite(X[i])) bad++;
-    /* every interval starts where the previous one ended (XX[k].x[1] == XX[k-1].x[end]) */
+    /* every interval starts where the previous one ended (XX[k].x[1] == XX[k-1].x[end]): exactly inside a block; where two blocks meet
+     * (k == 3) the left block's proposal was steered towards the frozen end point and ends within one Euler-Maruyama step's noise
+     * (sigma sqrt(dt) ~ 0.2 on this program's crude uniform grid; the reference's tau-transformed grids make that step tiny) of it */
     for (int k = 1; k < K; k++)
-        for (int j = 0; j < 3 * M; j++)
-            if (X[(size_t)(k * NPT) * 3 * M + j] != X[(size_t)(k * NPT - 1) * 3 * M + j]) bad++;
+        for (int j = 0; j < 3 * M; j++) {
+            const double a = X[(size_t)(k * NPT) * 3 * M + j], b = X[(size_t)(k * NPT - 1) * 3 * M + j];
+            if (k == i0[1] ? fabs(a - b) > 1.0 : a != b) bad++;
+        }
     printf("abi_smoke: %d of %d (block, chain) proposals accepted, ll[0] = %.6f, bad = %d\n", n_acc, NB * M, ll[0], bad);
     CHECK(p_dmt_destroy(ctx));
     return (bad == 0 && n_acc > 0 && n_acc < NB * M) ? 0 : 5;

@@ -32,19 +32,24 @@ def start(prob, seed=31, **kw):
 
 @pytest.mark.parametrize("name", NAMES)
 @pytest.mark.parametrize("M", [41, 64, 7])
-@pytest.mark.parametrize("lanes", [1, 4, "ws"])
+@pytest.mark.parametrize("lanes", [1, 4, "ws", "ws_compact"])
 def test_pipelined_sweep_equals_register_tile_sweep(name, M, lanes):
     """same inputs, same random stream, same arithmetic: equal up to FP64 rounding (different FMA contraction), decisions equal;
     with one lane per (chain, block), with four (the lanes split the generator calls), and with the warp-specialised kernel
     (csrc/sweep_ws_kernel.cuh: generator, inverse solve, proposal recursion and proposal likelihood on different warps, coupled by
-    shared-memory rings)"""
+    shared-memory rings) in both of its shapes (16 warps, one CTA per SM; 8 warps, two per SM)"""
     prob = problem(name, M)
     a, b = start(prob), start(prob)
     a.set_sweep_mode(1)
     if isinstance(lanes, str):
-        b.set_sweep_mode(3)
+        b.set_sweep_mode(3 if lanes == "ws" else 4)
     else:
         b.set_sweep_mode(2); b.set_fwd_lanes(lanes)
+    if lanes == "ws_compact" and prob.d > 4:
+        with pytest.raises(dmt_b200.DmtError):      # two CTAs of the wide state's rings do not fit one SM: the shape is not offered
+            b.blocking_sweep(0, 0)
+        a.close(); b.close()
+        return
     if lanes == 4 and prob.dw < 2:
         with pytest.raises(dmt_b200.DmtError):      # one Wiener coordinate: nothing to split, the wide mapping is not built
             b.blocking_sweep(0, 0)
@@ -81,14 +86,14 @@ def test_pipelined_sweep_refuses_what_it_cannot_do():
     ctx.set_sweep_mode(0)
     ctx.find_W_loglikhd_draw(0, 1)                  # automatic: falls back to the register-tile kernel (another CUDA kernel, not a CPU path)
     with pytest.raises(dmt_b200.DmtError):
-        ctx.set_sweep_mode(4)
+        ctx.set_sweep_mode(5)
     with pytest.raises(dmt_b200.DmtError):
         ctx.set_sweep_mode(3); ctx.find_W_loglikhd_draw(0, 1)
     ctx.close()
 
 
 @pytest.mark.parametrize("name", ["lorenz", "fhn", "prok"])
-@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("mode", [1, 2, 3, 4])
 def test_lazy_noise_changes_nothing_but_the_moment_W_is_computed(name, mode):
     """dmt_set_lazy_noise: the sweep stops storing W_acc / W°; paths, log-likelihoods and decisions are unchanged, and the accepted
     noise read back later is K5 of the accepted path under the law swept last — what find_W_for_X! returns."""
