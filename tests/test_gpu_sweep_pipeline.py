@@ -45,7 +45,7 @@ def test_pipelined_sweep_equals_register_tile_sweep(name, M, lanes):
         b.set_sweep_mode(3 if lanes == "ws" else 4)
     else:
         b.set_sweep_mode(2); b.set_fwd_lanes(lanes)
-    if lanes == "ws_compact" and prob.d > 4:
+    if lanes == "ws_compact" and prob.d > 3:
         with pytest.raises(dmt_b200.DmtError):      # two CTAs of the wide state's rings do not fit one SM: the shape is not offered
             b.blocking_sweep(0, 0)
         a.close(); b.close()
@@ -98,6 +98,8 @@ def test_lazy_noise_changes_nothing_but_the_moment_W_is_computed(name, mode):
     """dmt_set_lazy_noise: the sweep stops storing W_acc / W°; paths, log-likelihoods and decisions are unchanged, and the accepted
     noise read back later is K5 of the accepted path under the law swept last — what find_W_for_X! returns."""
     prob = problem(name, 45)
+    if mode == 4 and prob.d > 3:
+        pytest.skip("the compact shape is offered for state dimensions <= 3 only (its rings must fit an SM twice)")
     a, b = start(prob), start(prob)
     a.set_sweep_mode(2); b.set_sweep_mode(mode)
     b.set_lazy_noise(True)
