@@ -8,6 +8,7 @@
 #include "tsit5_kernel.cuh"
 
 #include <algorithm>
+#include <nvtx3/nvToolsExt.h> // header-only: ranges are emitted when DMT_NVTX=1 and a profiler is attached
 #include <type_traits>
 #include <cmath>
 #include <cstdio>
@@ -696,6 +697,19 @@ void fill_stats(dmt_ctx *c, Layout &L, double *host_out /* [2+3nb] */) {
     }
 }
 
+// NVTX range around a C-ABI operation (nsys / ncu --nvtx): off unless DMT_NVTX=1, so the hot loop pays one predictable branch
+struct NvtxRange {
+    bool on;
+    explicit NvtxRange(const char *name) {
+        static int enabled = -1;
+        if (enabled < 0) { const char *e = getenv("DMT_NVTX"); enabled = (e && e[0] == '1') ? 1 : 0; }
+        on = enabled == 1;
+        if (on) nvtxRangePushA(name);
+    }
+    ~NvtxRange() { if (on) nvtxRangePop(); }
+};
+#define DMT_RANGE(name) NvtxRange nvtx_range_(name)
+
 template <class F> int32_t guarded(dmt_ctx *ctx, F &&f) {
     if (!ctx) return DMT_ERR_ARG;
     try {
@@ -1155,6 +1169,7 @@ int32_t dmt_snapshot_wait(dmt_ctx *ctx) {
 }
 
 int32_t dmt_init_paths(dmt_ctx *ctx, int32_t layout, uint32_t iter0, int32_t max_tries, int32_t *n_failed) {
+    DMT_RANGE("dmt_init_paths");
     return guarded(ctx, [&] {
         Layout &L = layout_of(ctx, layout);
         REQUIRE(L.nb == 1 && L.last[0] && L.i0[0] == 0 && L.i1[0] == ctx->K - 1, DMT_ERR_ARG,
@@ -1181,6 +1196,7 @@ int32_t dmt_init_paths(dmt_ctx *ctx, int32_t layout, uint32_t iter0, int32_t max
 
 // ---------------------------------------------------------------------------------------------------------------- hot path
 int32_t dmt_set_artificial_obs(dmt_ctx *ctx, int32_t layout) {
+    DMT_RANGE("dmt_set_artificial_obs");
     return guarded(ctx, [&] {
         Layout &L = layout_of(ctx, layout);
         ++g_launches, set_artificial_obs_kernel<<<chain_grid(ctx, L.nb, 128), 128, 0, ctx->stream>>>(ctx->dev, L.dev, ctx->D);
@@ -1189,6 +1205,7 @@ int32_t dmt_set_artificial_obs(dmt_ctx *ctx, int32_t layout) {
 }
 
 int32_t dmt_recompute_guiding_term(dmt_ctx *ctx, int32_t layout, int32_t which) {
+    DMT_RANGE("dmt_recompute_guiding_term");
     return guarded(ctx, [&] {
         Layout &L = layout_of(ctx, layout);
         REQUIRE(which >= 1 && which <= 3, DMT_ERR_ARG, "which must be DMT_P_ONLY, DMT_PO_ONLY or DMT_P_BOTH");
@@ -1207,6 +1224,7 @@ int32_t dmt_find_W_for_X(dmt_ctx *ctx, int32_t layout) {
     return guarded(ctx, [&] { launch_fwd<OP_INVSOLVE>(ctx, layout_of(ctx, layout), FwdArgs{0, 0, 0, 0, nullptr}); });
 }
 int32_t dmt_loglikhd(dmt_ctx *ctx, int32_t layout, int32_t side, int32_t skip) {
+    DMT_RANGE("dmt_loglikhd");
     return guarded(ctx, [&] {
         check_law_side(ctx, side);
         REQUIRE(skip >= 0, DMT_ERR_ARG, "skip must be >= 0");
@@ -1218,6 +1236,7 @@ int32_t dmt_find_W_and_loglikhd(dmt_ctx *ctx, int32_t layout) {
 }
 
 int32_t dmt_draw_proposal_path(dmt_ctx *ctx, int32_t layout, uint32_t iter, const double *Z) {
+    DMT_RANGE("dmt_draw_proposal_path");
     return guarded(ctx, [&] {
         Layout &L = layout_of(ctx, layout);
         FwdArgs fa{iter, 0, 0, 0, nullptr};
@@ -1233,6 +1252,7 @@ int32_t dmt_draw_proposal_path(dmt_ctx *ctx, int32_t layout, uint32_t iter, cons
 }
 
 int32_t dmt_find_W_loglikhd_draw(dmt_ctx *ctx, int32_t layout, uint32_t iter, const double *Z) {
+    DMT_RANGE("dmt_find_W_loglikhd_draw");
     return guarded(ctx, [&] {
         Layout &L = layout_of(ctx, layout);
         FwdArgs fa{iter, 0, 0, 0, nullptr};
@@ -1248,6 +1268,7 @@ int32_t dmt_find_W_loglikhd_draw(dmt_ctx *ctx, int32_t layout, uint32_t iter, co
 }
 
 int32_t dmt_blocking_sweep(dmt_ctx *ctx, int32_t layout, uint32_t iter) {
+    DMT_RANGE("dmt_blocking_sweep");
     return guarded(ctx, [&] {
         Layout &L = layout_of(ctx, layout);
         ++g_launches, set_artificial_obs_kernel<<<chain_grid(ctx, L.nb, 128), 128, 0, ctx->stream>>>(ctx->dev, L.dev, ctx->D); // GP.set_obs!(be)
@@ -1263,6 +1284,7 @@ int32_t dmt_blocking_sweep(dmt_ctx *ctx, int32_t layout, uint32_t iter) {
 }
 
 int32_t dmt_recompute_path(dmt_ctx *ctx, int32_t layout, int32_t law_side, int32_t noise_side, int32_t skip) {
+    DMT_RANGE("dmt_recompute_path");
     return guarded(ctx, [&] {
         check_law_side(ctx, law_side); check_side(ctx, noise_side);
         REQUIRE(skip >= 0, DMT_ERR_ARG, "skip must be >= 0");
@@ -1271,6 +1293,7 @@ int32_t dmt_recompute_path(dmt_ctx *ctx, int32_t layout, int32_t law_side, int32
 }
 
 int32_t dmt_set_proposal_law(dmt_ctx *ctx, int32_t layout, int32_t critical_change, int32_t skip) {
+    DMT_RANGE("dmt_set_proposal_law");
     return guarded(ctx, [&] {
         check_law_side(ctx, 1);
         Layout &L = layout_of(ctx, layout);
@@ -1280,6 +1303,7 @@ int32_t dmt_set_proposal_law(dmt_ctx *ctx, int32_t layout, int32_t critical_chan
 }
 
 int32_t dmt_accept_reject_path(dmt_ctx *ctx, int32_t layout, uint32_t iter, const double *E) {
+    DMT_RANGE("dmt_accept_reject_path");
     return guarded(ctx, [&] {
         Layout &L = layout_of(ctx, layout);
         const double *dE = nullptr;
@@ -1641,6 +1665,7 @@ int32_t dmt_p2p_disable(dmt_ctx *ctx) {
     return guarded(ctx, [&] { ctx->p2p_ready = false; });
 }
 int32_t dmt_allreduce_stats(dmt_ctx *ctx, int32_t layout, double *out) {
+    DMT_RANGE("dmt_allreduce_stats");
     return guarded(ctx, [&] {
         Layout &L = layout_of(ctx, layout);
         REQUIRE(out, DMT_ERR_ARG, "null");

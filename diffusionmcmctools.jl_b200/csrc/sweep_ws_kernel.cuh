@@ -372,7 +372,9 @@ __global__ void __launch_bounds__(SH::THREADS, MINB) sweep_ws_kernel(const DevCt
         WsCursor u = cur_init();
         int k_loaded = -1, nst = 0;
         unsigned bad = 0u; // bit p: this lane's (chain, step) of pass p has failed
+        WS_TR_DECL
         for (int j = 0; j < T; j++) {
+            WS_TR(j, 0)
             if (u.k != k_loaded) {
                 stage_law(u.k);
                 nst = cx.nsteps[u.k];
@@ -383,6 +385,7 @@ __global__ void __launch_bounds__(SH::THREADS, MINB) sweep_ws_kernel(const DevCt
             const double *st = gring + (size_t)(j % NSG) * STAGE;
             const double dt = st[NG * 128 + s];
             wait_full(full_x, j, NSX);
+            WS_TR(j, 1)
             const double *xs0 = xring + (size_t)(j % NSX) * XS;
 #pragma unroll 1
             for (int p = 0; p < 4; p++) {
@@ -435,8 +438,10 @@ __global__ void __launch_bounds__(SH::THREADS, MINB) sweep_ws_kernel(const DevCt
             signal(empty_x, j, NSX);
             signal(empty_g, j, NSG);
             issue(); // tile j + NSG into the stage just released
+            WS_TR(j, 2)
             cur_next(u);
         }
+        WS_TR_DUMP("L")
 #pragma unroll
         for (int p = 0; p < 4; p++) {
             double v = lacc[p * 32 + lane];
