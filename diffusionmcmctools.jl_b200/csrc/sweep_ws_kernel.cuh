@@ -38,7 +38,22 @@
 #include <cstdio>
 #endif
 
+#ifndef DMT_WSC_LUNROLL // compact shape: passes of the L warp interleaved per loop trip (instruction-level parallelism for a lone warp)
+#define DMT_WSC_LUNROLL 1
+#endif
+#ifndef DMT_WSC_RUNROLL // compact shape: generator calls interleaved per loop trip
+#define DMT_WSC_RUNROLL 1
+#endif
+
+#ifndef DMT_WSC_LUNROLL // compact shape: passes of the L warp interleaved per loop trip (instruction-level parallelism for a lone warp)
+#define DMT_WSC_LUNROLL 1
+#endif
+#ifndef DMT_WSC_RUNROLL // compact shape: generator calls interleaved per loop trip
+#define DMT_WSC_RUNROLL 1
+#endif
+
 namespace dmt {
+constexpr int WSC_LUNROLL = DMT_WSC_LUNROLL, WSC_RUNROLL = DMT_WSC_RUNROLL;
 
 // Two shapes.  WIDE (16 warps: P, T, up to 6 R, 4 A, 4 L): the shortest time per tile, but 16 warps x 128 registers fill an SM's
 // register file — one CTA per SM.  COMPACT (8 warps: P, 2 R, 4 A and ONE warp that does the four L passes of a tile and issues the TMA
@@ -296,7 +311,7 @@ __global__ void __launch_bounds__(SH::THREADS, MINB) sweep_ws_kernel(const DevCt
             wait_empty(empty_z, j, NSZ);
             WS_TR(j, 1)
             double *zo = zring + (size_t)(j % NSZ) * ZS + lane;
-#pragma unroll 1
+#pragma unroll(SH::COMPACT ? WSC_RUNROLL : 1)
             for (int call = r; call < 2 * DW; call += NR) {
                 u32x4 ctr = {cx.chain_offset + (uint32_t)c, (uint32_t)(u.t0 + u.q), fa.iter, ctr_word3(STREAM_PCN, (uint32_t)ly.id, (uint32_t)call)};
                 double z0, z1;
@@ -387,7 +402,7 @@ __global__ void __launch_bounds__(SH::THREADS, MINB) sweep_ws_kernel(const DevCt
             wait_full(full_x, j, NSX);
             WS_TR(j, 1)
             const double *xs0 = xring + (size_t)(j % NSX) * XS;
-#pragma unroll 1
+#pragma unroll WSC_LUNROLL
             for (int p = 0; p < 4; p++) {
                 const int cl = 8 * p + (lane >> 2);
                 const double *sg = st + p * 32 + lane;
