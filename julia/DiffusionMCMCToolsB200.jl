@@ -195,12 +195,19 @@ function set_proposal_law!(be::DBE, θ°, pnames::Vector{Pair{Int,Int}}, critica
         th[:, j] .= θ°[i]
     end
     se.theta° = th
-    check(se.ctx, ccall((:dmt_equalize_laws, libdmt), Int32, (Ptr{Cvoid}, Int32, Int32, Int32), se.ctx, 3, 0, se.K - 1))
+    # GP.equalize_obs_params! / equalize_law_params! FIRST (src/biblock.jl:362-363): b° := b for every record; when b° had to be changed its
+    # guiding term belongs to other parameters, and the update is escalated to a critical one exactly like the reference does
+    changed = Ref{Int32}(0)
+    check(se.ctx, ccall((:dmt_equalize_laws, libdmt), Int32, (Ptr{Cvoid}, Int32, Int32, Int32, Ref{Int32}), se.ctx, 3, 0, se.K - 1, changed))
+    critical_change = critical_change || changed[] != 0
     check(se.ctx, ccall((:dmt_set_params, libdmt), Int32, (Ptr{Cvoid}, Int32, Int32, Int32, Int32, Ptr{Float64}), se.ctx, 1, 3, 0, se.K - 1, th))
-    if critical_change
-        for store in (0, 1)
+    # Auxiliary laws evaluated on the HOST (DeviceEnsemble built from a SamplingEnsemble): a critical update changes them, and only the
+    # reference's own objects know how — update those (DD.set_parameters! on the host proposal laws) and call upload_aux!(se, se_host, 1)
+    # BEFORE this function; nothing to do here.  Device-linearised auxiliary laws (raw-array constructor) are re-linearised below.
+    if critical_change && !isempty(se.xbar)
+        for store in (0, 1)   # the linearisation points are already on the device: NULL re-linearises there with the new θ°
             check(se.ctx, ccall((:dmt_set_aux_linearised, libdmt), Int32, (Ptr{Cvoid}, Int32, Int32, Int32, Int32, Ptr{Float64}),
-                                se.ctx, 1, store, 0, se.K - 1, se.xbar))
+                                se.ctx, 1, store, 0, se.K - 1, C_NULL))
         end
     end
     check(se.ctx, ccall((:dmt_set_proposal_law, libdmt), Int32, (Ptr{Cvoid}, Int32, Int32, Int32), se.ctx, be.layout, critical_change, skip))
@@ -367,6 +374,31 @@ function DeviceEnsemble(se_host::SamplingEnsemble; device=0, seed=UInt64(0), two
     end
     se
 end
+"""
+    upload_aux!(se, se_host, side; proposal=(side == 1))
+
+Re-evaluate `(B, β, σ̃σ̃')` of the host ensemble's CURRENT auxiliary laws (`u` or `u°`, both stores) with the reference's own code and upload
+them to law side `side` — what a critical parameter update needs when the auxiliary laws are host-evaluated.
+"""
+function upload_aux!(se::DeviceEnsemble, se_host::SamplingEnsemble, side::Integer; proposal::Bool=(side == 1))
+    recs = se_host.recordings; M, K, d = se.M, se.K, se.d
+    for (store, field) in ((0, :PP), (1, :PPb))
+        B = Array{Float64,3}(undef, M, d * d, K); β = Array{Float64,3}(undef, M, d, K); a = Array{Float64,3}(undef, M, d * d, K)
+        for r in 1:M, k in 1:K
+            u = proposal ? recs[r].u° : recs[r].u
+            P̃ = getfield(u, field)[k].P_aux; t = se.tt[_pt0(se)[k] + 1]
+            Bm = DD.B(t, P̃); βv = DD.β(t, P̃); σm = DD.σ(t, P̃); am = σm * σm'
+            for i in 1:d, j in 1:d
+                B[r, (i - 1) * d + j, k] = Bm[i, j]; a[r, (i - 1) * d + j, k] = am[i, j]
+            end
+            for i in 1:d
+                β[r, i, k] = βv[i]
+            end
+        end
+        check(se.ctx, ccall((:dmt_set_aux, libdmt), Int32, (Ptr{Cvoid}, Int32, Int32, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                            se.ctx, side, store, 0, K - 1, B, β, a))
+    end
+end
 DeviceEnsemble(aux_laws, recordings, tts, args=tuple(); device=0, seed=UInt64(0), two_sided_laws=true, max_layouts=8, chain_offset=0, kwargs...) =
     DeviceEnsemble(SamplingEnsemble(aux_laws, recordings, tts, args; kwargs...); device=device, seed=seed, two_sided_laws=two_sided_laws,
                    max_layouts=max_layouts, chain_offset=chain_offset, artificial_noise=get(kwargs, :artificial_noise, 1e-11))
@@ -441,7 +473,7 @@ accpt_rate(bc::DeviceBlockCollection, range) = [accpt_rate(bb, range) for bb in 
 ll_of_accepted(bb::DeviceBiBlock, i::Integer) = ll_of_accepted(bb.be, i)[bb.rec, bb.blk]                          # src/biblock.jl:222-225
 ll_of_accepted(bc::DeviceBlockCollection, i::Integer) = ll_of_accepted(bc.be, i)[bc.rec, :]                       # src/block_collection.jl:172
 
-export DeviceEnsemble, DeviceBlockEnsemble, DeviceBlockCollection, DeviceBiBlock, get_paths, get_X, get_W, trajectories,
+export DeviceEnsemble, DeviceBlockEnsemble, DeviceBlockCollection, DeviceBiBlock, upload_aux!, get_paths, get_X, get_W, trajectories,
     wiener_trajectories, pack_paths, pack_noise, recordings, blocks, blocking_sweep!, enable_guiding_cache!
 
 end # module
