@@ -178,3 +178,58 @@ def test_other_baseline_configs_at_full_size(cfg, orc, olib):
         assert acc.mean() < 0.98 and (cfg == "c5" or acc.mean() > 0.02)   # (C5's 50,000-step paths accept rarely at rho = 0.9)
         assert rel_err(ctx.get_X_chains(chains, 0), ora.X(0), tag=tag + "X") < 1e-10
     ctx.close()
+
+
+# ---- the configuration bench.py measures: lazy noise + guiding cache, at the per-GPU sizes of the 1 / 8 / 16-GPU splits ---------------
+@pytest.mark.parametrize("chains,lo,kernel", [(4096, 0, "sweep_pipe_kernel<lanes=1, lazy>"),            # 1 GPU
+                                              (512, 1536, "fwd_kernel<op=6, lanes=2, lazy>"),           # rank 3 of 8
+                                              (256, 3840, "sweep_ws_kernel<wide, lazy>")])              # rank 15 of 16: one round of CTAs
+def test_bench_configuration_slice_replay(chains, lo, kernel, orc, olib):
+    """C3 exactly as bench.py runs it (lazy noise, guiding cache, automatic kernel choice) on the slice of the 4096-chain ensemble a rank of
+    an N-GPU job holds: three sweeps per layout with accept steps; three chains of the slice — global Philox counters — are replayed call by
+    call on the oracle.  Also pins WHICH kernel the automatic choice takes at each size, so all three fused-pass kernels meet the oracle at
+    BASELINE scale."""
+    prob = configs.named_config("c3", M=chains, seed=123, chain_offset=lo)          # (the synthetic data of a rank, as bench.py draws them)
+    ctx = make_ctx(prob, seed=123, n_layouts=3, chain_offset=lo)
+    ctx.set_blocks(2, [(0, prob.K - 1)], 0.0)
+    ctx.recompute_guiding_term(2, _lib.P_ONLY)
+    assert ctx.init_paths(2, 0, 50) == 0
+    ctx.set_lazy_noise(True)
+    for lay in (0, 1):
+        ctx.enable_guiding_cache(lay)
+    sel = [0, chains // 2 + 1, chains - 1]
+    sub = copy.copy(prob)
+    sub.M = sub.P = len(sel)
+    sub.v, sub.xbar, sub.x0 = prob.v[:, :, sel].copy(), prob.xbar[:, :, sel].copy(), prob.x0[:, sel].copy()
+    oras = [OracleEnsemble(orc, olib, _one(sub, i), seed=123, chain_offset=lo + c) for i, c in enumerate(sel)]
+    X, W = ctx.get_X(0)[:, :, sel], ctx.get_W(0)[:, :, sel]
+    for i, ora in enumerate(oras):
+        for s in (0, 1):
+            ora.set_X(s, np.ascontiguousarray(X[:, :, i:i + 1])); ora.set_W(s, np.ascontiguousarray(W[:, :, i:i + 1]))
+    n_acc = 0
+    for it in range(3):
+        for lay in (0, 1):
+            ctx.blocking_sweep(lay, it)
+            assert ctx.last_forward_kernel() == kernel
+            ctx.accept_reject_path(lay, it)
+            acc = ctx.get_last_accept(lay)[:, sel]
+            Xd, lld, llod = ctx.get_X(0)[:, :, sel], ctx.get_ll(lay, 0)[:, sel], ctx.get_ll(lay, 1)[:, sel]
+            for i, ora in enumerate(oras):
+                ora.set_artificial_obs(lay); ora.recompute_guiding_term(lay); ora.find_W_for_X(lay); ora.loglikhd(lay); ora.draw(lay, it)
+                ll_o, llo_o = ora.ll(lay, 0)[:, 0].copy(), ora.ll(lay, 1)[:, 0].copy()
+                acc_o, _ = ora.accept(lay, it, layout_id=lay)
+                assert np.array_equal(acc[:, i], acc_o[:, 0]), (it, lay, i)
+                # after the accept step ll[side] have been swapped where accepted: compare the pre-accept values through the swap
+                pre_ll = np.where(acc[:, i], llod[:, i], lld[:, i]); pre_llo = np.where(acc[:, i], lld[:, i], llod[:, i])
+                assert rel_err(pre_ll, ll_o) < 1e-9 and rel_err(pre_llo[np.isfinite(llo_o)], llo_o[np.isfinite(llo_o)]) < 1e-9
+                assert rel_err(Xd[:, :, i:i + 1], ora.X(0)) < 1e-9
+            n_acc += int(acc.sum())
+    assert n_acc > 0
+    ctx.close()
+
+
+def _one(sub, i):
+    s = copy.copy(sub)
+    s.M = s.P = 1
+    s.v, s.xbar, s.x0 = sub.v[:, :, i:i + 1].copy(), sub.xbar[:, :, i:i + 1].copy(), sub.x0[:, i:i + 1].copy()
+    return s
