@@ -172,23 +172,27 @@ def make_problem(name, M, P=None, K=None, obs_dt=None, dt=None, seed=0, layouts=
     h = dt / sim_sub
     nsub = int(round(obs_dt / h))
     gens = [np.random.default_rng([seed, chain_offset + p]) for p in range(P)] if P <= 64 else None
-    big = np.random.default_rng([seed, 1_000_003, chain_offset])
+    # (large ensembles: one generator per observation interval, keyed by the interval, filled chain-major up to column chain_offset + P
+    # with the shard's columns kept — so a rank of a sharded run sees exactly its slice of the unsharded ensemble's data)
+    PT = chain_offset + P
     x = x0p.copy()
     v = np.empty((K, m, P))
     xbar = np.empty((K, d, P))
     Lc = np.linalg.cholesky(Sigma)
     nw_sim = 8 if model == PROK else dw
     for k in range(K):
-        for _ in range(nsub):
+        if gens is None:
+            dW_k = np.random.default_rng([seed, 1_000_003, k]).normal(size=(PT, nsub, nw_sim))[chain_offset:] * np.sqrt(h)
+        for jsub in range(nsub):
             if gens is not None:
                 dWn = np.stack([g.normal(size=nw_sim) for g in gens], axis=1) * np.sqrt(h)
             else:
-                dWn = big.normal(size=(nw_sim, P)) * np.sqrt(h)
+                dWn = dW_k[:, jsub, :].T
             x = clamp(model, th, x + drift(model, th, x) * h + noise(model, th, x, dWn))
         if gens is not None:
             eta = np.stack([g.normal(size=m) for g in gens], axis=1)
         else:
-            eta = big.normal(size=(m, P))
+            eta = np.random.default_rng([seed, 1_000_004, k]).normal(size=(PT, m))[chain_offset:].T
         v[k] = L @ x + Lc @ eta
         if model in (LV, PROK):  # noisy observations of a positive state: keep them inside the law's domain, otherwise the guided
             v[k] = clamp(model, th, v[k]) if m == d else v[k]   # proposal is pulled across the boundary and never succeeds

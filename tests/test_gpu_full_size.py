@@ -189,7 +189,10 @@ def test_bench_configuration_slice_replay(chains, lo, kernel, orc, olib):
     an N-GPU job holds: three sweeps per layout with accept steps; three chains of the slice — global Philox counters — are replayed call by
     call on the oracle.  Also pins WHICH kernel the automatic choice takes at each size, so all three fused-pass kernels meet the oracle at
     BASELINE scale."""
-    prob = configs.named_config("c3", M=chains, seed=123, chain_offset=lo)          # (the synthetic data of a rank, as bench.py draws them)
+    prob = configs.named_config("c3", M=chains, seed=123, chain_offset=lo)          # the rank's slice of the ensemble's synthetic data
+    if chains == 512:                                                               # (checked once: a shard IS a slice of the unsharded data)
+        full = configs.named_config("c3", seed=123)
+        assert np.array_equal(prob.v, full.v[:, :, lo:lo + chains]) and np.array_equal(prob.x0, full.x0[:, lo:lo + chains])
     ctx = make_ctx(prob, seed=123, n_layouts=3, chain_offset=lo)
     ctx.set_blocks(2, [(0, prob.K - 1)], 0.0)
     ctx.recompute_guiding_term(2, _lib.P_ONLY)
