@@ -183,6 +183,7 @@ struct dmt_ctx {
     int W_stale_layout = -1; // >= 0: W_acc is not materialised; K5 over this layout rebuilds it (ensure_W)
     int G_owner = -1;        // layout whose K1 wrote the shared accepted-law store last (-1: unknown / laws changed)
     bool parP_mixed = false; // a masked swap_PP! made the law parity chain-dependent
+    bool aux_all_linearised = true; // every auxiliary law so far came from dmt_set_aux_linearised: B has the Jacobian's sparsity (JacMask)
 
     double *scratch(size_t n) {
         if (d_scratch.n < n) d_scratch.alloc(n, false);
@@ -470,7 +471,11 @@ template <class MD> void launch_bwd_model(dmt_ctx *c, Layout &L, const BwdArgs &
     if (coop_ok && c->bwd_mode != 1 && !getenv("DMT_NO_COOP_K1")) {
         // wide state, no exact-observation interval: D lanes per parameter set (kernels.cuh, bwd_coop_kernel)
         constexpr int per_cta = 4 * (32 / MD::D);
-        ++g_launches, bwd_coop_kernel<MD><<<dim3((c->P + per_cta - 1) / per_cta, L.nb, nz), 128, 0, c->stream>>>(c->dev, L.dev, ba);
+        const dim3 grid((c->P + per_cta - 1) / per_cta, L.nb, nz);
+        if (JacMask<MD>::SPARSE && c->aux_all_linearised && !getenv("DMT_K1_DENSE"))
+            ++g_launches, bwd_coop_kernel<MD, JacMask<MD>::SPARSE><<<grid, 128, 0, c->stream>>>(c->dev, L.dev, ba);
+        else
+            ++g_launches, bwd_coop_kernel<MD, false><<<grid, 128, 0, c->stream>>>(c->dev, L.dev, ba);
     } else {
         ++g_launches, bwd_kernel<MD><<<pset_grid(c, L.nb, BWD_TPB, nz), BWD_TPB, 0, c->stream>>>(c->dev, L.dev, ba);
     }
@@ -520,10 +525,9 @@ void invalidate_caches(dmt_ctx *c) { // every caller is about to change the acce
 }
 void cache_apply(dmt_ctx *c, Layout &L) { // the per-sweep K1: F = F0 + Psi v ; c = c0 + q.v + v'Qv/2
     L.F_stale = false;
-    const dim3 g0((c->P + 127) / 128, c->NT), g1((c->P + 127) / 128, std::max(c->NTb, 1));
+    const dim3 g((c->P + 127) / 128, c->K, c->NTb > 0 ? 2 : 1);
     DMT_D_SWITCH(c->D,
-                 ++g_launches, cache_apply_kernel<DD><<<g0, 128, 0, c->stream>>>(c->dev, L.dev, 0, c->d_k_of_tile.p);
-                 if (c->NTb > 0) ++g_launches, cache_apply_kernel<DD><<<g1, 128, 0, c->stream>>>(c->dev, L.dev, 1, c->d_k_of_ppbtile.p);
+                 ++g_launches, cache_apply_kernel<DD><<<g, 128, 0, c->stream>>>(c->dev, L.dev);
                  ++g_launches, cache_apply_c_kernel<DD><<<pset_grid(c, L.nb, 128), 128, 0, c->stream>>>(c->dev, L.dev));
     CK(cudaGetLastError());
 }
@@ -922,6 +926,7 @@ int32_t dmt_set_aux(dmt_ctx *ctx, int32_t side, int32_t store, int32_t k0, int32
         if (side == 0) { ensure_W(ctx); invalidate_caches(ctx); } // the accepted laws change: cached guiding terms are stale
         REQUIRE(store == 0 || store == 1, DMT_ERR_ARG, "store must be 0 (PP) or 1 (PPb)");
         REQUIRE(B && beta && atil, DMT_ERR_ARG, "null aux array");
+        ctx->aux_all_linearised = false; // a host-evaluated B may be dense: the backward filter stops skipping the Jacobian's structural zeros
         const int D = ctx->D, NH = ctx->NH, nk = k1 - k0 + 1;
         const size_t P = ctx->P;
         double *r0 = ctx->d_aux[0][store].p, *r1 = ctx->d_aux[1][store].p;

@@ -537,7 +537,8 @@ __global__ void __launch_bounds__(BWD_TPB, DMT_BWD_MINB) bwd_kernel(const DevCtx
 //     (HC)_{rj} = sum_k H_rk C_kj          and, by symmetry of H,          (HC)_{jr} = sum_k H_kj C_kr
 // so no transpose exchange is needed.  32/D psets per warp, 32x more threads, same arithmetic per component as bwd_kernel
 // (results agree to FP64 rounding).  Terminal blocks of diagonal-a models only (what C5 needs); others use bwd_kernel.
-template <class MD>
+// SPARSE: B carries the structural zeros of the model's Jacobian (JacMask): the product skips them at compile time.
+template <class MD, bool SPARSE = false>
 __global__ void __launch_bounds__(128) bwd_coop_kernel(const DevCtx cx, const LayoutDev ly, const BwdArgs ba) {
     constexpr int D = MD::D, NH = D * (D + 1) / 2, NG = NH + D, NAUX = D * D + D + NH, GPW = 32 / D;
     constexpr unsigned FULL = 0xffffffffu;
@@ -651,6 +652,7 @@ __global__ void __launch_bounds__(128) bwd_coop_kernel(const DevCtx cx, const La
             for (int q = 0; q < D; q++) {
 #pragma unroll
                 for (int j = 0; j < D; j++) {
+                    if (SPARSE && !JacMask<MD>::nz(q, j)) continue; // a structural zero of C (compile-time: q, j are unrolled)
                     const double cqj = blk[q * D + j];
                     Mx[j] = fma(Hr[q], cqj, Mx[j]); // (HC)_{rj}
                     if (j == q) trC += cqj;
@@ -752,14 +754,20 @@ __global__ void cache_extract_kernel(const DevCtx cx, const LayoutDev ly, int st
         }
     }
 }
-// the per-sweep K1 of a cached layout: F = F0 + Psi v for every tile of every non-terminal block
+// the per-sweep K1 of a cached layout: F = F0 + Psi v for every tile of every non-terminal block.
+// One thread = one (parameter set, observation interval): the test "did this block's end point move?" — six scalar loads — is made
+// once per interval and the thread then streams the interval's tiles.  (One thread per (parameter set, TILE) spent its time on that
+// test: 1.31 ms per C3 sweep whatever fraction of the blocks had moved, i.e. whatever it had to stream.)   grid (ceil(P/128), K, 2 stores)
 template <int D>
-__global__ void cache_apply_kernel(const DevCtx cx, const LayoutDev ly, int store, const int *k_of_t) {
+__global__ void cache_apply_kernel(const DevCtx cx, const LayoutDev ly) {
     constexpr int NH = D * (D + 1) / 2, NG = NH + D, NF = D + D * D;
-    const int ps = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y;
+    const int ps = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y, store = blockIdx.z;
     if (ps >= cx.P) return;
     int b;
-    if (!cache_tile_of(cx, ly, store, k_of_t[t], b) || ly.last[b]) return; // terminal block: no artificial observation
+    if (!cache_tile_of(cx, ly, store, k, b) || ly.last[b]) return; // terminal block: no artificial observation
+    const int t0 = store ? cx.ppb_tile0[k] : cx.tile0[k];
+    if (t0 < 0) return;
+    const int ntl = (cx.nsteps[k] + 3) >> 2;
     const size_t P = cx.P;
     const int kend = ly.i1[b];
     const int sv = cx.parP[1][(size_t)kend * P + ps];
@@ -771,19 +779,21 @@ __global__ void cache_apply_kernel(const DevCtx cx, const LayoutDev ly, int stor
         same = same && (v[mm] == ly.v_last[((size_t)b * D + mm) * P + ps]);
     }
     if (same) return;
-    double *gp = ly.Gl[store] + (((size_t)t * NG + NH) * P + ps) * 4;
-    const double *fp = ly.FP[store] + ((size_t)t * NF * P + ps) * 4;
+    double *gp = ly.Gl[store] + (((size_t)t0 * NG + NH) * P + ps) * 4;
+    const double *fp = ly.FP[store] + ((size_t)t0 * NF * P + ps) * 4;
+    for (int q = 0; q < ntl; q++, gp += (size_t)NG * P * 4, fp += (size_t)NF * P * 4) {
 #pragma unroll
-    for (int i = 0; i < D; i++) {
-        double f[4], p[4];
-        ld256(fp + (size_t)i * P * 4, f);
+        for (int i = 0; i < D; i++) {
+            double f[4], p[4];
+            ld256(fp + (size_t)i * P * 4, f);
 #pragma unroll
-        for (int mm = 0; mm < D; mm++) {
-            ld256(fp + (size_t)(D + i * D + mm) * P * 4, p);
+            for (int mm = 0; mm < D; mm++) {
+                ld256(fp + (size_t)(D + i * D + mm) * P * 4, p);
 #pragma unroll
-            for (int s = 0; s < 4; s++) f[s] = fma(p[s], v[mm], f[s]);
+                for (int s = 0; s < 4; s++) f[s] = fma(p[s], v[mm], f[s]);
+            }
+            st256(gp + (size_t)i * P * 4, f);
         }
-        st256(gp + (size_t)i * P * 4, f);
     }
 }
 // c at the block start of probe run `run` -> Crun[run][nb][P]

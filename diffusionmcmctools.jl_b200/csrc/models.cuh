@@ -309,4 +309,19 @@ template <> struct Model<M_OU2> {
     static __device__ bool bound_ok(const Par &, const double *) { return true; }
 };
 
+// ------------------------------------------------------------------------------------------- structural zeros of the Jacobian
+// When the auxiliary law is the device-side Jacobian linearisation of the target (dmt_set_aux_linearised), B has the Jacobian's sparsity
+// pattern, and the backward filter's d^3 product H (B - a H / 2) only needs the entries that can be non-zero.  nz(q, j): entry (q, j) of
+// C = B - atilde H / 2 may be non-zero (rows of C that carry noise are full: atilde H fills them).  Default: dense.
+template <class MD> struct JacMask {
+    static constexpr bool SPARSE = false;
+    static __host__ __device__ constexpr bool nz(int, int) { return true; }
+};
+template <> struct JacMask<Model<M_JR>> { // Jansen-Rit: x' = (x3, x4, x5, ...), three second-order blocks coupled through sigmoids; noise on row 4
+    static constexpr bool SPARSE = true;
+    static __host__ __device__ constexpr bool nz(int q, int j) {
+        return q == 4 || (q < 3 && j == q + 3) || (q == 3 && j <= 3) || (q == 5 && (j == 0 || j == 2 || j == 5));
+    }
+};
+
 } // namespace dmt

@@ -591,3 +591,29 @@ def test_tsit5_backward_filter_matches_the_oracle_twin(orc, olib, name, blocking
         H, F, c = ctx.get_guiding_term(k, 0, 1 if (blocking and k == 2) else 0)
         assert np.array_equal(F[:-1], rk4[k][1][:-1])
     ctx.close()
+
+
+@pytest.mark.own_lanes
+def test_jansen_rit_sparse_backward_filter_equals_the_dense_one(orc, olib):
+    """bwd_coop_kernel<JansenRit, SPARSE>: when every auxiliary law is the device-side Jacobian linearisation, B carries the Jacobian's
+    structural zeros and the d^3 product of the Riccati right-hand side skips them at compile time (JacMask, csrc/models.cuh).  Same
+    numbers as the dense product (the skipped terms are exact zeros) and as the oracle; a host-uploaded B (dmt_set_aux) switches the
+    context back to the dense kernel for good."""
+    import os
+    K = 5
+    prob = small_problem("jr", M=20, K=K, layouts=[([(0, K - 1)], 0.5)], seed=11, nsteps=12)
+    ctx = make_ctx(prob, seed=2)
+    ora = OracleEnsemble(orc, olib, prob, seed=2)
+    ctx.recompute_guiding_term(0, _lib.P_ONLY); ora.recompute_guiding_term(0)
+    sparse = [ctx.get_guiding_term(k, 0, 0) for k in range(K)]
+    for k in range(K):
+        compare_guiding(ctx, ora, k, 0, 0, tol=1e-10, tag="jr_sparse_k1")
+    os.environ["DMT_K1_DENSE"] = "1"
+    try:
+        ctx.recompute_guiding_term(0, _lib.P_ONLY)
+    finally:
+        del os.environ["DMT_K1_DENSE"]
+    for k in range(K):
+        H, F, c = ctx.get_guiding_term(k, 0, 0)
+        assert rel_err(H[:-1], sparse[k][0][:-1]) < 1e-13 and rel_err(F[:-1], sparse[k][1][:-1]) < 1e-13 and rel_err(c[:1], sparse[k][2][:1]) < 1e-13
+    ctx.close()
