@@ -402,18 +402,21 @@ template <class MD> bool launch_sweep_pipe(dmt_ctx *c, Layout &L, const FwdArgs 
     // it never won: 2.56 against 1.40 ms at 1024 chains.)  Mid-size ensembles — a doubled grid of the register-tile kernel still fits one
     // wave — go to that kernel with two lanes per (chain, block), which splits the generator: 1.35 against 1.40 ms at 1024 chains, 1.03
     // against 1.38 ms at 512 (profiles/r02_tuning.md).
-    constexpr int GW = MD::DW >= 2 ? 4 : 1; // the wide mapping exists for these models only
-    bool g4 = false;
+    constexpr int GW = MD::DW >= 2 ? 4 : 1; // the wide mappings exist for these models only
+    constexpr int G2 = MD::DW >= 2 ? 2 : 1;
+    bool g4 = false, g2 = false;
     if (c->fwd_lanes != 0) { // dmt_set_fwd_lanes together with dmt_set_sweep_mode(2): force the mapping
-        if (c->fwd_lanes != 1 && !(c->fwd_lanes == 4 && GW == 4))
-            throw DmtError(DMT_ERR_UNSUPPORTED, "the pipelined sweep maps 1 or (models with >= 2 Wiener coordinates) 4 lanes to a (chain, block)");
+        if (c->fwd_lanes != 1 && !((c->fwd_lanes == 4 || c->fwd_lanes == 2) && GW == 4))
+            throw DmtError(DMT_ERR_UNSUPPORTED, "the pipelined sweep maps 1 or (models with >= 2 Wiener coordinates) 2 or 4 lanes to a (chain, block)");
         g4 = c->fwd_lanes == 4;
+        g2 = c->fwd_lanes == 2;
     } else if (c->sweep_mode == 0 && MD::DW >= 2) {
         int w2 = 0;
         launch_fwd_lanes<MD, OP_SWEEP, false, 2>(c, L, fa, &w2);
         if ((size_t)c->M * L.nb * 2 <= (size_t)w2) return false;
     }
-    if (g4) launch_sweep_pipe_g<MD, GW>(c, L, fa, lazy);
+    if (g2) launch_sweep_pipe_g<MD, G2>(c, L, fa, lazy);
+    else if (g4) launch_sweep_pipe_g<MD, GW>(c, L, fa, lazy);
     else launch_sweep_pipe_g<MD, 1>(c, L, fa, lazy);
     if (lazy) c->W_stale_layout = L.dev.id;
     return true;
