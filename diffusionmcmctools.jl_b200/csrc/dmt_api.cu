@@ -528,7 +528,10 @@ void invalidate_caches(dmt_ctx *c) { // every caller is about to change the acce
 }
 void cache_apply(dmt_ctx *c, Layout &L) { // the per-sweep K1: F = F0 + Psi v ; c = c0 + q.v + v'Qv/2
     L.F_stale = false;
-    const dim3 g((c->P + 127) / 128, c->K, c->NTb > 0 ? 2 : 1);
+    int tiles_max = 1; // longest block, in tiles: ~24 tile groups per thread
+    for (int b = 0; b < L.nb; b++) tiles_max = std::max(tiles_max, c->tile0[L.i1[b] + 1] - c->tile0[L.i0[b]]);
+    const int Z = std::min(16, std::max(1, tiles_max / (FPG * 24)));
+    const dim3 g(((size_t)c->P * FPG + 127) / 128, L.nb, Z);
     DMT_D_SWITCH(c->D,
                  ++g_launches, cache_apply_kernel<DD><<<g, 128, 0, c->stream>>>(c->dev, L.dev);
                  ++g_launches, cache_apply_c_kernel<DD><<<pset_grid(c, L.nb, 128), 128, 0, c->stream>>>(c->dev, L.dev));
@@ -539,7 +542,7 @@ void cache_build(dmt_ctx *c, Layout &L) {
     const size_t nt[2] = {(size_t)c->NT, (size_t)std::max(c->NTb, 1)};
     for (int st = 0; st < 2; st++) {
         if (L.d_Gl[st].n != nt[st] * c->NG * P * 4) L.d_Gl[st].alloc(nt[st] * c->NG * P * 4);
-        if (L.d_FP[st].n != nt[st] * NF * P * 4) L.d_FP[st].alloc(nt[st] * NF * P * 4);
+        if (L.d_FP[st].n != fp_tiles_padded(nt[st]) * NF * P * 4) L.d_FP[st].alloc(fp_tiles_padded(nt[st]) * NF * P * 4);
         if (L.d_c0l[st].n != (size_t)c->K * P) L.d_c0l[st].alloc((size_t)c->K * P);
         L.dev.FP[st] = L.d_FP[st].p;
     }

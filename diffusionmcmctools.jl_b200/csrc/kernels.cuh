@@ -79,7 +79,7 @@ struct LayoutDev {
     double *Gl[2];     // [store] tiles like cx.G[slot][store]
     double *c0l[2];    // [store] [K][P]
     // guiding cache: (F, c) of a block are exactly affine / quadratic in the block's artificial end-point observation v
-    double *FP[2];     // [store] [tiles][D + D*D][P][4]: F0 (v = 0) then Psi[i][m] = dF_i/dv_m
+    double *FP[2];     // [store] [tiles / FPG][D + D*D][P][FPG][4]: F0 (v = 0) then Psi[i][m] = dF_i/dv_m  (fp_off below)
     double *cq;        // [nb][1 + D + NH][P]: c = c0 + q.v + v'Qv/2 at the block start
     double *v_last;    // [nb][D][P]: the artificial observation the private F, c were last materialised for
     const int *blk_of_k; // [K] block of this layout that contains interval k
@@ -724,6 +724,19 @@ __global__ void __launch_bounds__(128) bwd_coop_kernel(const DevCtx cx, const La
 // and the covariance-form start are affine in v).  So per layout we keep F0 = F(v=0), Psi = dF/dv and (c0, q, Q) of
 // c = c0 + q.v + v'Qv/2 — obtained by probing the unchanged bwd_kernel with v = 0, +-s e_m, s(e_m+e_n) — and a sweep's K1
 // becomes the streaming update F = F0 + Psi v (120 B per step instead of ~320 FP64 instructions per step).
+// Layout of F0, Psi.  cache_apply_kernel SKIPS whole (parameter set, block) pairs, so neighbouring parameter sets are streamed
+// independently of each other — and DRAM / L2 move 64-byte sector pairs: with one 32-byte sector per (tile, component, parameter set)
+// next to its NEIGHBOUR's sector, a moved block next to an unmoved one fetched both (measured, profiles/r02ag_summary.md: 7.1 GB read
+// where ~3.2 GB were needed).  So FPG consecutive tiles of ONE parameter set are stored next to each other: a lane owns a whole
+// 128-byte line per component and tile group, every fetched byte belongs to a block that moved.
+#ifndef DMT_FPG
+#define DMT_FPG 4
+#endif
+constexpr int FPG = DMT_FPG;
+__host__ __device__ __forceinline__ size_t fp_tiles_padded(size_t nt) { return (nt + FPG - 1) / FPG * FPG; }
+__device__ __forceinline__ size_t fp_off(int t, int comp, int NF, size_t P, int ps) { // doubles; the sector of (tile t, component, pset)
+    return ((((size_t)(t / FPG) * NF + comp) * P + ps) * FPG + (t % FPG)) * 4;
+}
 __device__ __forceinline__ bool cache_tile_of(const DevCtx &cx, const LayoutDev &ly, int store, int k, int &b) {
     b = ly.blk_of_k[k];
     const bool is_plast = (k == ly.i1[b]) && !ly.last[b]; // this interval's law comes from PPb in this layout
@@ -739,60 +752,107 @@ __global__ void cache_extract_kernel(const DevCtx cx, const LayoutDev ly, int st
     if (!cache_tile_of(cx, ly, store, k_of_t[t], b)) return;
     const size_t P = cx.P;
     const double *gp = ly.Gl[store] + (((size_t)t * NG + NH) * P + ps) * 4;
-    double *fp = ly.FP[store] + ((size_t)t * NF * P + ps) * 4;
+    double *fp = ly.FP[store];
 #pragma unroll
     for (int i = 0; i < D; i++) {
         double f[4], f0[4];
         ld256(gp + (size_t)i * P * 4, f);
         if (mode == 0) {
-            st256(fp + (size_t)i * P * 4, f);
+            st256(fp + fp_off(t, i, NF, P, ps), f);
         } else {
-            ld256(fp + (size_t)i * P * 4, f0);
+            ld256(fp + fp_off(t, i, NF, P, ps), f0);
 #pragma unroll
             for (int s = 0; s < 4; s++) f[s] = (f[s] - f0[s]) * inv_scale;
-            st256(fp + (size_t)(D + i * D + m) * P * 4, f);
+            st256(fp + fp_off(t, D + i * D + m, NF, P, ps), f);
         }
     }
 }
-// the per-sweep K1 of a cached layout: F = F0 + Psi v for every tile of every non-terminal block.
-// One thread = one (parameter set, observation interval): the test "did this block's end point move?" — six scalar loads — is made
-// once per interval and the thread then streams the interval's tiles.  (One thread per (parameter set, TILE) spent its time on that
-// test: 1.31 ms per C3 sweep whatever fraction of the blocks had moved, i.e. whatever it had to stream.)   grid (ceil(P/128), K, 2 stores)
+// the per-sweep K1 of a cached layout: F = F0 + Psi v for every tile of every non-terminal block whose end point moved.
+// A CTA owns (128 / FPG parameter sets, block, slice z of the block's tile groups).  Its first warp makes the test "did this block's end
+// point move?" once per parameter set and COMPACTS the ones that did (ballot + popc) into shared memory together with their v; the CTA's
+// threads then walk the flattened items (tile group, moved parameter set, tile of the group), so every warp runs with all lanes active
+// whatever fraction moved (ncu, profiles/r02ak_summary.md: with one static lane group per parameter set the pass reached the DRAM roof only
+// when ~85 % had moved — the bytes in flight scaled with the active lanes) and reads whole 128-byte lines of parameter sets that moved.
+// The block's intervals i0..i1-1 live in store 0, its last interval (the PPb law) in store 1.    grid (ceil(P * FPG / 128), nb, Z)
 template <int D>
-__global__ void cache_apply_kernel(const DevCtx cx, const LayoutDev ly) {
+__global__ void __launch_bounds__(128) cache_apply_kernel(const DevCtx cx, const LayoutDev ly) {
     constexpr int NH = D * (D + 1) / 2, NG = NH + D, NF = D + D * D;
-    const int ps = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y, store = blockIdx.z;
-    if (ps >= cx.P) return;
-    int b;
-    if (!cache_tile_of(cx, ly, store, k, b) || ly.last[b]) return; // terminal block: no artificial observation
-    const int t0 = store ? cx.ppb_tile0[k] : cx.tile0[k];
-    if (t0 < 0) return;
-    const int ntl = (cx.nsteps[k] + 3) >> 2;
+    constexpr int NPS = 128 / FPG; // parameter sets per CTA
+    static_assert(NPS <= 32 && NPS * FPG == 128, "one warp compacts the CTA's parameter sets");
+    __shared__ double vs[NPS][D];
+    __shared__ int psl[NPS];
+    __shared__ int n_moved;
+    const int b = blockIdx.y;
+    if (ly.last[b]) return; // terminal block: no artificial observation
     const size_t P = cx.P;
     const int kend = ly.i1[b];
-    const int sv = cx.parP[1][(size_t)kend * P + ps];
-    double v[D];
-    bool same = true; // the block's end point did not move (its last proposal in the other layout was rejected): F is current
-#pragma unroll
-    for (int mm = 0; mm < D; mm++) {
-        v[mm] = cx.vart[sv][((size_t)kend * D + mm) * P + ps];
-        same = same && (v[mm] == ly.v_last[((size_t)b * D + mm) * P + ps]);
-    }
-    if (same) return;
-    double *gp = ly.Gl[store] + (((size_t)t0 * NG + NH) * P + ps) * 4;
-    const double *fp = ly.FP[store] + ((size_t)t0 * NF * P + ps) * 4;
-    for (int q = 0; q < ntl; q++, gp += (size_t)NG * P * 4, fp += (size_t)NF * P * 4) {
-#pragma unroll
-        for (int i = 0; i < D; i++) {
-            double f[4], p[4];
-            ld256(fp + (size_t)i * P * 4, f);
+    if (threadIdx.x < 32) {
+        const int ps = blockIdx.x * NPS + threadIdx.x;
+        bool moved = false; // false: the end point did not move (the block's last proposal in the other layout was rejected), F is current
+        double v[D];
+        if (threadIdx.x < NPS && ps < cx.P) {
+            const int sv = cx.parP[1][(size_t)kend * P + ps];
 #pragma unroll
             for (int mm = 0; mm < D; mm++) {
-                ld256(fp + (size_t)(D + i * D + mm) * P * 4, p);
-#pragma unroll
-                for (int s = 0; s < 4; s++) f[s] = fma(p[s], v[mm], f[s]);
+                v[mm] = cx.vart[sv][((size_t)kend * D + mm) * P + ps];
+                moved = moved || !(v[mm] == ly.v_last[((size_t)b * D + mm) * P + ps]);
             }
-            st256(gp + (size_t)i * P * 4, f);
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, moved);
+        if (moved) {
+            const int j = __popc(mask & ((1u << threadIdx.x) - 1u));
+            psl[j] = ps;
+#pragma unroll
+            for (int mm = 0; mm < D; mm++) vs[j][mm] = v[mm];
+        }
+        if (threadIdx.x == 0) n_moved = __popc(mask);
+    }
+    __syncthreads();
+    const int nm = n_moved;
+    if (nm == 0) return;
+    const int per_g = nm * FPG; // items per tile group
+    constexpr size_t cstr = (size_t)FPG * 4; // component stride / P of the F0, Psi store
+    for (int store = 0; store < 2; store++) {
+        int ta, tb;
+        if (store == 0) { ta = cx.tile0[ly.i0[b]]; tb = cx.tile0[kend]; }
+        else {
+            ta = cx.ppb_tile0[kend];
+            if (ta < 0) continue;
+            tb = ta + ((cx.nsteps[kend] + 3) >> 2);
+        }
+        if (tb <= ta) continue;
+        const int g0 = ta / FPG, n_items = ((tb - 1) / FPG - g0 + 1) * per_g;
+        const double *fpb = ly.FP[store];
+        double *gpb = ly.Gl[store] + (size_t)NH * P * 4;
+        for (int id = (int)(blockIdx.z * 128 + threadIdx.x); id < n_items; id += 128 * (int)gridDim.z) {
+            const int g = id / per_g, r = id - g * per_g, j = r / FPG;
+            const int t = (g0 + g) * FPG + (r % FPG);
+            if (t < ta || t >= tb) continue;
+            const int ps = psl[j];
+            double v[D];
+#pragma unroll
+            for (int mm = 0; mm < D; mm++) v[mm] = vs[j][mm];
+            const double *fp = fpb + fp_off(t, 0, NF, P, ps);
+            double *gp = gpb + ((size_t)t * NG * P + ps) * 4;
+            constexpr int CB = D <= 3 ? D : 1; // components per batch: every load of a batch is in flight before the first FMA
+#pragma unroll
+            for (int i0 = 0; i0 < D; i0 += CB) {
+                double f[CB][4], p[CB][D][4];
+#pragma unroll
+                for (int i = 0; i < CB; i++) {
+                    ld256(fp + (size_t)(i0 + i) * P * cstr, f[i]);
+#pragma unroll
+                    for (int mm = 0; mm < D; mm++) ld256(fp + (size_t)(D + (i0 + i) * D + mm) * P * cstr, p[i][mm]);
+                }
+#pragma unroll
+                for (int i = 0; i < CB; i++) {
+#pragma unroll
+                    for (int mm = 0; mm < D; mm++)
+#pragma unroll
+                        for (int s = 0; s < 4; s++) f[i][s] = fma(p[i][mm][s], v[mm], f[i][s]);
+                    st256(gp + (size_t)(i0 + i) * P * 4, f[i]);
+                }
+            }
         }
     }
 }
