@@ -56,7 +56,7 @@ def parse():
     ap.add_argument("--one-call", action="store_true", help="blocking sweep through dmt_blocking_sweep (same launches; per-kernel timing is then not available)")
     ap.add_argument("--no-cache", action="store_true", help="blocking sweep with the full backward filter every sweep (no guiding cache)")
     ap.add_argument("--separate", action="store_true", help="blocking sweep with the three separate passes instead of the fused one")
-    ap.add_argument("--sweep-mode", type=int, default=0, help="fused pass: 0 auto (software-pipelined where eligible), 1 register-tile kernel, 2 pipelined")
+    ap.add_argument("--sweep-mode", type=int, default=0, help="fused pass: 0 auto, 1 register-tile kernel, 2 software-pipelined, 3 / 4 warp-specialised (wide / compact), 5 step-parallel (4 lanes per (chain, block))")
     ap.add_argument("--fwd-lanes", type=int, default=0, help="lanes per (chain, block) in the forward kernel (0: automatic)")
     ap.add_argument("--eager-noise", action="store_true", help="the sweep stores W_acc / W° (default: lazy noise, rebuilt from X on demand)")
     return ap.parse_args()

@@ -5,6 +5,7 @@
 #include "fwd_kernel.cuh"
 #include "sweep_kernel.cuh"
 #include "sweep_ws_kernel.cuh"
+#include "sweep_sp_kernel.cuh"
 #include "tsit5_kernel.cuh"
 
 #include <algorithm>
@@ -313,6 +314,11 @@ template <class MD, int G> void launch_sweep_pipe_g(dmt_ctx *c, Layout &L, const
 }
 // the warp-specialised sweep (sweep_ws_kernel.cuh): a pipeline of warps per group of 32 chains and block.  Two shapes: WsSmall for
 // ensembles that cannot fill the GPU (more helper warps around the one recursion warp, deep rings), WsLarge for full ones
+#ifndef DMT_SP_MAX_UNITS_DEFAULT
+#define DMT_SP_MAX_UNITS_DEFAULT 14080 // 1280 chains x 11 blocks.  Measured (Lorenz, lazy noise, fused pass in ms at 512 / 768 / 1024 / 1280 / 1536
+                                       // chains x 10 blocks; profiles/r02_tuning.md §4e): step-parallel 1.00 / 1.07 / 1.24 / 1.32 / 1.91, two lanes per
+                                       // (chain, block) in the register-tile kernel 1.03 / 1.05 / 1.35 / 1.37 / 1.39
+#endif
 #ifndef DMT_WS_NR // (tuning builds: -DDMT_WS_NR=.. -DDMT_WS_NSG=.. -DDMT_WS_NSR=..)
 #define DMT_WS_NR 6
 #endif
@@ -358,6 +364,13 @@ template <class MD, class SH, int MINB> void launch_sweep_ws(dmt_ctx *c, Layout 
     if (lazy) ++g_launches, sweep_ws_kernel<MD, true, SH, MINB><<<grid, SH::THREADS, smem, c->stream>>>(c->dev, L.dev, fa);
     else ++g_launches, sweep_ws_kernel<MD, false, SH, MINB><<<grid, SH::THREADS, smem, c->stream>>>(c->dev, L.dev, fa);
 }
+// the step-parallel sweep (sweep_sp_kernel.cuh): four lanes per (chain, block), lane = step of the tile
+template <class MD> void launch_sweep_sp(dmt_ctx *c, Layout &L, const FwdArgs &fa, bool lazy) {
+    const dim3 grid((unsigned)((c->M + 7) / 8), L.nb, 1);
+    snprintf(c->last_fwd_kernel, sizeof(c->last_fwd_kernel), "sweep_sp_kernel<step lanes=4%s>", lazy ? ", lazy" : "");
+    if (lazy) ++g_launches, sweep_sp_kernel<MD, true><<<grid, 32, 0, c->stream>>>(c->dev, L.dev, fa);
+    else ++g_launches, sweep_sp_kernel<MD, false><<<grid, 32, 0, c->stream>>>(c->dev, L.dev, fa);
+}
 // the software-pipelined sweep (sweep_kernel.cuh): one parameter set per chain in chain order, uniform law parity, device RNG
 template <class MD> bool launch_sweep_pipe(dmt_ctx *c, Layout &L, const FwdArgs &fa) {
     static int env_off = -1;
@@ -381,6 +394,13 @@ template <class MD> bool launch_sweep_pipe(dmt_ctx *c, Layout &L, const FwdArgs 
         static int ws_rounds = -1;
         if (ws_rounds < 0) { const char *e = getenv("DMT_WS_MAX_ROUNDS"); ws_rounds = e ? atoi(e) : 1; }
         const bool automatic = c->sweep_mode == 0 && c->fwd_lanes == 0;
+        static int sp_max_units = -1; // automatic: the step-parallel kernel while (chain, block) units <= this (0: never)
+        if (sp_max_units < 0) { const char *e = getenv("DMT_SP_MAX_UNITS"); sp_max_units = e ? atoi(e) : DMT_SP_MAX_UNITS_DEFAULT; }
+        if (c->sweep_mode == 5 || (automatic && MD::DW >= 2 && !(wave_w > 0 && units <= (size_t)ws_rounds * wave_w) && (size_t)c->M * L.nb <= (size_t)sp_max_units)) {
+            launch_sweep_sp<MD>(c, L, fa, lazy);
+            if (lazy) c->W_stale_layout = L.dev.id;
+            return true;
+        }
         if (c->sweep_mode == 4 && !CFITS) throw DmtError(DMT_ERR_UNSUPPORTED, "the compact warp-specialised sweep does not fit this model's state dimension");
         if (c->sweep_mode == 3 || (automatic && wave_w > 0 && units <= (size_t)ws_rounds * wave_w)) {
             launch_sweep_ws<MD, Wide, 1>(c, L, fa, lazy);
@@ -1528,7 +1548,7 @@ int32_t dmt_get_last_forward_kernel(dmt_ctx *ctx, char *buf, int32_t len) {
 }
 int32_t dmt_set_sweep_mode(dmt_ctx *ctx, int32_t mode) {
     return guarded(ctx, [&] {
-        if (mode < 0 || mode > 4) throw DmtError(DMT_ERR_ARG, "mode must be 0 (auto), 1 (register-tile kernel), 2 (software-pipelined kernel), 3 or 4 (warp-specialised kernel, wide / compact shape)");
+        if (mode < 0 || mode > 5) throw DmtError(DMT_ERR_ARG, "mode must be 0 (auto), 1 (register-tile kernel), 2 (software-pipelined kernel), 3 or 4 (warp-specialised kernel, wide / compact shape) or 5 (step-parallel kernel)");
         ctx->sweep_mode = mode;
     });
 }

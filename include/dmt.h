@@ -230,8 +230,11 @@ int32_t dmt_set_fwd_lanes(dmt_ctx *ctx, int32_t lanes);
  * DMT_ERR_UNSUPPORTED.  3 / 4 = warp-specialised kernel (sweep_ws_kernel.cuh: per group of 32 chains and block a CTA whose
  * warps form a pipeline — TMA producer, generator warps, inverse solve + accepted likelihood, the proposal's recursion, the proposal's
  * likelihood — over shared-memory rings) in its wide (16 warps, one CTA per SM) / compact (8 warps, two per SM) shape, under the same
- * conditions, or DMT_ERR_UNSUPPORTED.  Automatic: warp-specialised while the grid of (32 chains, block) units fits one round of CTAs,
- * then two lanes per (chain, block) in the register-tile kernel while that grid fits one wave, then the pipelined kernel.  Same arithmetic, results equal up to FP64 rounding (different FMA contraction). */
+ * conditions, or DMT_ERR_UNSUPPORTED.  5 = step-parallel kernel (sweep_sp_kernel.cuh: four lanes per (chain, block), lane s owns step s of every
+ * 4-step tile; only the proposal's recursion runs as four rounds with a shuffle broadcast), same conditions, or DMT_ERR_UNSUPPORTED.
+ * Automatic: warp-specialised while the grid of (32 chains, block) units fits one round of CTAs, then (models with >= 2 Wiener coordinates)
+ * step-parallel up to 14,080 (chain, block) units, then two lanes per (chain, block) in the register-tile kernel while that grid fits one
+ * wave, then the pipelined kernel.  Same arithmetic, results equal up to FP64 rounding (different FMA contraction). */
 int32_t dmt_set_sweep_mode(dmt_ctx *ctx, int32_t mode);
 /* Diagnostics: name and thread mapping of the forward kernel (K2-K5) this context launched last, e.g. "sweep_ws_kernel<lazy>",
  * "sweep_pipe_kernel<lanes=1, lazy>", "fwd_kernel<op=6, lanes=4>" — what a benchmark should print instead of guessing the automatic

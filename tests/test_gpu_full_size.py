@@ -182,12 +182,13 @@ def test_other_baseline_configs_at_full_size(cfg, orc, olib):
 
 # ---- the configuration bench.py measures: lazy noise + guiding cache, at the per-GPU sizes of the 1 / 8 / 16-GPU splits ---------------
 @pytest.mark.parametrize("chains,lo,kernel", [(4096, 0, "sweep_pipe_kernel<lanes=1, lazy>"),            # 1 GPU
-                                              (512, 1536, "fwd_kernel<op=6, lanes=2, lazy>"),           # rank 3 of 8
+                                              (1536, 1536, "fwd_kernel<op=6, lanes=2, lazy>"),          # (a 3-GPU-like shard: two lanes per (chain, block))
+                                              (512, 1536, "sweep_sp_kernel<step lanes=4, lazy>"),       # rank 3 of 8: step-parallel lanes
                                               (256, 3840, "sweep_ws_kernel<wide, lazy>")])              # rank 15 of 16: one round of CTAs
 def test_bench_configuration_slice_replay(chains, lo, kernel, orc, olib):
     """C3 exactly as bench.py runs it (lazy noise, guiding cache, automatic kernel choice) on the slice of the 4096-chain ensemble a rank of
     an N-GPU job holds: three sweeps per layout with accept steps; three chains of the slice — global Philox counters — are replayed call by
-    call on the oracle.  Also pins WHICH kernel the automatic choice takes at each size, so all three fused-pass kernels meet the oracle at
+    call on the oracle.  Also pins WHICH kernel the automatic choice takes at each size, so all four fused-pass kernels meet the oracle at
     BASELINE scale."""
     prob = configs.named_config("c3", M=chains, seed=123, chain_offset=lo)          # the rank's slice of the ensemble's synthetic data
     if chains == 512:                                                               # (checked once: a shard IS a slice of the unsharded data)

@@ -32,17 +32,18 @@ def start(prob, seed=31, **kw):
 
 @pytest.mark.parametrize("name", NAMES)
 @pytest.mark.parametrize("M", [41, 64, 7])
-@pytest.mark.parametrize("lanes", [1, 4, "ws", "ws_compact"])
+@pytest.mark.parametrize("lanes", [1, 4, "ws", "ws_compact", "sp"])
 def test_pipelined_sweep_equals_register_tile_sweep(name, M, lanes):
     """same inputs, same random stream, same arithmetic: equal up to FP64 rounding (different FMA contraction), decisions equal;
     with one lane per (chain, block), with four (the lanes split the generator calls), and with the warp-specialised kernel
     (csrc/sweep_ws_kernel.cuh: generator, inverse solve, proposal recursion and proposal likelihood on different warps, coupled by
-    shared-memory rings) in both of its shapes (16 warps, one CTA per SM; 8 warps, two per SM)"""
+    shared-memory rings) in both of its shapes (16 warps, one CTA per SM; 8 warps, two per SM), and with the step-parallel kernel
+    (csrc/sweep_sp_kernel.cuh: four lanes per (chain, block), lane = step of the tile; ll and ll° summed in a different order)"""
     prob = problem(name, M)
     a, b = start(prob), start(prob)
     a.set_sweep_mode(1)
     if isinstance(lanes, str):
-        b.set_sweep_mode(3 if lanes == "ws" else 4)
+        b.set_sweep_mode({"ws": 3, "ws_compact": 4, "sp": 5}[lanes])
     else:
         b.set_sweep_mode(2); b.set_fwd_lanes(lanes)
     if lanes == "ws_compact" and prob.d > 3:
@@ -86,14 +87,16 @@ def test_pipelined_sweep_refuses_what_it_cannot_do():
     ctx.set_sweep_mode(0)
     ctx.find_W_loglikhd_draw(0, 1)                  # automatic: falls back to the register-tile kernel (another CUDA kernel, not a CPU path)
     with pytest.raises(dmt_b200.DmtError):
-        ctx.set_sweep_mode(5)
+        ctx.set_sweep_mode(6)
     with pytest.raises(dmt_b200.DmtError):
         ctx.set_sweep_mode(3); ctx.find_W_loglikhd_draw(0, 1)
+    with pytest.raises(dmt_b200.DmtError):
+        ctx.set_sweep_mode(5); ctx.find_W_loglikhd_draw(0, 1)
     ctx.close()
 
 
 @pytest.mark.parametrize("name", ["lorenz", "fhn", "prok"])
-@pytest.mark.parametrize("mode", [1, 2, 3, 4])
+@pytest.mark.parametrize("mode", [1, 2, 3, 4, 5])
 def test_lazy_noise_changes_nothing_but_the_moment_W_is_computed(name, mode):
     """dmt_set_lazy_noise: the sweep stops storing W_acc / W°; paths, log-likelihoods and decisions are unchanged, and the accepted
     noise read back later is K5 of the accepted path under the law swept last — what find_W_for_X! returns."""
