@@ -315,9 +315,9 @@ template <class MD, int G> void launch_sweep_pipe_g(dmt_ctx *c, Layout &L, const
 // the warp-specialised sweep (sweep_ws_kernel.cuh): a pipeline of warps per group of 32 chains and block.  Two shapes: WsSmall for
 // ensembles that cannot fill the GPU (more helper warps around the one recursion warp, deep rings), WsLarge for full ones
 #ifndef DMT_SP_MAX_UNITS_DEFAULT
-#define DMT_SP_MAX_UNITS_DEFAULT 14080 // 1280 chains x 11 blocks.  Measured (Lorenz, lazy noise, fused pass in ms at 512 / 768 / 1024 / 1280 / 1536
-                                       // chains x 10 blocks; profiles/r02_tuning.md §4e): step-parallel 1.00 / 1.07 / 1.24 / 1.32 / 1.91, two lanes per
-                                       // (chain, block) in the register-tile kernel 1.03 / 1.05 / 1.35 / 1.37 / 1.39
+#define DMT_SP_MAX_UNITS_DEFAULT 14080 // 1280 chains x 11 blocks (12 resident warps per SM at 168 registers).  Measured (Lorenz, lazy noise, fused
+                                       // pass in ms at 512 / 1024 / 1280 chains x 10 blocks; profiles/r02_tuning.md §4e): step-parallel 0.83 / 1.10 /
+                                       // 1.18, two lanes per (chain, block) in the register-tile kernel 1.03 / 1.35 / 1.37
 #endif
 #ifndef DMT_WS_NR // (tuning builds: -DDMT_WS_NR=.. -DDMT_WS_NSG=.. -DDMT_WS_NSR=..)
 #define DMT_WS_NR 6

@@ -18,6 +18,7 @@
 // A warp holds 8 chains; everything is warp-uniform (lanes beyond the ensemble shadow the last chain and never store).
 #pragma once
 #include "fwd_kernel.cuh"
+#include <type_traits>
 
 namespace dmt {
 
@@ -27,6 +28,14 @@ __device__ __forceinline__ double ld64s(const double *p) { // streaming 8-byte e
     return v;
 }
 __device__ __forceinline__ double shfl4(double v, int src) { return __shfl_sync(0xffffffffu, v, src, 4); }
+// v[s] for a lane-dependent s in 0..3 as two levels of selects (a chain of `s == 0 ? .. : s == 1 ? ..` became three divergent branch
+// regions per tile: 8 % of the stall samples, profiles/r02an_summary.md)
+__device__ __forceinline__ double sel4(int s, double a, double b, double c, double d) {
+    const bool b0 = (s & 1) != 0, b1 = (s & 2) != 0;
+    const int lo0 = b0 ? __double2loint(b) : __double2loint(a), hi0 = b0 ? __double2hiint(b) : __double2hiint(a);
+    const int lo1 = b0 ? __double2loint(d) : __double2loint(c), hi1 = b0 ? __double2hiint(d) : __double2hiint(c);
+    return __hiloint2double(b1 ? hi1 : hi0, b1 ? lo1 : lo0);
+}
 
 template <class MD, bool LAZYW>
 __global__ void __launch_bounds__(32) sweep_sp_kernel(const DevCtx cx, const LayoutDev ly, const FwdArgs fa) {
@@ -76,6 +85,18 @@ __global__ void __launch_bounds__(32) sweep_sp_kernel(const DevCtx cx, const Lay
     }
     double ll = 0.0, llo = 0.0; // this lane's partial sums
     bool ok = true;
+    {   // loglikhd_obs(PP[1], y1) = -c - y'Hy/2 + F'y  (src/block.jl:178): lane 0 holds H, F at the block's first grid point (the prefetched tile 0)
+        double s0 = -*g_tile_of<NG>(cx, ly, i0, i1, last, 0, ps).c0;
+#pragma unroll
+        for (int i = 0; i < D; i++) {
+            double hx = 0.0;
+#pragma unroll
+            for (int j = 0; j < D; j++) hx = fma(gN[sidx<D>(i, j)], xa[j], hx);
+            s0 += xa[i] * (gN[NH + i] - 0.5 * hx);
+        }
+        ll = s == 0 ? s0 : 0.0;
+        llo = ll; // same law, same start point
+    }
 
     for (int k = i0; k <= i1; ++k) {
         const GTile<NG> gt = g_tile_of<NG>(cx, ly, k, i1, last, 0, ps);
@@ -128,7 +149,7 @@ __global__ void __launch_bounds__(32) sweep_sp_kernel(const DevCtx cx, const Lay
                 double z[4 * DW];
                 tile_normals_coop<DW, 4>(cx.seed, cx.chain_offset + (uint32_t)c, (uint32_t)(t0 + q), fa.iter, (uint32_t)ly.id, s, z);
 #pragma unroll
-                for (int j = 0; j < DW; j++) zs[j] = s == 0 ? z[j] : s == 1 ? z[DW + j] : s == 2 ? z[2 * DW + j] : z[3 * DW + j];
+                for (int j = 0; j < DW; j++) zs[j] = sel4(s, z[j], z[DW + j], z[2 * DW + j], z[3 * DW + j]);
             }
             const bool mine = 4 * q + s < nst; // this lane's step exists (false only in the padding of an interval's last tile)
             const double *Hs = g, *F = g + NH;
@@ -143,33 +164,21 @@ __global__ void __launch_bounds__(32) sweep_sp_kernel(const DevCtx cx, const Lay
 #pragma unroll
             for (int i = 0; i < D; i++) xa[i] = shfl4(xt[i], 3); // (padding steps of a last tile: unused, the next interval reloads xa)
 
-            if (k == i0 && q == 0 && s == 0) { // loglikhd_obs(PP[1], y1) = -c - y'Hy/2 + F'y  (src/block.jl:178)
-                double s0 = -*gt.c0;
-#pragma unroll
-                for (int i = 0; i < D; i++) {
-                    double hx = 0.0;
-#pragma unroll
-                    for (int j = 0; j < D; j++) hx = fma(Hs[sidx<D>(i, j)], xl[j], hx);
-                    s0 += xl[i] * (F[i] - 0.5 * hx);
-                }
-                ll = s0;
-                llo = s0; // same law, same start point
-            }
-
             // ---- K4 on the accepted path, K5, K3 — step s, all four steps of the tile at once
             double dwo[DW];
             {
                 double gd[D], G = 0.0, res[D], dwv[DW];
                 const typename MD::Diff df(par, xl);
                 guided_terms<MD, true>(par, df, Bm, beta, at, Hs, F, xl, gd, G);
-                if (mine) ll = fma(G, dt, ll);
+                ll = mine ? fma(G, dt, ll) : ll;
 #pragma unroll
                 for (int a = 0; a < D; a++) res[a] = xt[a] - xl[a] - gd[a] * dt; // K5: dW = sigma^+ (x' - x - (b + a r) dt)   (A.5)
                 df.inv_sig(res, dwv);
 #pragma unroll
                 for (int j = 0; j < DW; j++) { // K3: dW° = rho dW + sqrt(1-rho^2) sqrt(dt) xi   (A.2)
-                    dwo[j] = rho * dwv[j] + crho * sq * zs[j];
-                    if (!mine) { dwv[j] = 0.0; dwo[j] = 0.0; }
+                    const double wj = rho * dwv[j] + crho * sq * zs[j];
+                    dwo[j] = mine ? wj : 0.0;
+                    dwv[j] = mine ? dwv[j] : 0.0;
                 }
                 if (!LAZYW && live) {
 #pragma unroll
@@ -185,32 +194,40 @@ __global__ void __launch_bounds__(32) sweep_sp_kernel(const DevCtx cx, const Lay
             double xmine[D], xleft[D];
 #pragma unroll
             for (int a = 0; a < D; a++) { xmine[a] = 0.0; xleft[a] = xo[a]; }
+            auto rounds = [&](auto full_c) { // FULL (every step of the tile exists): the four rounds form one basic block
+                constexpr bool FULL = decltype(full_c)::value;
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if (4 * q + u < nst) { // warp-uniform: every chain shares the time grid
+                for (int u = 0; u < 4; u++) {
+                if (FULL || 4 * q + u < nst) { // warp-uniform: every chain shares the time grid
                     double gdo[D], Gu = 0.0, swo[D], xon[D];
                     const typename MD::Diff dfo(par, xo);
                     guided_terms<MD, false>(par, dfo, Bm, beta, at, Hs, F, xo, gdo, Gu);
                     dfo.sig_mul(dwo, swo);
 #pragma unroll
                     for (int a = 0; a < D; a++) xon[a] = fma(gdo[a], dt, xo[a]) + swo[a];
-                    if (s == u) {
-                        bool fin = dfo.ok();
+                    bool fin = dfo.ok();
 #pragma unroll
-                        for (int a = 0; a < D; a++) fin = fin && isfinite(xon[a]);
-                        ok = ok && fin && MD::bound_ok(par, xon); // src/block.jl:181 (ll° := -Inf once, after the loop)
+                    for (int a = 0; a < D; a++) fin = fin && isfinite(xon[a]);
+                    fin = fin && MD::bound_ok(par, xon); // src/block.jl:181 (ll° := -Inf once, after the loop)
+                    const bool own = s == u;             // selects, not a divergent branch
+                    ok = own ? (ok && fin) : ok;
 #pragma unroll
-                        for (int a = 0; a < D; a++) { xmine[a] = xon[a]; xleft[a] = xo[a]; }
+                    for (int a = 0; a < D; a++) {
+                        xmine[a] = own ? xon[a] : xmine[a];
+                        xleft[a] = own ? xo[a] : xleft[a];
                     }
 #pragma unroll
                     for (int a = 0; a < D; a++) xo[a] = shfl4(xon[a], u);
                 }
             }
+            };
+            if (4 * q + 4 <= nst) rounds(std::true_type{});
+            else rounds(std::false_type{});
             {   // K4 on the proposal, step s
                 double gdo[D], Go = 0.0;
                 const typename MD::Diff dfo(par, xleft);
                 guided_terms<MD, true>(par, dfo, Bm, beta, at, Hs, F, xleft, gdo, Go);
-                if (mine) llo = fma(Go, dt, llo);
+                llo = mine ? fma(Go, dt, llo) : llo;
             }
             if (live) {
 #pragma unroll
