@@ -32,6 +32,14 @@ template <int N, int I = 0, class F> __device__ __forceinline__ void static_for(
     }
 }
 
+// One lane of a converged warp, chosen by the hardware (elect.sync).  With `if (lane == 0)` ptxas cannot know that a single lane is active and
+// wraps EVERY bulk copy — a uniform-datapath instruction — in its own elect-one loop (R2UR ... ELECT ... BRA.U.ANY, ~12 instructions per copy,
+// 11 copies per tile); behind elect.sync the operands are uniform by construction.
+__device__ __forceinline__ bool elect_one_lane() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
 template <class MD> constexpr int sweep_pipe_minb() { return MD::D <= 3 ? 10 : 1; } // 10 warps per SM at <= 200 registers: C3 in one wave
 
 template <class MD> constexpr size_t sweep_pipe_smem() {
@@ -80,7 +88,11 @@ __global__ void __launch_bounds__(32, sweep_pipe_minb<MD>()) sweep_pipe_kernel(c
     double xnx[D][4];
     auto prefetch = [&]() { // issue every load of tile (kn, qn), then advance the cursor
         if (!more) return;
+#ifdef DMT_SW_LANE0_ISSUE
         if (lane == 0) {
+#else
+        if (elect_one_lane()) {
+#endif
             uint64_t *bar = &bars[n_prod & 1];
             double *dst = ring + (size_t)(n_prod & 1) * STAGE;
             mbar_expect_tx(bar, NG * chunk_bytes + 64u);
